@@ -1,0 +1,179 @@
+/*
+ * neunet_b200.h -- C-ABI of libneunet_b200.so: the B200-native (sm_100a) dense forward/backward
+ * hot path of AkiRusProd/numpy-nn-model ("neunet").
+ *
+ * This is the boundary a maintainer of the reference binds with ctypes.
+ * It follows the conventions of the reference's own native plug-ins (neunet/nn/experimental):
+ *   - plain `extern "C"` functions, raw DEVICE pointers, C-contiguous fp32 unless stated,
+ *     the caller allocates every input, output and scratch buffer
+ *     (reference: experimental/utils.py:64-85, experimental/linear/linear.py:126-150,184-212);
+ *   - outputs are overwritten, never accumulated (accumulation stays in Tensor.apply_grad,
+ *     neunet/autograd.py:85-93);
+ *   - trailing `cudaStream_t` like cudaLinearSwishForward / FusedAdamWStep.
+ * Deliberate fixes over the reference ABI: every function returns an int status instead of
+ * printf+exit (linear_cublaslt_no_manual_mem.cu:91-94), dims are int64_t (the reference declares
+ * `int` in C and c_size_t in Python, experimental/linear/linear.py:38-65), and all symbols carry a
+ * unique `nnb_` prefix (the reference's .so files export clashing names under RTLD_GLOBAL).
+ *
+ * Numerics: tensor-core contractions take bf16 operands with fp32 accumulation.
+ *   NNB_PREC_BF16    one bf16 product            (~2e-3 rel. vs fp32; throughput mode)
+ *   NNB_PREC_BF16X3  x = hi + lo split, hi*hi + hi*lo + lo*hi  (~1e-5 rel.; parity mode)
+ * Everything that is not a contraction (epilogues, normalisation, optimizer) is fp32.
+ */
+#ifndef NEUNET_B200_H
+#define NEUNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* status codes */
+#define NNB_OK 0
+#define NNB_ERR_INVALID 1     /* bad argument (null pointer, non-positive dim, misaligned buffer) */
+#define NNB_ERR_CUDA 2        /* a CUDA runtime/driver call failed */
+#define NNB_ERR_WORKSPACE 3   /* workspace too small; call the matching *_workspace_bytes() */
+#define NNB_ERR_UNSUPPORTED 4 /* shape/option outside what the kernels implement (never a CPU fallback) */
+
+#define NNB_PREC_BF16 0
+#define NNB_PREC_BF16X3 1
+
+#define NNB_ACT_NONE 0
+#define NNB_ACT_SWISH 1 /* x * sigmoid(beta * x), neunet/nn/activations.py:221-233 */
+
+#define NNB_OPT_ADAM_L2 0 /* grad += wd * p          (neunet/optim.py:24-25) */
+#define NNB_OPT_ADAMW 1   /* p -= lr * wd * p first  (neunet/optim.py:59-60) */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* nnb_last_error(void);
+int nnb_version(void);
+/* Fails with NNB_ERR_UNSUPPORTED unless the current device is compute capability 10.x. */
+int nnb_device_check(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernels this library has launched since the last reset (bench.py's `gpu_launches`). */
+uint64_t nnb_launch_count(void);
+void nnb_launch_count_reset(void);
+
+/* ---- nn.Linear ------------------------------------------------------------------------------
+ * Replaces cudaLinearModuleForward / cudaLinearModuleBackward
+ * (neunet/nn/experimental/linear/linear_cublaslt_no_manual_mem.cu:114-140, 142-184) and the fused
+ * cudaLinearSwishForward / cudaLinearSwishBackward
+ * (neunet/nn/experimental/linear_swish/linear_swish_cutlass_evt_full.cu:558-663, 680-818).
+ * Semantics are those of neunet/nn/layers/linear.py:17-24,48-58:
+ *   O[M,N] = act(X[M,K] . W[N,K]^T + bias[N])         Z (optional) receives the pre-activation
+ *   dX[M,K] = dZ . W      dW[N,K] = dZ^T . X      db[N] = sum_rows dZ,
+ *   with dZ = dO (act NONE) or dO * swish'(Z) (act SWISH; Z must be the saved pre-activation).
+ * bias, Z, dX, db may be NULL (dX NULL skips the dgrad GEMM).
+ * W_staged: NULL, or a buffer filled by nnb_stage_weight() for the CURRENT contents of W
+ * (lets the caller convert weights to bf16 once per optimizer step instead of once per call).
+ */
+size_t nnb_linear_workspace_bytes(int64_t M, int64_t K, int64_t N, int prec, int backward);
+int nnb_linear_forward(const float* X, const float* W, const float* bias, float* O, float* Z,
+                       int64_t M, int64_t K, int64_t N, int act, float beta, int prec,
+                       const void* W_staged, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
+int nnb_linear_backward(const float* X, const float* W, const float* Z, const float* dO,
+                        float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
+                        float beta, int prec, const void* W_staged, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+size_t nnb_weight_staged_bytes(int64_t rows, int64_t cols, int prec);
+int nnb_stage_weight(const float* W, int64_t rows, int64_t cols, int prec, void* dst,
+                     cudaStream_t stream);
+
+/* ---- Tensor.matmul --------------------------------------------------------------------------
+ * The reference has no native matmul entry point (neunet/autograd.py:192-230 calls xp.matmul);
+ * this one is defined in the same style. Operands are 4-D strided fp32 views
+ * A[b0,b1,M,K], B[b0,b1,K,N] given by ELEMENT strides {s_b0, s_b1, s_row, s_col} (0 = broadcast,
+ * transposed views allowed); C / dA / dB are C-contiguous [b0,b1,M,N] / [b0,b1,M,K] / [b0,b1,K,N].
+ *   forward : C  = alpha * A . B
+ *   backward: dA = alpha * G . B^T   (autograd.py:209)     dB = alpha * A^T . G   (autograd.py:211)
+ * dA or dB may be NULL. Un-broadcasting a gradient stays in Tensor._reverse_broadcast.
+ */
+size_t nnb_matmul_workspace_bytes(int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N,
+                                  int prec, int backward);
+int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* B,
+                       const int64_t b_strides[4], float* C, int64_t b0, int64_t b1, int64_t M,
+                       int64_t K, int64_t N, float alpha, int prec, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+int nnb_matmul_backward(const float* A, const int64_t a_strides[4], const float* B,
+                        const int64_t b_strides[4], const float* G, float* dA, float* dB,
+                        int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N, float alpha,
+                        int prec, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- nn.Conv2d ------------------------------------------------------------------------------
+ * NCHW cross-correlation exactly as neunet/nn/layers/conv2d.py:297-355 (forward) and 16-117
+ * (backward): X[B,Cin,H,W], Wt[Cout,Cin,kh,kw], bias[Cout] or NULL, O[B,Cout,Ho,Wo] with
+ * Ho = (H + pad[0] + pad[1] - dil[0]*(kh-1) - 1) / stride[0] + 1 (conv2d.py:246-260);
+ * pad = {top, bottom, left, right} (the 4-tuple Conv2d.build() produces, conv2d.py:237-243).
+ * The reference has no native conv entry point. dX or db may be NULL.
+ */
+typedef struct nnb_conv2d_desc {
+    int64_t B, Cin, H, W, Cout, kh, kw;
+    int32_t stride[2];
+    int32_t pad[4];
+    int32_t dil[2];
+} nnb_conv2d_desc;
+int nnb_conv2d_out_shape(const nnb_conv2d_desc* d, int64_t* Ho, int64_t* Wo);
+size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backward);
+int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* bias,
+                       float* O, int prec, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
+int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* dO,
+                        float* dX, float* dW, float* db, int prec, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- epilogue ops as standalone kernels (same maths as the fused forms) ----------------------
+ * Swish: cudaSwishForward/Backward (experimental/activations/swish/swish.cu:14-80),
+ *        semantics neunet/nn/activations.py:208-233.
+ * Softmax over the middle axis of a [outer, n, inner] view: cudaSoftmaxForward/Backward
+ *        (experimental/activations/softmax/softmax.cu:144-151, 229-237), activations.py:437-459.
+ *        mask (optional, forward only): int32 [outer, n, inner]-broadcastable via mask_outer_div:
+ *        rows with mask==0 get -1e9 before the softmax and `scale` multiplies the input first
+ *        (the GPT example's where(mask==0,-1e9) + /sqrt(d), examples/gpt.ipynb cell 2).
+ * RMSNorm: RMSNormForward/Backward (experimental/rmsnorm/rmsnorm.cu:116-140, 282-308),
+ *        semantics neunet/nn/layers/rmsnorm.py:39-94. dw/db are full column sums over rows.
+ */
+int nnb_swish_forward(const float* x, float* y, int64_t n, float beta, cudaStream_t stream);
+int nnb_swish_backward(const float* x, const float* grad, float* dx, int64_t n, float beta,
+                       cudaStream_t stream);
+int nnb_softmax_forward(const float* x, float* y, int64_t outer, int64_t n, int64_t inner,
+                        cudaStream_t stream);
+int nnb_softmax_backward(const float* y, const float* grad, float* dx, int64_t outer, int64_t n,
+                         int64_t inner, cudaStream_t stream);
+int nnb_rmsnorm_forward(const float* X, const float* w, const float* b, float* Y, float* X_std,
+                        float* X_norm, int64_t rows, int64_t cols, float eps, cudaStream_t stream);
+size_t nnb_rmsnorm_workspace_bytes(int64_t rows, int64_t cols);
+int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const float* X_std,
+                         const float* X_norm, float* dX, float* dw, float* db, int64_t rows,
+                         int64_t cols, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+
+/* ---- multi-tensor Adam / AdamW ---------------------------------------------------------------
+ * Replaces the per-tensor Python loops of neunet/optim.py:17-33 (Adam) and 52-69 (AdamW) and the
+ * reference's CreateFusedOptimizer / FusedAdamWStep / DestroyFusedOptimizer
+ * (experimental/optim/fused_adamw/fused_adamw_multitensor.cu:306-340).
+ * nnb_adamw_create uploads the pointer table ONCE (the reference re-uploads it every step,
+ * fused_adamw_multitensor.cu:288-291); p/g/m/v are arrays of n device pointers, sizes in elements.
+ * Tensors whose g[i] is NULL are skipped, like `if param.grad is None: continue` (optim.py:21-22).
+ * step: 1-based step count t; bias corrections 1-beta^t are computed in double on the host, as the
+ * reference does in Python floats. grad_scale multiplies every gradient first (1/world_size after
+ * a sum all-reduce; 1.0 otherwise).
+ */
+typedef struct nnb_adamw nnb_adamw;
+int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const* g,
+                     float* const* m, float* const* v, const int64_t* sizes, cudaStream_t stream);
+int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stream);
+int nnb_adamw_step(nnb_adamw* opt, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int64_t step, int mode, float grad_scale,
+                   cudaStream_t stream);
+int nnb_adamw_destroy(nnb_adamw* opt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUNET_B200_H */

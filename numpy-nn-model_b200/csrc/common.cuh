@@ -1,0 +1,124 @@
+// Shared host/device declarations for libneunet_b200 (internal; the public C-ABI is include/neunet_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/neunet_b200.h"
+
+namespace nnb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+// The reference's native modules printf+exit() on failure (linear_cublaslt_no_manual_mem.cu:91-94);
+// here every entry point returns an int status and keeps the message for nnb_last_error().
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define NNB_CUDA_OK(expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::nnb::fail(NNB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    } while (0)
+
+#define NNB_REQUIRE(cond, ...)                                         \
+    do {                                                               \
+        if (!(cond)) return ::nnb::fail(NNB_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// Kernel-launch accounting (bench.py reports `gpu_launches`).
+void count_launch(int n = 1);
+
+int num_sms();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- staged bf16 operands ---------------------------------------------------------------------
+// The fp32 tensors the reference API hands us are converted once per use ("staged") into bf16
+// planes that TMA can tile: `hi` = bf16(x) and, in BF16X3 mode, `lo` = bf16(x - hi).
+// A staged matrix is row-major [batch][rows][ld] with ld = round_up(cols, 8) so the row pitch is a
+// multiple of 16 bytes (TMA requirement), and every plane starts 256-byte aligned.
+struct Staged {
+    const __nv_bfloat16* hi = nullptr;
+    const __nv_bfloat16* lo = nullptr;  // null in BF16 mode
+    int64_t rows = 0, cols = 0, ld = 0;
+    int64_t batch = 1;
+    int64_t batch_stride = 0;  // elements
+};
+
+static inline int64_t staged_ld(int64_t cols) { return round_up(cols, 8); }
+static inline size_t staged_plane_bytes(int64_t batch, int64_t rows, int64_t cols) {
+    return (size_t)round_up(batch * rows * staged_ld(cols) * 2, 256);
+}
+
+// 4-D strided fp32 view -> staged bf16 planes (optionally transposing the last two dims).
+// view dims: [b0][b1][rows][cols] with element strides s_b0, s_b1, s_r, s_c.
+struct View4 {
+    const float* ptr;
+    int64_t b0, b1, rows, cols;
+    int64_t s_b0, s_b1, s_r, s_c;
+};
+static inline View4 view2d(const float* p, int64_t rows, int64_t cols, int64_t ld) {
+    return View4{p, 1, 1, rows, cols, 0, 0, ld, 1};
+}
+
+// Elementwise transform fused into staging.
+enum StageOp {
+    STAGE_COPY = 0,
+    STAGE_SWISH_BWD = 1,  // out = src * swish'(aux)  (aux = saved pre-activation z, same shape/strides)
+};
+
+size_t stage_colsum_scratch_bytes(int64_t cols);
+
+// dst planes must hold staged_plane_bytes() each. If `colsum` is non-null it receives
+// sum over (batch, rows) of the *transformed fp32* values per column (bias gradient), length cols.
+int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst_hi,
+                  __nv_bfloat16* dst_lo, int op, const float* aux, float beta, float* colsum,
+                  float* colsum_scratch, cudaStream_t stream, Staged* out);
+
+// ---- GEMM ---------------------------------------------------------------------------------------
+// D[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )
+// A "K-major" operand is staged as [rows = M or N][cols = K]; an "MN-major" operand is staged as
+// [rows = K][cols = M or N] (i.e. the untransposed matrix when the reduction runs over its rows).
+struct GemmOperand {
+    Staged st;
+    bool mn_major = false;
+};
+
+struct GemmEpilogue {
+    float alpha = 1.0f;
+    const float* bias = nullptr;  // [N], added per output column
+    float* Z = nullptr;           // optional side store of the pre-activation (same layout as D)
+    int act = NNB_ACT_NONE;
+    float beta = 1.0f;
+    __nv_bfloat16* D16 = nullptr;  // optional bf16 shadow of D (ld = ldd16)
+    int64_t ldd16 = 0;
+};
+
+struct GemmProblem {
+    int64_t M = 0, N = 0, K = 0, batch = 1;
+    GemmOperand A, B;
+    float* D = nullptr;
+    int64_t ldd = 0, batch_stride_d = 0;
+    bool reduce_batch = false;  // sum over the batch dimension into ONE output (wgrad-style)
+    // optional output column map: addr = (col / col_group) * group_stride + row * ldd + col % col_group
+    // (lets a [Cout, B*Ho*Wo] GEMM write NCHW directly); 0 = plain row-major
+    int64_t col_group = 0, group_stride = 0;
+    bool bias_per_row = false;
+    GemmEpilogue epi;
+    // split-K scratch (fp32); required when the heuristic picks splits > 1
+    float* splitk_ws = nullptr;
+    size_t splitk_ws_bytes = 0;
+    int force_bn = 0;      // 0 = heuristic
+    int force_splits = 0;  // 0 = heuristic
+};
+
+size_t gemm_splitk_ws_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);
+int gemm(const GemmProblem& p, cudaStream_t stream);
+
+}  // namespace nnb

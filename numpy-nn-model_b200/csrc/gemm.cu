@@ -1,0 +1,578 @@
+// tcgen05 GEMM for sm_100a: D = epilogue(alpha * sum_seg A_seg . B_seg^T)
+//
+//   * operands are staged bf16 planes (common.cuh: Staged); fp32 accumulation in TMEM
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) feeds a multi-stage smem ring,
+//     one thread issues tcgen05.mma (UMMA 128 x BN x 16), accumulators are double-buffered in TMEM
+//     so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs, one per SM)
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//     warps 4..7 = epilogue (tcgen05.ld -> smem transpose -> coalesced global stores)
+//   * both operand majors are supported through the UMMA descriptors, so the three Linear GEMMs
+//     (fwd X.W^T, dgrad g.W, wgrad g^T.X; neunet/nn/layers/linear.py:19-22,54) and the matmul
+//     backward forms (neunet/autograd.py:209-211) read the SAME staged buffers, no transposes
+//   * BF16X3 precision = three (A,B) segment pairs accumulated into one TMEM tile
+//   * split-K / reduce-over-batch for wgrad-shaped problems (tiny output, huge reduction)
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nnb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int UMMA_K = 16;
+constexpr int MAX_SEG = 3;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;
+constexpr int SMEM_BUDGET = 200 * 1024;  // operand ring budget
+
+struct GemmMaps {
+    CUtensorMap a[MAX_SEG];
+    CUtensorMap b[MAX_SEG];
+};
+
+struct KArgs {
+    int M, N;
+    int kblocks;       // ceil(K / BK)
+    int out_batches;   // independent output matrices
+    int red_batches;   // batches summed into one output (reduce_batch mode), else 1
+    int a_bcast, b_bcast;
+    int nseg;
+    int splits, iters_per_split;  // split over the (red_batches * kblocks) iteration space
+    int num_m, num_n;
+    float* D;
+    long long ldd, batch_stride_d;
+    int col_group;           // output column index map: addr = (col / cg) * gs + row * ldd + col % cg
+    long long group_stride;
+    float alpha;
+    const float* bias;
+    int bias_per_row;
+    float* Z;
+    int act;
+    float beta;
+    __nv_bfloat16* D16;
+    long long ldd16;
+    float* ws;  // split-K partials [split][out_batch][M][N]
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+    // UMMA shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1.
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128.
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
+           ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act, float beta) {
+    if (act == NNB_ACT_SWISH) return x / (1.0f + __expf(-beta * x));
+    return x;
+}
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES + 256 + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * C::A_BYTES;
+    float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + EPI_SCRATCH_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) {
+            ptx::tma_prefetch_desc(&maps.a[s]);
+            ptx::tma_prefetch_desc(&maps.b[s]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full[i], 1);
+            ptx::mbar_init(&tmem_empty[i], 128);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_batch = p.num_m * p.num_n;
+    const int tiles = tiles_per_batch * p.out_batches;
+    const int work = tiles * p.splits;
+    const int total_iters = p.red_batches * p.kblocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < work; w += gridDim.x) {
+                const int split = w / tiles;
+                const int t = w - split * tiles;
+                const int ob = t / tiles_per_batch;
+                const int r = t - ob * tiles_per_batch;
+                const int m0 = (r % p.num_m) * BM;
+                const int n0 = (r / p.num_m) * BN;
+                const int it0 = split * p.iters_per_split;
+                const int it1 = min(it0 + p.iters_per_split, total_iters);
+                for (int it = it0; it < it1; ++it) {
+                    const int rb = it / p.kblocks;
+                    const int k0 = (it - rb * p.kblocks) * BK;
+                    const int bidx = (p.red_batches > 1) ? rb : ob;
+                    const int ba = p.a_bcast ? 0 : bidx;
+                    const int bb = p.b_bcast ? 0 : bidx;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        uint8_t* sa = smem_a + stage * C::A_BYTES;
+                        uint8_t* sb = smem_b + stage * C::B_BYTES;
+                        if (!A_MN) {
+                            ptx::tma_load_3d(sa, &maps.a[s], &full_bar[stage], k0, m0, ba);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BM / 64; ++i)
+                                ptx::tma_load_3d(sa + i * (BK * 128), &maps.a[s], &full_bar[stage],
+                                                 m0 + i * 64, k0, ba);
+                        }
+                        if (!B_MN) {
+                            ptx::tma_load_3d(sb, &maps.b[s], &full_bar[stage], k0, n0, bb);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                ptx::tma_load_3d(sb + i * (BK * 128), &maps.b[s], &full_bar[stage],
+                                                 n0 + i * 64, k0, bb);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+        // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
+        // MN-major: atoms of [64 mn x 8 k] = 1024 B; SBO = stride between 8-k groups (1024 B),
+        //           LBO = stride between 64-wide mn atoms (BK * 128 B).
+        constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, B_LBO = B_MN ? BK * 128 : 0;
+        constexpr uint32_t A_KSTEP = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+        constexpr uint32_t B_KSTEP = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int local_iter = 0;
+        for (int w = blockIdx.x; w < work; w += gridDim.x, ++local_iter) {
+            const int split = w / tiles;
+            const int it0 = split * p.iters_per_split;
+            const int it1 = min(it0 + p.iters_per_split, total_iters);
+            const int n_pipe = (it1 - it0) * p.nseg;
+            const int acc = local_iter & 1;
+            const uint32_t acc_phase = (local_iter >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int i = 0; i < n_pipe; ++i) {
+                ptx::mbar_wait(&full_bar[stage], phase, 3);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t da =
+                        make_smem_desc(ptx::smem_u32(smem_a + stage * C::A_BYTES), A_LBO, 1024);
+                    const uint64_t db =
+                        make_smem_desc(ptx::smem_u32(smem_b + stage * C::B_BYTES), B_LBO, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * A_KSTEP),
+                                         db + (uint64_t)(k * B_KSTEP), idesc,
+                                         (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (i == n_pipe - 1) ptx::umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;  // TMEM lane quarter this warp may read
+        float* scratch = epi_scratch + q * (32 * 33);
+        int local_iter = 0;
+        for (int w = blockIdx.x; w < work; w += gridDim.x, ++local_iter) {
+            const int split = w / tiles;
+            const int t = w - split * tiles;
+            const int ob = t / tiles_per_batch;
+            const int r = t - ob * tiles_per_batch;
+            const int m0 = (r % p.num_m) * BM;
+            const int n0 = (r / p.num_m) * BN;
+            const int acc = local_iter & 1;
+            const uint32_t acc_phase = (local_iter >> 1) & 1;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase, 4);
+            ptx::tc_fence_after();
+            const int row_base = m0 + q * 32;
+            const bool rows_live = row_base < p.M;
+            constexpr int NCHUNK = BN / 32;
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N || !rows_live) {
+                    if (c == NCHUNK - 1) {
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tmem_empty[acc]);
+                    }
+                    continue;
+                }
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (c == NCHUNK - 1) {
+                    // accumulator fully drained into registers: hand the TMEM buffer back
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int col = col0 + lane;
+                const bool col_ok = col < p.N;
+                if (p.splits > 1) {
+                    float* wsp = p.ws + ((long long)(split * p.out_batches + ob) * p.M) * p.N;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = row_base + rr;
+                        if (row < p.M && col_ok)
+                            wsp[(long long)row * p.N + col] = scratch[rr * 33 + lane];
+                    }
+                } else {
+                    long long coff;
+                    if (p.col_group > 0) {
+                        const int g = col / p.col_group;
+                        coff = (long long)g * p.group_stride + (col - g * p.col_group);
+                    } else {
+                        coff = col;
+                    }
+                    coff += (long long)ob * p.batch_stride_d;
+                    float cb = 0.f;
+                    if (p.bias != nullptr && !p.bias_per_row && col_ok) cb = p.bias[col];
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = row_base + rr;
+                        if (row < p.M && col_ok) {
+                            float x = p.alpha * scratch[rr * 33 + lane];
+                            if (p.bias != nullptr) x += p.bias_per_row ? p.bias[row] : cb;
+                            const long long off = (long long)row * p.ldd + coff;
+                            if (p.Z != nullptr) p.Z[off] = x;
+                            x = apply_act(x, p.act, p.beta);
+                            p.D[off] = x;
+                            if (p.D16 != nullptr)
+                                p.D16[(long long)row * p.ldd16 + col] = __float2bfloat16(x);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// Sum split-K partials and apply the epilogue.
+__global__ void splitk_reduce_kernel(const KArgs p) {
+    const long long per = (long long)p.M * p.N;
+    const long long total = per * p.out_batches;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < p.splits; ++s) acc += p.ws[(long long)s * total + i];
+        const int ob = (int)(i / per);
+        const long long rcol = i - (long long)ob * per;
+        const int row = (int)(rcol / p.N);
+        const int col = (int)(rcol - (long long)row * p.N);
+        long long coff;
+        if (p.col_group > 0) {
+            const int g = col / p.col_group;
+            coff = (long long)g * p.group_stride + (col - g * p.col_group);
+        } else {
+            coff = col;
+        }
+        coff += (long long)ob * p.batch_stride_d;
+        float x = p.alpha * acc;
+        if (p.bias != nullptr) x += p.bias_per_row ? p.bias[row] : p.bias[col];
+        const long long off = (long long)row * p.ldd + coff;
+        if (p.Z != nullptr) p.Z[off] = x;
+        x = apply_act(x, p.act, p.beta);
+        p.D[off] = x;
+        if (p.D16 != nullptr) p.D16[(long long)row * p.ldd16 + col] = __float2bfloat16(x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// inner = contiguous dimension. box = {64 x box_rows x 1}.
+int encode_map(CUtensorMap* m, const __nv_bfloat16* ptr, int64_t inner, int64_t rows, int64_t ld,
+               int64_t batch, int64_t batch_stride, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(NNB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t bs = (batch > 1) ? (cuuint64_t)batch_stride * 2 : (cuuint64_t)rows * ld * 2;
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, bs};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15))
+        return fail(NNB_ERR_INVALID, "staged operand not 16-byte aligned for TMA");
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NNB_ERR_CUDA,
+                    "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld ld=%lld batch=%lld",
+                    (int)r, (long long)inner, (long long)rows, (long long)ld, (long long)batch);
+    return NNB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const GemmMaps& maps, const KArgs& ka, int grid, cudaStream_t stream) {
+    using C = Cfg<BN>;
+    auto kfn = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        NNB_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES));
+        configured = true;
+    }
+    kfn<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, ka);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+template <int BN>
+int launch_major(bool a_mn, bool b_mn, const GemmMaps& maps, const KArgs& ka, int grid,
+                 cudaStream_t stream) {
+    if (!a_mn && !b_mn) return launch<BN, false, false>(maps, ka, grid, stream);
+    if (a_mn && !b_mn) return launch<BN, true, false>(maps, ka, grid, stream);
+    if constexpr (BN >= 64) {
+        if (!a_mn && b_mn) return launch<BN, false, true>(maps, ka, grid, stream);
+        return launch<BN, true, true>(maps, ka, grid, stream);
+    } else {
+        return fail(NNB_ERR_UNSUPPORTED, "MN-major B needs BN >= 64");
+    }
+}
+
+}  // namespace
+
+size_t gemm_splitk_ws_bytes(int64_t M, int64_t N, int64_t K, int64_t batch) {
+    // worst case the heuristic may pick: <= 2 * SMs partial tiles of 128 x 256 worth of output
+    (void)K;
+    const int64_t max_splits = 64;
+    int64_t per = M * N * batch * 4;
+    int64_t cap = (int64_t)2 * 160 * 128 * 256 * 4 + per;  // splits are chosen so partials stay below this
+    return (size_t)std::min(per * max_splits, cap);
+}
+
+int gemm(const GemmProblem& g, cudaStream_t stream) {
+    NNB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.batch > 0, "gemm: non-positive dimension");
+    NNB_REQUIRE(g.D != nullptr, "gemm: null output");
+    NNB_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "gemm: dim too large");
+    const bool x3 = g.A.st.lo != nullptr && g.B.st.lo != nullptr;
+    const bool a_mn = g.A.mn_major, b_mn = g.B.mn_major;
+    const bool reduce_batch = g.reduce_batch;
+    const int64_t out_batches = reduce_batch ? 1 : g.batch;
+    const int64_t red_batches = reduce_batch ? g.batch : 1;
+    const int sms = num_sms();
+
+    // ---- tile shape: maximise (MMA efficiency of the tile width) x (fill of the last wave)
+    int bn;
+    if (g.force_bn) {
+        bn = g.force_bn;
+    } else {
+        const int cands[4] = {256, 128, 64, 32};
+        const double eff[4] = {1.0, 0.92, 0.62, 0.36};
+        double best = -1.0;
+        bn = b_mn ? 64 : 32;
+        for (int i = 0; i < 4; ++i) {
+            const int c = cands[i];
+            if (b_mn && c < 64) continue;
+            if (c > 32 && c / 2 >= g.N) continue;  // half the width already covers N
+            const int64_t t = ceil_div(g.M, BM) * ceil_div(g.N, c) * out_batches;
+            double fill = (double)t / (double)(ceil_div(t, sms) * sms);
+            if (t * 2 <= sms) fill = 0.9;  // split-K will spread the reduction instead
+            const double used = (double)g.N / (double)(ceil_div(g.N, c) * c);
+            const double score = eff[i] * fill * used;
+            if (score > best) { best = score; bn = c; }
+        }
+    }
+    NNB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad BN %d", bn);
+    NNB_REQUIRE(!(b_mn && bn < 64), "gemm: MN-major B needs BN >= 64");
+
+    const int64_t num_m = ceil_div(g.M, BM), num_n = ceil_div(g.N, bn);
+    const int64_t tiles = num_m * num_n * out_batches;
+    const int64_t kblocks = ceil_div(g.K, BK);
+    const int64_t total_iters = kblocks * red_batches;
+
+    // ---- split-K
+    int64_t splits = 1;
+    if (g.force_splits > 0) {
+        splits = g.force_splits;
+    } else if (tiles * 2 <= sms && total_iters >= 8) {
+        splits = std::min<int64_t>(sms / tiles, total_iters / 4);
+        splits = std::min<int64_t>(splits, 64);
+    }
+    splits = std::max<int64_t>(1, std::min(splits, total_iters));
+    int64_t ips = ceil_div(total_iters, splits);
+    splits = ceil_div(total_iters, ips);
+    if (splits > 1) {
+        const size_t need = (size_t)splits * out_batches * g.M * g.N * 4;
+        if (g.splitk_ws == nullptr || g.splitk_ws_bytes < need) {
+            if (g.force_splits > 0)
+                return fail(NNB_ERR_WORKSPACE, "gemm: split-K workspace too small (%zu < %zu)",
+                            g.splitk_ws_bytes, need);
+            // shrink to what fits
+            splits = g.splitk_ws ? (int64_t)(g.splitk_ws_bytes / ((size_t)out_batches * g.M * g.N * 4)) : 1;
+            splits = std::max<int64_t>(1, splits);
+            ips = ceil_div(total_iters, splits);
+            splits = ceil_div(total_iters, ips);
+        }
+    }
+
+    // ---- tensor maps
+    GemmMaps maps;
+    std::memset(&maps, 0, sizeof(maps));
+    const int nseg = x3 ? 3 : 1;
+    // segment order: small terms first (lo*hi, hi*lo), then hi*hi
+    const __nv_bfloat16* a_planes[3];
+    const __nv_bfloat16* b_planes[3];
+    if (x3) {
+        a_planes[0] = g.A.st.lo; b_planes[0] = g.B.st.hi;
+        a_planes[1] = g.A.st.hi; b_planes[1] = g.B.st.lo;
+        a_planes[2] = g.A.st.hi; b_planes[2] = g.B.st.hi;
+    } else {
+        a_planes[0] = g.A.st.hi; b_planes[0] = g.B.st.hi;
+    }
+    const bool a_bcast = g.batch > 1 && g.A.st.batch <= 1;
+    const bool b_bcast = g.batch > 1 && g.B.st.batch <= 1;
+    for (int s = 0; s < nseg; ++s) {
+        int rc;
+        // K-major: staged [rows = M][cols = K] -> inner K, box rows = BM.
+        // MN-major: staged [rows = K][cols = M] -> inner M, box = 64 x BK.
+        if (!a_mn) {
+            NNB_REQUIRE(g.A.st.rows == g.M && g.A.st.cols == g.K, "gemm: A staged shape mismatch");
+            rc = encode_map(&maps.a[s], a_planes[s], g.K, g.M, g.A.st.ld, a_bcast ? 1 : g.batch,
+                            g.A.st.batch_stride, BM);
+        } else {
+            NNB_REQUIRE(g.A.st.rows == g.K && g.A.st.cols == g.M, "gemm: A staged shape mismatch (MN)");
+            rc = encode_map(&maps.a[s], a_planes[s], g.M, g.K, g.A.st.ld, a_bcast ? 1 : g.batch,
+                            g.A.st.batch_stride, BK);
+        }
+        if (rc) return rc;
+        if (!b_mn) {
+            NNB_REQUIRE(g.B.st.rows == g.N && g.B.st.cols == g.K, "gemm: B staged shape mismatch");
+            rc = encode_map(&maps.b[s], b_planes[s], g.K, g.N, g.B.st.ld, b_bcast ? 1 : g.batch,
+                            g.B.st.batch_stride, bn);
+        } else {
+            NNB_REQUIRE(g.B.st.rows == g.K && g.B.st.cols == g.N, "gemm: B staged shape mismatch (MN)");
+            rc = encode_map(&maps.b[s], b_planes[s], g.N, g.K, g.B.st.ld, b_bcast ? 1 : g.batch,
+                            g.B.st.batch_stride, BK);
+        }
+        if (rc) return rc;
+    }
+
+    KArgs ka;
+    std::memset(&ka, 0, sizeof(ka));
+    ka.M = (int)g.M; ka.N = (int)g.N;
+    ka.kblocks = (int)kblocks;
+    ka.out_batches = (int)out_batches;
+    ka.red_batches = (int)red_batches;
+    ka.a_bcast = a_bcast; ka.b_bcast = b_bcast;
+    ka.nseg = nseg;
+    ka.splits = (int)splits; ka.iters_per_split = (int)ips;
+    ka.num_m = (int)num_m; ka.num_n = (int)num_n;
+    ka.D = g.D; ka.ldd = g.ldd; ka.batch_stride_d = reduce_batch ? 0 : g.batch_stride_d;
+    ka.col_group = 0; ka.group_stride = 0;
+    ka.alpha = g.epi.alpha; ka.bias = g.epi.bias; ka.bias_per_row = 0;
+    ka.Z = g.epi.Z; ka.act = g.epi.act; ka.beta = g.epi.beta;
+    ka.D16 = g.epi.D16; ka.ldd16 = g.epi.ldd16;
+    ka.ws = g.splitk_ws;
+    if (g.col_group > 0) { ka.col_group = (int)g.col_group; ka.group_stride = g.group_stride; }
+    ka.bias_per_row = g.bias_per_row ? 1 : 0;
+
+    const int64_t work = tiles * splits;
+    const int grid = (int)std::min<int64_t>(work, sms);
+    int rc;
+    switch (bn) {
+        case 32: rc = launch_major<32>(a_mn, b_mn, maps, ka, grid, stream); break;
+        case 64: rc = launch_major<64>(a_mn, b_mn, maps, ka, grid, stream); break;
+        case 128: rc = launch_major<128>(a_mn, b_mn, maps, ka, grid, stream); break;
+        default: rc = launch_major<256>(a_mn, b_mn, maps, ka, grid, stream); break;
+    }
+    if (rc) return rc;
+    if (splits > 1) {
+        const int64_t total = g.M * g.N * out_batches;
+        const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sms * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ka);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+    }
+    return NNB_OK;
+}
+
+}  // namespace nnb

@@ -1,0 +1,70 @@
+// Library-wide plumbing: error string, launch counter, device queries.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace nnb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int num_sms() {
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 148;
+        sms[dev] = v;
+    }
+    return sms[dev];
+}
+
+}  // namespace nnb
+
+extern "C" {
+
+const char* nnb_last_error(void) { return nnb::g_err; }
+
+int nnb_version(void) { return 100; }
+
+int nnb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0, maj = 0, min = 0, sms = 0;
+    NNB_CUDA_OK(cudaGetDevice(&dev));
+    NNB_CUDA_OK(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+    NNB_CUDA_OK(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+    NNB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sm_count) *sm_count = sms;
+    if (cc_major) *cc_major = maj;
+    if (cc_minor) *cc_minor = min;
+    if (maj != 10)
+        return nnb::fail(NNB_ERR_UNSUPPORTED,
+                         "libneunet_b200 is built for sm_100a only; device %d is sm_%d%d", dev, maj,
+                         min);
+    return NNB_OK;
+}
+
+uint64_t nnb_launch_count(void) { return nnb::g_launches.load(); }
+void nnb_launch_count_reset(void) { nnb::g_launches.store(0); }
+
+}  // extern "C"

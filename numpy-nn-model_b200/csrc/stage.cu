@@ -1,0 +1,179 @@
+// Operand staging: strided fp32 views -> bf16 (hi [+ lo]) planes that TMA can tile.
+// HBM-bound streaming kernels: 16-byte loads, 8-byte packed bf16 stores, optional fused
+// Swish-backward transform (dZ = dO * swish'(Z), neunet/nn/activations.py:212-216) and fused
+// column sums (bias gradient, neunet/nn/layers/linear.py:23-24) so `dO` is read from HBM once.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nnb {
+namespace {
+
+__device__ __forceinline__ float swish_grad(float z, float beta) {
+    // d/dz [z * sigmoid(beta z)] = beta*f + sigmoid(beta z) * (1 - beta*f)
+    const float s = 1.0f / (1.0f + __expf(-beta * z));
+    const float f = z * s;
+    return beta * f + s * (1.0f - beta * f);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+struct StageArgs {
+    View4 v;
+    const float* aux;
+    float beta;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    long long ld, plane_stride;  // elements
+    float* partial;              // [gridDim.z * gridDim.y][cols] column partial sums, or null
+    int rows_per_block;
+    int vec_ok;
+};
+
+// thread -> 4 consecutive columns; block.y loops over a chunk of rows; blockIdx.z = batch.
+template <bool X3, int OP>
+__global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int bz = blockIdx.z;
+    const int i0 = bz / (int)a.v.b1, i1 = bz - i0 * (int)a.v.b1;
+    const float* src = a.v.ptr + i0 * a.v.s_b0 + i1 * a.v.s_b1;
+    const float* aux = (OP == STAGE_SWISH_BWD) ? a.aux + i0 * a.v.s_b0 + i1 * a.v.s_b1 : nullptr;
+    const long long r0 = (long long)blockIdx.y * a.rows_per_block;
+    const long long r1 = min(r0 + a.rows_per_block, (long long)a.v.rows);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < a.v.cols) {
+        const bool full = c + 3 < a.v.cols;
+        for (long long r = r0; r < r1; ++r) {
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full && a.vec_ok) {
+                const float4 t = *reinterpret_cast<const float4*>(src + r * a.v.s_r + c);
+                x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+                if (OP == STAGE_SWISH_BWD) {
+                    const float4 z = *reinterpret_cast<const float4*>(aux + r * a.v.s_r + c);
+                    x[0] *= swish_grad(z.x, a.beta); x[1] *= swish_grad(z.y, a.beta);
+                    x[2] *= swish_grad(z.z, a.beta); x[3] *= swish_grad(z.w, a.beta);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c + j < a.v.cols) {
+                        const long long off = r * a.v.s_r + (c + j) * a.v.s_c;
+                        x[j] = src[off];
+                        if (OP == STAGE_SWISH_BWD) x[j] *= swish_grad(aux[off], a.beta);
+                    }
+                }
+            }
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                split_bf16(x[j], h[j], l[j]);
+                cs[j] += x[j];
+            }
+            const long long o = (long long)bz * a.plane_stride + r * a.ld + c;
+            if (full) {
+                *reinterpret_cast<uint2*>(a.hi + o) = *reinterpret_cast<const uint2*>(h);
+                if (X3) *reinterpret_cast<uint2*>(a.lo + o) = *reinterpret_cast<const uint2*>(l);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c + j < a.v.cols) {
+                        a.hi[o + j] = h[j];
+                        if (X3) a.lo[o + j] = l[j];
+                    }
+                }
+            }
+        }
+        if (a.partial != nullptr) {
+            float* prow = a.partial + ((long long)blockIdx.z * gridDim.y + blockIdx.y) * a.v.cols;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < a.v.cols) prow[c + j] = cs[j];
+        }
+    }
+}
+
+__global__ void colsum_reduce_kernel(const float* partial, int nparts, long long cols, float* out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(long long)p * cols + c];
+    out[c] = s;
+}
+
+}  // namespace
+
+size_t stage_colsum_scratch_bytes(int64_t cols) {
+    return (size_t)round_up(cols * 4 * 1024, 256);  // <= 1024 row chunks
+}
+
+int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst_hi,
+                  __nv_bfloat16* dst_lo, int op, const float* aux, float beta, float* colsum,
+                  float* colsum_scratch, cudaStream_t stream, Staged* out) {
+    NNB_REQUIRE(!transpose, "stage_operand: transposing stage not implemented (use MN-major operand)");
+    NNB_REQUIRE(src.ptr && dst_hi, "stage_operand: null pointer");
+    NNB_REQUIRE(src.rows > 0 && src.cols > 0 && src.b0 > 0 && src.b1 > 0, "stage_operand: empty view");
+    const bool x3 = prec == NNB_PREC_BF16X3;
+    NNB_REQUIRE(!x3 || dst_lo, "stage_operand: BF16X3 needs a lo plane");
+    NNB_REQUIRE(op == STAGE_COPY || aux, "stage_operand: transform needs aux");
+    NNB_REQUIRE(!colsum || colsum_scratch, "stage_operand: colsum needs scratch");
+    const int64_t batch = src.b0 * src.b1;
+    const int64_t ld = staged_ld(src.cols);
+
+    StageArgs a;
+    a.v = src;
+    a.aux = aux;
+    a.beta = beta;
+    a.hi = dst_hi;
+    a.lo = dst_lo;
+    a.ld = ld;
+    a.plane_stride = src.rows * ld;
+    a.partial = nullptr;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    a.vec_ok = src.s_c == 1 && (src.s_r % 4) == 0 && (src.s_b0 % 4) == 0 && (src.s_b1 % 4) == 0 &&
+               al16(src.ptr) && (aux == nullptr || al16(aux));
+
+    const int threads = 128;
+    const int64_t gx = ceil_div(src.cols, threads * 4);
+    const int sms = num_sms();
+    int64_t want_y = std::max<int64_t>(1, (int64_t)sms * 16 / std::max<int64_t>(1, gx * batch));
+    want_y = std::min<int64_t>(want_y, 1024);
+    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(want_y, 1024 / batch));
+    NNB_REQUIRE(!colsum || batch <= 1024, "stage_operand: colsum with batch > 1024");
+    int64_t rpb = std::max<int64_t>(1, ceil_div(src.rows, want_y));
+    const int64_t gy = ceil_div(src.rows, rpb);
+    NNB_REQUIRE(batch <= 65535 && gy <= 65535, "stage_operand: grid too large");
+    a.rows_per_block = (int)rpb;
+    if (colsum) a.partial = colsum_scratch;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
+    if (x3) {
+        if (op == STAGE_SWISH_BWD) stage_rows_kernel<true, STAGE_SWISH_BWD><<<grid, threads, 0, stream>>>(a);
+        else stage_rows_kernel<true, STAGE_COPY><<<grid, threads, 0, stream>>>(a);
+    } else {
+        if (op == STAGE_SWISH_BWD) stage_rows_kernel<false, STAGE_SWISH_BWD><<<grid, threads, 0, stream>>>(a);
+        else stage_rows_kernel<false, STAGE_COPY><<<grid, threads, 0, stream>>>(a);
+    }
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    if (colsum) {
+        const int nparts = (int)(gy * batch);
+        colsum_reduce_kernel<<<(unsigned)ceil_div(src.cols, 256), 256, 0, stream>>>(
+            colsum_scratch, nparts, src.cols, colsum);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+    }
+    if (out) {
+        out->hi = dst_hi;
+        out->lo = x3 ? dst_lo : nullptr;
+        out->rows = src.rows;
+        out->cols = src.cols;
+        out->ld = ld;
+        out->batch = batch;
+        out->batch_stride = src.rows * ld;
+    }
+    return NNB_OK;
+}
+
+}  // namespace nnb
