@@ -248,7 +248,9 @@ def conv2d_backward(x, w, b, g, stride=(1, 1), pad4=(0, 0, 0, 0), dilation=(1, 1
 # optimizers  (neunet/optim.py)
 # ----------------------------------------------------------------------------------------------
 def adam_step(p, g, m, v, t, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-    """One Adam update of one tensor (optim.py:17-33); t is the 1-based step. Returns (p, m, v)."""
+    """One Adam update of one tensor (optim.py:17-33); t is the 1-based step. Returns (p, m, v).
+    Hyper-parameters are Python floats as in the reference (NumPy scalars would promote to fp64)."""
+    lr, eps, weight_decay, betas = float(lr), float(eps), float(weight_decay), (float(betas[0]), float(betas[1]))
     if weight_decay != 0:
         g = g + weight_decay * p
     m = betas[0] * m + (1 - betas[0]) * g
@@ -261,6 +263,7 @@ def adam_step(p, g, m, v, t, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay
 
 def adamw_step(p, g, m, v, t, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
     """One AdamW update (optim.py:52-69): decoupled decay first, then the Adam update."""
+    lr, eps, weight_decay, betas = float(lr), float(eps), float(weight_decay), (float(betas[0]), float(betas[1]))
     if weight_decay != 0:
         p = p - lr * weight_decay * p
     m = betas[0] * m + (1 - betas[0]) * g
