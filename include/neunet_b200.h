@@ -132,9 +132,6 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
  *        semantics neunet/nn/activations.py:208-233.
  * Softmax over the middle axis of a [outer, n, inner] view: cudaSoftmaxForward/Backward
  *        (experimental/activations/softmax/softmax.cu:144-151, 229-237), activations.py:437-459.
- *        mask (optional, forward only): int32 [outer, n, inner]-broadcastable via mask_outer_div:
- *        rows with mask==0 get -1e9 before the softmax and `scale` multiplies the input first
- *        (the GPT example's where(mask==0,-1e9) + /sqrt(d), examples/gpt.ipynb cell 2).
  * RMSNorm: RMSNormForward/Backward (experimental/rmsnorm/rmsnorm.cu:116-140, 282-308),
  *        semantics neunet/nn/layers/rmsnorm.py:39-94. dw/db are full column sums over rows.
  */
@@ -160,16 +157,17 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
  * nnb_adamw_create uploads the pointer table ONCE (the reference re-uploads it every step,
  * fused_adamw_multitensor.cu:288-291); p/g/m/v are arrays of n device pointers, sizes in elements.
  * Tensors whose g[i] is NULL are skipped, like `if param.grad is None: continue` (optim.py:21-22).
- * step: 1-based step count t; bias corrections 1-beta^t are computed in double on the host, as the
- * reference does in Python floats. grad_scale multiplies every gradient first (1/world_size after
+ * step: 1-based step count t. Hyper-parameters are doubles: 1-beta, 1-beta^t and lr*wd are formed in
+ * double on the host and rounded once to fp32, exactly where the reference forms them as Python
+ * floats before NumPy casts them to the array dtype. grad_scale multiplies every gradient first (1/world_size after
  * a sum all-reduce; 1.0 otherwise).
  */
 typedef struct nnb_adamw nnb_adamw;
 int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const* g,
                      float* const* m, float* const* v, const int64_t* sizes, cudaStream_t stream);
 int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stream);
-int nnb_adamw_step(nnb_adamw* opt, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int64_t step, int mode, float grad_scale,
+int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, int mode, float grad_scale,
                    cudaStream_t stream);
 int nnb_adamw_destroy(nnb_adamw* opt);
 

@@ -1,0 +1,457 @@
+// nn.Conv2d forward / backward (NCHW), semantics of neunet/nn/layers/conv2d.py:16-117, 297-355.
+//
+// Large-channel layers run as GEMMs on the tcgen05 kernel:
+//   fwd  : O[o, (b,ho,wo)]  = W[o, (i,k,l)] . col(X)[(b,ho,wo), (i,k,l)]^T      + bias[o]
+//   wgrad: dW[o, (i,k,l)]   = g'[o, (b,ho,wo)] . col(X)[(b,ho,wo), (i,k,l)]     (reduction over b,ho,wo)
+//   dgrad: dX[i, (b,y,x)]   = Wr[i, (o,k,l)] . colT(g)[(b,y,x), (o,k,l)]^T      (Wr = rot180, in/out swapped;
+//          colT gathers g through the stride -- the reference's zero-stuffed, (k-1)-padded grad, conv2d.py:35-96)
+// with one generic gather kernel producing the bf16 `col` planes and the GEMM epilogue writing NCHW
+// directly through its column-group index map. Tiny-channel layers (the MNIST classifier's 1->8 and
+// 8->16, the DDPM 128->3 output) use direct fp32 CUDA-core kernels: a 128-wide tensor tile would
+// be >90 % padding there.
+#include <algorithm>
+
+#include "common.cuh"
+#include "workspace.cuh"
+
+namespace nnb {
+namespace {
+
+int planes(int prec) { return prec == NNB_PREC_BF16X3 ? 2 : 1; }
+
+struct Geo {
+    int B, Cin, H, W, Cout, kh, kw, Ho, Wo;
+    int s0, s1, pt, pl, d0, d1;
+};
+
+// Generic gather ("im2col"):
+//   col[(b, p, q)][(c, k, l)] = src[b, c, yy, xx]  with  ny = p*sp0 - off0 + k*dk0,  yy = ny / up0
+//   (0 unless ny % up0 == 0 and 0 <= yy < Hs; same along x).
+// forward / wgrad: src = X,  (p,q) = (ho,wo), sp = stride, off = pad, dk = dilation, up = 1
+// dgrad          : src = dO, (p,q) = (y,x),   sp = 1, off = dil*(k-1) - pad, dk = dilation, up = stride
+//                  (taps are then the rot180-flipped ones, matched by the flipped weight staging)
+struct GatherArgs {
+    const float* src;
+    int C, Hs, Ws;          // source channels / spatial size
+    int P, Q;               // output positions per image
+    int kh, kw;
+    int sp0, sp1, off0, off1, dk0, dk1, up0, up1;
+    long long M;            // B * P * Q rows
+    int Kc;                 // C * kh * kw cols
+    long long ld;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(256) gather_cols_kernel(const GatherArgs a) {
+    // thread -> one (row m, 4 consecutive kidx); kidx fastest so stores coalesce
+    const int kq = (a.Kc + 3) >> 2;
+    const long long total = a.M * kq;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long m = idx / kq;
+        const int k4 = (int)(idx - m * kq) * 4;
+        const int q = (int)(m % a.Q);
+        const long long t = m / a.Q;
+        const int p = (int)(t % a.P);
+        const int b = (int)(t / a.P);
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kidx = k4 + j;
+            float v = 0.f;
+            if (kidx < a.Kc) {
+                const int lw = kidx % a.kw;
+                const int t2 = kidx / a.kw;
+                const int kk = t2 % a.kh;
+                const int c = t2 / a.kh;
+                const int ny = p * a.sp0 - a.off0 + kk * a.dk0;
+                const int nx = q * a.sp1 - a.off1 + lw * a.dk1;
+                if (ny >= 0 && nx >= 0 && (ny % a.up0) == 0 && (nx % a.up1) == 0) {
+                    const int yy = ny / a.up0, xx = nx / a.up1;
+                    if (yy < a.Hs && xx < a.Ws)
+                        v = a.src[(((long long)b * a.C + c) * a.Hs + yy) * a.Ws + xx];
+                }
+            }
+            h[j] = __float2bfloat16_rn(v);
+            l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+        }
+        const long long o = m * a.ld + k4;  // ld % 8 == 0 and k4 % 4 == 0 -> 8-byte aligned
+        *reinterpret_cast<uint2*>(a.hi + o) = *reinterpret_cast<const uint2*>(h);
+        if (X3) *reinterpret_cast<uint2*>(a.lo + o) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+
+// Wr[i][(o, k', l')] = W[o][i][kh-1-k'][kw-1-l']   (rot180 + in/out swap, conv2d.py:91)
+template <bool X3>
+__global__ void stage_weight_dgrad_kernel(const float* __restrict__ W, int Cout, int Cin, int kh,
+                                          int kw, long long ld, __nv_bfloat16* hi,
+                                          __nv_bfloat16* lo) {
+    const int khw = kh * kw;
+    const long long total = (long long)Cin * Cout * khw;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int kl = (int)(idx % khw);
+        const long long t = idx / khw;
+        const int o = (int)(t % Cout);
+        const int i = (int)(t / Cout);
+        const float v = W[((long long)o * Cin + i) * khw + (khw - 1 - kl)];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const long long dst = (long long)i * ld + (long long)o * khw + kl;
+        hi[dst] = h;
+        if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// g'[o][(b, hw)] = dO[b][o][hw]
+template <bool X3>
+__global__ void stage_nchw_to_c_bhw_kernel(const float* __restrict__ g, int B, int C, int HW,
+                                           long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long long total = (long long)B * C * HW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int hw = (int)(idx % HW);
+        const long long t = idx / HW;
+        const int c = (int)(t % C);
+        const int b = (int)(t / C);
+        const float v = g[idx];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const long long dst = (long long)c * ld + (long long)b * HW + hw;
+        hi[dst] = h;
+        if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// db[o] = sum_{b,h,w} dO[b,o,h,w]   (conv2d.py:94) -- one block per channel, fixed-order tree reduce
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ g, int B, int C,
+                                                          int HW, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    float s = 0.f;
+    const long long n = (long long)B * HW;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long b = i / HW, hw = i - b * HW;
+        s += g[(b * C + c) * HW + hw];
+    }
+    __shared__ float red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = red[0];
+}
+
+// ---------------------------------------------------------------- direct fp32 kernels (tiny channel counts)
+__global__ void __launch_bounds__(256)
+direct_fwd_kernel(const Geo g, const float* __restrict__ X, const float* __restrict__ Wt,
+                  const float* __restrict__ bias, float* __restrict__ O) {
+    const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int wo = (int)(idx % g.Wo);
+        long long t = idx / g.Wo;
+        const int ho = (int)(t % g.Ho); t /= g.Ho;
+        const int o = (int)(t % g.Cout);
+        const int b = (int)(t / g.Cout);
+        float acc = 0.f;
+        for (int i = 0; i < g.Cin; ++i) {
+            const float* xp = X + ((long long)b * g.Cin + i) * g.H * g.W;
+            const float* wp = Wt + ((long long)o * g.Cin + i) * g.kh * g.kw;
+            for (int k = 0; k < g.kh; ++k) {
+                const int y = ho * g.s0 - g.pt + k * g.d0;
+                if (y < 0 || y >= g.H) continue;
+                for (int l = 0; l < g.kw; ++l) {
+                    const int x = wo * g.s1 - g.pl + l * g.d1;
+                    if (x < 0 || x >= g.W) continue;
+                    acc += xp[y * g.W + x] * wp[k * g.kw + l];
+                }
+            }
+        }
+        if (bias) acc += bias[o];
+        O[idx] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+direct_dgrad_kernel(const Geo g, const float* __restrict__ dO, const float* __restrict__ Wt,
+                    float* __restrict__ dX) {
+    const long long total = (long long)g.B * g.Cin * g.H * g.W;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % g.W);
+        long long t = idx / g.W;
+        const int y = (int)(t % g.H); t /= g.H;
+        const int i = (int)(t % g.Cin);
+        const int b = (int)(t / g.Cin);
+        float acc = 0.f;
+        for (int k = 0; k < g.kh; ++k) {
+            const int ny = y + g.pt - k * g.d0;
+            if (ny < 0 || ny % g.s0) continue;
+            const int ho = ny / g.s0;
+            if (ho >= g.Ho) continue;
+            for (int l = 0; l < g.kw; ++l) {
+                const int nx = x + g.pl - l * g.d1;
+                if (nx < 0 || nx % g.s1) continue;
+                const int wo = nx / g.s1;
+                if (wo >= g.Wo) continue;
+                for (int o = 0; o < g.Cout; ++o)
+                    acc += dO[(((long long)b * g.Cout + o) * g.Ho + ho) * g.Wo + wo] *
+                           Wt[(((long long)o * g.Cin + i) * g.kh + k) * g.kw + l];
+            }
+        }
+        dX[idx] = acc;
+    }
+}
+
+// one block per weight element (o, i, k, l): reduce over (b, ho, wo)
+__global__ void __launch_bounds__(256)
+direct_wgrad_kernel(const Geo g, const float* __restrict__ X, const float* __restrict__ dO,
+                    float* __restrict__ dW) {
+    int idx = blockIdx.x;
+    const int l = idx % g.kw; idx /= g.kw;
+    const int k = idx % g.kh; idx /= g.kh;
+    const int i = idx % g.Cin;
+    const int o = idx / g.Cin;
+    const int HWo = g.Ho * g.Wo;
+    const long long n = (long long)g.B * HWo;
+    float s = 0.f;
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+        const int b = (int)(e / HWo);
+        const int r = (int)(e - (long long)b * HWo);
+        const int ho = r / g.Wo, wo = r - ho * g.Wo;
+        const int y = ho * g.s0 - g.pt + k * g.d0;
+        const int x = wo * g.s1 - g.pl + l * g.d1;
+        if (y >= 0 && y < g.H && x >= 0 && x < g.W)
+            s += X[(((long long)b * g.Cin + i) * g.H + y) * g.W + x] *
+                 dO[((long long)b * g.Cout + o) * HWo + r];
+    }
+    __shared__ float red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dW[blockIdx.x] = red[0];
+}
+
+int grid_for(long long n, int threads) {
+    return (int)std::max<long long>(1, std::min<long long>(ceil_div(n, threads), (long long)num_sms() * 32));
+}
+
+int make_geo(const nnb_conv2d_desc* d, Geo* g) {
+    NNB_REQUIRE(d, "conv2d: null descriptor");
+    NNB_REQUIRE(d->B > 0 && d->Cin > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->kh > 0 && d->kw > 0,
+                "conv2d: non-positive dimension");
+    NNB_REQUIRE(d->stride[0] > 0 && d->stride[1] > 0 && d->dil[0] > 0 && d->dil[1] > 0, "conv2d: bad stride/dilation");
+    NNB_REQUIRE(d->pad[0] >= 0 && d->pad[1] >= 0 && d->pad[2] >= 0 && d->pad[3] >= 0, "conv2d: negative padding");
+    const int64_t eh = d->H + d->pad[0] + d->pad[1] - d->dil[0] * (d->kh - 1) - 1;
+    const int64_t ew = d->W + d->pad[2] + d->pad[3] - d->dil[1] * (d->kw - 1) - 1;
+    NNB_REQUIRE(eh >= 0 && ew >= 0, "conv2d: kernel larger than padded input");
+    g->B = (int)d->B; g->Cin = (int)d->Cin; g->H = (int)d->H; g->W = (int)d->W; g->Cout = (int)d->Cout;
+    g->kh = (int)d->kh; g->kw = (int)d->kw;
+    g->Ho = (int)(eh / d->stride[0] + 1);  // conv2d.py:246-260
+    g->Wo = (int)(ew / d->stride[1] + 1);
+    g->s0 = d->stride[0]; g->s1 = d->stride[1];
+    g->pt = d->pad[0]; g->pl = d->pad[2];
+    g->d0 = d->dil[0]; g->d1 = d->dil[1];
+    NNB_REQUIRE((int64_t)g->B * g->Ho * g->Wo < (1ll << 31) && (int64_t)g->B * g->H * g->W < (1ll << 31),
+                "conv2d: too many output positions");
+    return NNB_OK;
+}
+
+bool use_direct(const Geo& g) { return g.Cout < 32; }
+
+int run_gather(const GatherArgs& a, bool x3, cudaStream_t stream) {
+    const long long total = a.M * ((a.Kc + 3) / 4);
+    if (x3) gather_cols_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(a);
+    else gather_cols_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(a);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+struct Planes {
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+};
+Planes take_planes(Bump& ws, int64_t rows, int64_t cols, int prec) {
+    Planes p;
+    p.hi = static_cast<__nv_bfloat16*>(ws.take(staged_plane_bytes(1, rows, cols)));
+    p.lo = prec == NNB_PREC_BF16X3 ? static_cast<__nv_bfloat16*>(ws.take(staged_plane_bytes(1, rows, cols))) : nullptr;
+    return p;
+}
+Staged as_staged(const Planes& p, int64_t rows, int64_t cols) {
+    Staged s;
+    s.hi = p.hi; s.lo = p.lo; s.rows = rows; s.cols = cols; s.ld = staged_ld(cols);
+    s.batch = 1; s.batch_stride = rows * s.ld;
+    return s;
+}
+
+}  // namespace
+}  // namespace nnb
+
+using namespace nnb;
+
+extern "C" {
+
+int nnb_conv2d_out_shape(const nnb_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
+    Geo g;
+    int rc = make_geo(d, &g);
+    if (rc) return rc;
+    if (Ho) *Ho = g.Ho;
+    if (Wo) *Wo = g.Wo;
+    return NNB_OK;
+}
+
+size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backward) {
+    Geo g;
+    if (make_geo(d, &g)) return 0;
+    if (use_direct(g)) return 256;
+    const size_t p = planes(prec);
+    const int64_t M = (int64_t)g.B * g.Ho * g.Wo, Kc = (int64_t)g.Cin * g.kh * g.kw;
+    const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
+    size_t b = 8192;
+    b += p * staged_plane_bytes(1, M, Kc);  // col(X)
+    if (!backward) {
+        b += p * staged_plane_bytes(1, g.Cout, Kc);  // W
+        b += gemm_splitk_ws_bytes(g.Cout, M, Kc, 1);
+    } else {
+        b += p * staged_plane_bytes(1, g.Cout, M);   // g'
+        b += p * staged_plane_bytes(1, Mx, Kg);      // colT(g)
+        b += p * staged_plane_bytes(1, g.Cin, Kg);   // Wr
+        b += std::max(gemm_splitk_ws_bytes(g.Cout, Kc, M, 1), gemm_splitk_ws_bytes(g.Cin, Mx, Kg, 1));
+    }
+    return b;
+}
+
+int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* bias,
+                       float* O, int prec, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+    NNB_REQUIRE(X && Wt && O, "nnb_conv2d_forward: null pointer");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_forward: bad prec");
+    Geo g;
+    int rc = make_geo(d, &g);
+    if (rc) return rc;
+    if (use_direct(g)) {
+        const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
+        direct_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(g, X, Wt, bias, O);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+        return NNB_OK;
+    }
+    const bool x3 = prec == NNB_PREC_BF16X3;
+    const int64_t HWo = (int64_t)g.Ho * g.Wo, M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
+    Bump ws(workspace, workspace_bytes);
+    Planes col = take_planes(ws, M, Kc, prec);
+    Planes wp = take_planes(ws, g.Cout, Kc, prec);
+    if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_forward: workspace too small (need >= %zu)", ws.off);
+    GatherArgs a{X, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+                 M, (int)Kc, staged_ld(Kc), col.hi, col.lo};
+    rc = run_gather(a, x3, stream);
+    if (rc) return rc;
+    Staged wst;
+    rc = stage_operand(view2d(Wt, g.Cout, Kc, Kc), false, prec, wp.hi, wp.lo, STAGE_COPY, nullptr, 0.f,
+                       nullptr, nullptr, stream, &wst);
+    if (rc) return rc;
+    GemmProblem p;
+    p.M = g.Cout; p.N = M; p.K = Kc;
+    p.A.st = wst;
+    p.B.st = as_staged(col, M, Kc);
+    p.D = O; p.ldd = HWo;
+    p.col_group = HWo; p.group_stride = (int64_t)g.Cout * HWo;
+    p.epi.bias = bias; p.bias_per_row = true;
+    p.splitk_ws_bytes = ws.remaining();
+    p.splitk_ws = static_cast<float*>(ws.take(p.splitk_ws_bytes));
+    return gemm(p, stream);
+}
+
+int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* dO,
+                        float* dX, float* dW, float* db, int prec, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream) {
+    NNB_REQUIRE(X && Wt && dO && dW, "nnb_conv2d_backward: null pointer");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_backward: bad prec");
+    Geo g;
+    int rc = make_geo(d, &g);
+    if (rc) return rc;
+    const int64_t HWo = (int64_t)g.Ho * g.Wo;
+    if (db) {
+        channel_sum_kernel<<<g.Cout, 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, db);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+    }
+    if (use_direct(g)) {
+        direct_wgrad_kernel<<<g.Cout * g.Cin * g.kh * g.kw, 256, 0, stream>>>(g, X, dO, dW);
+        count_launch();
+        if (dX) {
+            const long long total = (long long)g.B * g.Cin * g.H * g.W;
+            direct_dgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(g, dO, Wt, dX);
+            count_launch();
+        }
+        NNB_CUDA_OK(cudaGetLastError());
+        return NNB_OK;
+    }
+    const bool x3 = prec == NNB_PREC_BF16X3;
+    const int64_t M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
+    const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
+    Bump ws(workspace, workspace_bytes);
+    Planes col = take_planes(ws, M, Kc, prec);
+    Planes gp = take_planes(ws, g.Cout, M, prec);
+    Planes colg{nullptr, nullptr}, wr{nullptr, nullptr};
+    if (dX) {
+        colg = take_planes(ws, Mx, Kg, prec);
+        wr = take_planes(ws, g.Cin, Kg, prec);
+    }
+    if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
+    const size_t sk_bytes = ws.remaining();
+    float* sk = static_cast<float*>(ws.take(sk_bytes));
+
+    // ---- wgrad: dW[o, (i,k,l)] = sum_{(b,ho,wo)} g'[o, (b,ho,wo)] * col[(b,ho,wo), (i,k,l)]   (conv2d.py:93)
+    GatherArgs a{X, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+                 M, (int)Kc, staged_ld(Kc), col.hi, col.lo};
+    rc = run_gather(a, x3, stream);
+    if (rc) return rc;
+    {
+        const long long total = (long long)g.B * g.Cout * HWo;
+        if (x3) stage_nchw_to_c_bhw_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, staged_ld(M), gp.hi, gp.lo);
+        else stage_nchw_to_c_bhw_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, staged_ld(M), gp.hi, gp.lo);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+        GemmProblem p;
+        p.M = g.Cout; p.N = Kc; p.K = M;
+        p.A.st = as_staged(gp, g.Cout, M);               // [Cout][M]: K-major
+        p.B.st = as_staged(col, M, Kc); p.B.mn_major = true;  // [M(reduction)][Kc]
+        p.D = dW; p.ldd = Kc;
+        p.splitk_ws = sk; p.splitk_ws_bytes = sk_bytes;
+        rc = gemm(p, stream);
+        if (rc) return rc;
+    }
+    // ---- dgrad: dX[i, (b,y,x)] = sum_{(o,k',l')} Wr[i,(o,k',l')] * colT[(b,y,x),(o,k',l')]   (conv2d.py:35-106)
+    if (dX) {
+        GatherArgs ga{dO, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
+                      g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1, g.s0, g.s1,
+                      Mx, (int)Kg, staged_ld(Kg), colg.hi, colg.lo};
+        rc = run_gather(ga, x3, stream);
+        if (rc) return rc;
+        const long long total = (long long)g.Cin * Kg;
+        if (x3) stage_weight_dgrad_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, staged_ld(Kg), wr.hi, wr.lo);
+        else stage_weight_dgrad_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, staged_ld(Kg), wr.hi, wr.lo);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+        const int64_t HW = (int64_t)g.H * g.W;
+        GemmProblem p;
+        p.M = g.Cin; p.N = Mx; p.K = Kg;
+        p.A.st = as_staged(wr, g.Cin, Kg);
+        p.B.st = as_staged(colg, Mx, Kg);
+        p.D = dX; p.ldd = HW;
+        p.col_group = HW; p.group_stride = (int64_t)g.Cin * HW;
+        p.splitk_ws = sk; p.splitk_ws_bytes = sk_bytes;
+        rc = gemm(p, stream);
+        if (rc) return rc;
+    }
+    return NNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+// Stand-alone (un-fused) forms of the epilogue ops: Swish, Softmax(axis), RMSNorm.
+// All are HBM-bound streaming kernels: 16-byte accesses where alignment allows, warp-shuffle
+// reductions, grids sized in multiples of the SM count.
+// Reference semantics: neunet/nn/activations.py:208-233 (Swish), 437-459 (Softmax),
+// neunet/nn/layers/rmsnorm.py:39-94 (RMSNorm).
+#include <algorithm>
+#include <cfloat>
+
+#include "common.cuh"
+#include "workspace.cuh"
+
+namespace nnb {
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float swish_f(float x, float beta) { return x * sigmoidf_(beta * x); }
+__device__ __forceinline__ float swish_df(float x, float beta) {
+    const float s = sigmoidf_(beta * x);
+    const float f = x * s;
+    return beta * f + s * (1.0f - beta * f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- Swish
+template <bool BWD>
+__global__ void swish_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                             float* __restrict__ y, long long n, float beta, int vec) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec) {
+        const long long n4 = n >> 2;
+        for (long long i = tid; i < n4; i += stride) {
+            const float4 a = reinterpret_cast<const float4*>(x)[i];
+            float4 r;
+            if (BWD) {
+                const float4 gg = reinterpret_cast<const float4*>(g)[i];
+                r.x = gg.x * swish_df(a.x, beta); r.y = gg.y * swish_df(a.y, beta);
+                r.z = gg.z * swish_df(a.z, beta); r.w = gg.w * swish_df(a.w, beta);
+            } else {
+                r.x = swish_f(a.x, beta); r.y = swish_f(a.y, beta);
+                r.z = swish_f(a.z, beta); r.w = swish_f(a.w, beta);
+            }
+            reinterpret_cast<float4*>(y)[i] = r;
+        }
+        for (long long i = (n4 << 2) + tid; i < n; i += stride)
+            y[i] = BWD ? g[i] * swish_df(x[i], beta) : swish_f(x[i], beta);
+    } else {
+        for (long long i = tid; i < n; i += stride)
+            y[i] = BWD ? g[i] * swish_df(x[i], beta) : swish_f(x[i], beta);
+    }
+}
+
+// ---------------------------------------------------------------- Softmax
+// inner == 1: one warp per row (online max/sum in one pass, second pass writes).
+template <bool BWD>
+__global__ void softmax_rows_kernel(const float* __restrict__ a, const float* __restrict__ g,
+                                    float* __restrict__ out, long long rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const float* ar = a + row * n;
+    float* orow = out + row * n;
+    if (!BWD) {
+        float m = -FLT_MAX, s = 0.f;
+        for (int i = lane; i < n; i += 32) {
+            const float v = ar[i];
+            if (v > m) { s *= expf(m - v); m = v; }
+            s += expf(v - m);
+        }
+        const float mm = warp_max(m);
+        s *= expf(m - mm);
+        s = warp_sum(s);
+        for (int i = lane; i < n; i += 32) orow[i] = expf(ar[i] - mm) / s;
+    } else {
+        const float* gr = g + row * n;
+        float d = 0.f;
+        for (int i = lane; i < n; i += 32) d += gr[i] * ar[i];
+        d = warp_sum(d);
+        for (int i = lane; i < n; i += 32) orow[i] = (gr[i] - d) * ar[i];
+    }
+}
+
+// inner > 1: one thread per (outer, inner) column, striding over the softmax axis (coalesced on inner).
+template <bool BWD>
+__global__ void softmax_strided_kernel(const float* __restrict__ a, const float* __restrict__ g,
+                                       float* __restrict__ out, long long outer, int n,
+                                       long long inner) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= outer * inner) return;
+    const long long o = idx / inner, in = idx - o * inner;
+    const long long base = o * n * inner + in;
+    if (!BWD) {
+        float m = -FLT_MAX;
+        for (int i = 0; i < n; ++i) m = fmaxf(m, a[base + i * inner]);
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += expf(a[base + i * inner] - m);
+        for (int i = 0; i < n; ++i) out[base + i * inner] = expf(a[base + i * inner] - m) / s;
+    } else {
+        float d = 0.f;
+        for (int i = 0; i < n; ++i) d += g[base + i * inner] * a[base + i * inner];
+        for (int i = 0; i < n; ++i) out[base + i * inner] = (g[base + i * inner] - d) * a[base + i * inner];
+    }
+}
+
+// ---------------------------------------------------------------- RMSNorm
+// one warp per row
+__global__ void rmsnorm_fwd_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                   const float* __restrict__ b, float* __restrict__ Y,
+                                   float* __restrict__ Xstd, float* __restrict__ Xnorm,
+                                   long long rows, int cols, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const float* x = X + row * cols;
+    float ss = 0.f;
+    for (int i = lane; i < cols; i += 32) ss += x[i] * x[i];
+    ss = warp_sum(ss);
+    const float std = sqrtf(ss / (float)cols + eps);
+    if (lane == 0 && Xstd) Xstd[row] = std;
+    for (int i = lane; i < cols; i += 32) {
+        const float xn = x[i] / std;
+        if (Xnorm) Xnorm[row * cols + i] = xn;
+        float y = xn * w[i];
+        if (b) y += b[i];
+        Y[row * cols + i] = y;
+    }
+}
+
+__global__ void rmsnorm_bwd_dx_kernel(const float* __restrict__ gY, const float* __restrict__ X,
+                                      const float* __restrict__ w, const float* __restrict__ Xstd,
+                                      float* __restrict__ dX, long long rows, int cols) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const float* x = X + row * cols;
+    const float* g = gY + row * cols;
+    const float std = Xstd[row];
+    float dot = 0.f;
+    for (int i = lane; i < cols; i += 32) dot += w[i] * g[i] * x[i] / std;
+    dot = warp_sum(dot);
+    const float c = dot / (float)cols;
+    const float inv2 = 1.0f / (std * std);
+    // (dXhat * std - x * sum(dXhat * x / std) / N) / std^2   (rmsnorm.py:51)
+    for (int i = lane; i < cols; i += 32) dX[row * cols + i] = (w[i] * g[i] * std - x[i] * c) * inv2;
+}
+
+// column partial sums of gY * (X / std) and gY over a chunk of rows; thread = column
+__global__ void rmsnorm_bwd_cols_kernel(const float* __restrict__ gY, const float* __restrict__ X,
+                                        const float* __restrict__ Xstd, float* __restrict__ pw,
+                                        float* __restrict__ pb, long long rows, int cols,
+                                        int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    float sw = 0.f, sb = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+        const float g = gY[r * cols + c];
+        sw += g * (X[r * cols + c] / Xstd[r]);
+        sb += g;
+    }
+    pw[(long long)blockIdx.y * cols + c] = sw;
+    if (pb) pb[(long long)blockIdx.y * cols + c] = sb;
+}
+
+__global__ void colsum2_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
+                                      int nparts, int cols, float* __restrict__ dw,
+                                      float* __restrict__ db) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float sw = 0.f, sb = 0.f;
+    for (int p = 0; p < nparts; ++p) {
+        sw += pw[(long long)p * cols + c];
+        if (db) sb += pb[(long long)p * cols + c];
+    }
+    dw[c] = sw;
+    if (db) db[c] = sb;
+}
+
+int ew_grid(long long n_threads_needed, int threads) {
+    const long long blocks = ceil_div(n_threads_needed, threads);
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)num_sms() * 16));
+}
+
+constexpr int RMS_MAX_PARTS = 256;
+
+}  // namespace
+}  // namespace nnb
+
+using namespace nnb;
+
+extern "C" {
+
+int nnb_swish_forward(const float* x, float* y, int64_t n, float beta, cudaStream_t stream) {
+    NNB_REQUIRE(x && y && n > 0, "nnb_swish_forward: bad arguments");
+    const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    swish_kernel<false><<<ew_grid(vec ? (n + 3) / 4 : n, 256), 256, 0, stream>>>(x, nullptr, y, n, beta, vec);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_swish_backward(const float* x, const float* grad, float* dx, int64_t n, float beta,
+                       cudaStream_t stream) {
+    NNB_REQUIRE(x && grad && dx && n > 0, "nnb_swish_backward: bad arguments");
+    const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad) |
+                      reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    swish_kernel<true><<<ew_grid(vec ? (n + 3) / 4 : n, 256), 256, 0, stream>>>(x, grad, dx, n, beta, vec);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_softmax_forward(const float* x, float* y, int64_t outer, int64_t n, int64_t inner,
+                        cudaStream_t stream) {
+    NNB_REQUIRE(x && y, "nnb_softmax_forward: null pointer");
+    NNB_REQUIRE(outer > 0 && n > 0 && inner > 0 && n < (1ll << 31), "nnb_softmax_forward: bad shape");
+    if (inner == 1) {
+        const long long blocks = ceil_div(outer * 32, 256);
+        softmax_rows_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, nullptr, y, outer, (int)n);
+    } else {
+        const long long blocks = ceil_div(outer * inner, 256);
+        softmax_strided_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, nullptr, y, outer, (int)n, inner);
+    }
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_softmax_backward(const float* y, const float* grad, float* dx, int64_t outer, int64_t n,
+                         int64_t inner, cudaStream_t stream) {
+    NNB_REQUIRE(y && grad && dx, "nnb_softmax_backward: null pointer");
+    NNB_REQUIRE(outer > 0 && n > 0 && inner > 0 && n < (1ll << 31), "nnb_softmax_backward: bad shape");
+    if (inner == 1) {
+        const long long blocks = ceil_div(outer * 32, 256);
+        softmax_rows_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(y, grad, dx, outer, (int)n);
+    } else {
+        const long long blocks = ceil_div(outer * inner, 256);
+        softmax_strided_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(y, grad, dx, outer, (int)n, inner);
+    }
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_rmsnorm_forward(const float* X, const float* w, const float* b, float* Y, float* X_std,
+                        float* X_norm, int64_t rows, int64_t cols, float eps, cudaStream_t stream) {
+    NNB_REQUIRE(X && w && Y, "nnb_rmsnorm_forward: null pointer");
+    NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_forward: bad shape");
+    const long long blocks = ceil_div(rows * 32, 256);
+    rmsnorm_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, w, b, Y, X_std, X_norm, rows, (int)cols, eps);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+size_t nnb_rmsnorm_workspace_bytes(int64_t rows, int64_t cols) {
+    (void)rows;
+    return (size_t)(2 * RMS_MAX_PARTS * cols * 4 + 512);
+}
+
+int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const float* X_std,
+                         const float* X_norm, float* dX, float* dw, float* db, int64_t rows,
+                         int64_t cols, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream) {
+    (void)X_norm;  // recomputed as X / X_std: cheaper than reading a second [rows, cols] array
+    NNB_REQUIRE(gY && X && w && X_std && dX, "nnb_rmsnorm_backward: null pointer");
+    NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_backward: bad shape");
+    const long long blocks = ceil_div(rows * 32, 256);
+    rmsnorm_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gY, X, w, X_std, dX, rows, (int)cols);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    if (dw) {
+        Bump ws(workspace, workspace_bytes);
+        float* pw = static_cast<float*>(ws.take((size_t)RMS_MAX_PARTS * cols * 4));
+        float* pb = db ? static_cast<float*>(ws.take((size_t)RMS_MAX_PARTS * cols * 4)) : nullptr;
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_rmsnorm_backward: workspace too small");
+        const int gx = (int)ceil_div(cols, 128);
+        long long parts = std::max<long long>(1, std::min<long long>(RMS_MAX_PARTS, (long long)num_sms() * 4 / gx));
+        parts = std::min<long long>(parts, rows);
+        const int rpb = (int)ceil_div(rows, parts);
+        parts = ceil_div(rows, rpb);
+        rmsnorm_bwd_cols_kernel<<<dim3(gx, (unsigned)parts), 128, 0, stream>>>(gY, X, X_std, pw, pb, rows, (int)cols, rpb);
+        colsum2_reduce_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, stream>>>(pw, pb, (int)parts, (int)cols, dw, db);
+        count_launch(2);
+        NNB_CUDA_OK(cudaGetLastError());
+    }
+    return NNB_OK;
+}
+
+}  // extern "C"

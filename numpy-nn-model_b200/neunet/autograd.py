@@ -1,0 +1,583 @@
+"""Tape-based autograd ``Tensor`` with the reference's public contract (neunet/autograd.py):
+
+* ``Tensor(data, args, op, requires_grad, dtype, device)`` -- data is copied and cast to float32
+  unless a dtype is given (autograd.py:16-19); ``device`` is ``"cpu"`` (NumPy) or ``"cuda"``
+  (torch CUDA storage + the sm_100a kernels of ``neunet.b200``).
+* every differentiable result carries ``.args`` and a ``grad_fn(*args, grad=...)`` that ends in
+  ``arg.apply_grad(array)`` (autograd.py:85-93); ``backward()`` seeds ones, topologically sorts the
+  tape and calls the ``grad_fn``s in reverse (autograd.py:965-1002). Layers plug into the same tape
+  by returning Tensor subclasses with a hand-written ``grad_fn`` (``_LinearTensor`` etc.).
+
+The implementation is new: ops are built from two small factories instead of ~45 hand-written
+methods, the tape sort is iterative (no recursion limit on deep GPT tapes), results are wrapped
+without the reference's extra copy, and ``matmul`` on ``"cuda"`` calls the tcgen05 GEMM
+(forward and both backward contractions) with no array-library fallback.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+from . import backend as _be
+from .backend import get_xp
+
+
+def _is_arr(x):
+    return isinstance(x, np.ndarray) or _be.is_device_array(x)
+
+
+class Tensor:
+    __array_priority__ = 1000  # NumPy scalars/arrays defer to Tensor's reflected operators
+
+    def __init__(self, data: Any, args=None, op=None, requires_grad: bool = True, dtype=None, device="cpu"):
+        if device not in ("cpu", "cuda"):
+            raise ValueError("Device must be 'cpu' or 'cuda'")
+        self.xp = get_xp(device)
+        if isinstance(data, Tensor):
+            data = data.data
+        want = np.float32 if dtype is None else dtype
+        if device == "cpu":
+            if _be.is_device_array(data):
+                data = _be.to_host(data)
+            self.data = np.array(data, dtype=_be.to_numpy_dtype(want))
+        else:
+            self.data = self.xp.array(data, dtype=want)
+        self.grad = None
+        self.op = op
+        self.args = args
+        self.requires_grad = requires_grad
+        self.device = device
+        self.grad_fn = _no_grad_fn
+
+    # ---------------------------------------------------------------------------------------
+    @classmethod
+    def _wrap(cls, data, args, op, requires_grad, device, cast=True):
+        """Internal constructor for op results: no defensive copy; float32 cast like the
+        reference's ``Tensor(result, ...)`` (autograd.py:16-19) unless ``cast`` is False."""
+        t = cls.__new__(cls)
+        t.xp = get_xp(device)
+        if cast:
+            if device == "cpu":
+                data = np.asarray(data)
+                if data.dtype != np.float32:
+                    data = data.astype(np.float32)
+            elif data.dtype != _be.torch.float32:
+                data = data.to(_be.torch.float32)
+        t.data = data
+        t.grad = None
+        t.op = op
+        t.args = args
+        t.requires_grad = requires_grad
+        t.device = device
+        t.grad_fn = _no_grad_fn
+        return t
+
+    def ensure_tensor(self, t, requires_grad=False) -> "Tensor":
+        if isinstance(t, Tensor):
+            if t.device != self.device:
+                raise ValueError("Tensors must be on the same device")
+            return t
+        return Tensor(t, requires_grad=requires_grad, device=self.device, dtype=self.dtype)
+
+    # ---- host / device movement -------------------------------------------------------------
+    def numpy(self) -> np.ndarray:
+        if self.device != "cpu":
+            raise ValueError("Tensor must be on the CPU")
+        if self.requires_grad:
+            raise ValueError("Tensor must not require gradient")
+        return self.data
+
+    def to(self, device) -> "Tensor":
+        if device == self.device:
+            return self
+        if device not in ("cpu", "cuda"):
+            raise ValueError("Device must be 'cpu' or 'cuda'")
+        return Tensor(self.data, requires_grad=self.requires_grad, dtype=self.dtype, device=device)
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def cuda(self):
+        return self.to("cuda")
+
+    def detach(self) -> "Tensor":
+        return Tensor(self.data, args=None, op=self.op, requires_grad=False, dtype=self.dtype, device=self.device)
+
+    def item(self):
+        return self.data.item()
+
+    def contiguous(self) -> "Tensor":
+        # the reference's contiguous() is value-preserving and returns self (autograd.py:81-83)
+        return self
+
+    # ---- gradient accumulation ---------------------------------------------------------------
+    def apply_grad(self, grad):
+        if not self.requires_grad:
+            return
+        grad = self._reverse_broadcast(grad)
+        self.grad = grad if self.grad is None else self.grad + grad
+
+    def _reverse_broadcast(self, grad):
+        """Sum a broadcast gradient back to this tensor's shape (autograd.py:948-962)."""
+        gshape, sshape = tuple(grad.shape), tuple(self.data.shape)
+        if gshape == sshape:
+            return grad
+        xp = self.xp
+        if len(sshape) == len(gshape):
+            axes = tuple(i for i, (a, b) in enumerate(zip(sshape, gshape)) if a != b)
+            grad = xp.sum(grad, axis=axes, keepdims=True)
+        else:
+            padded = (1,) * (len(gshape) - len(sshape)) + sshape
+            axes = tuple(i for i, (a, b) in enumerate(zip(padded, gshape)) if a != b)
+            grad = xp.sum(grad, axis=axes)
+        return grad.reshape(sshape)
+
+    # ---- op factories ---------------------------------------------------------------------------
+    def _binary(self, t, op, fwd, bwd_self, bwd_t):
+        t = self.ensure_tensor(t)
+        rg = self.requires_grad or t.requires_grad
+        out = Tensor._wrap(fwd(self.data, t.data), (self, t) if rg else None, op, rg, self.device)
+        if rg:
+            def grad_fn(a: "Tensor", b: "Tensor", grad):
+                if a.requires_grad:
+                    a.apply_grad(bwd_self(a, b, grad))
+                if b.requires_grad:
+                    b.apply_grad(bwd_t(a, b, grad))
+            out.grad_fn = grad_fn
+        return out
+
+    def _unary(self, op, value, bwd):
+        out = Tensor._wrap(value, (self,), op, self.requires_grad, self.device)
+
+        def grad_fn(a: "Tensor", grad):
+            if a.requires_grad:
+                a.apply_grad(bwd(a, grad))
+        out.grad_fn = grad_fn
+        return out
+
+    # ---- arithmetic -------------------------------------------------------------------------------
+    def add(self, t):
+        return self._binary(t, "add", lambda a, b: a + b, lambda a, b, g: g, lambda a, b, g: g)
+
+    def sub(self, t):
+        return self._binary(t, "sub", lambda a, b: a - b, lambda a, b, g: g, lambda a, b, g: -g)
+
+    def mul(self, t):
+        return self._binary(t, "mul", lambda a, b: a * b, lambda a, b, g: g * b.data, lambda a, b, g: g * a.data)
+
+    def div(self, t):
+        return self._binary(t, "div", lambda a, b: a / b, lambda a, b, g: g / b.data,
+                            lambda a, b, g: -g * a.data / (b.data ** 2))
+
+    def power(self, t):
+        xp = self.xp
+        return self._binary(t, "power", lambda a, b: a ** b,
+                            lambda a, b, g: g * b.data * a.data ** (b.data - 1),
+                            lambda a, b, g: g * a.data ** b.data * xp.log(a.data))
+
+    def maximum(self, t):
+        xp = self.xp
+        return self._binary(t, "maximum", lambda a, b: xp.maximum(a, b),
+                            lambda a, b, g: g * (a.data >= b.data), lambda a, b, g: g * (a.data <= b.data))
+
+    def minimum(self, t):
+        xp = self.xp
+        return self._binary(t, "minimum", lambda a, b: xp.minimum(a, b),
+                            lambda a, b, g: g * (a.data <= b.data), lambda a, b, g: g * (a.data >= b.data))
+
+    def matmul(self, t):
+        """``xp.matmul`` forward; backward follows the four rank cases of autograd.py:206-226.
+        On "cuda" all three contractions run on the tcgen05 GEMM (neunet.b200)."""
+        t = self.ensure_tensor(t)
+        rg = self.requires_grad or t.requires_grad
+        xp = self.xp
+        out = Tensor._wrap(xp.matmul(self.data, t.data), (self, t) if rg else None, "matmul", rg, self.device)
+        if not rg:
+            return out
+
+        if self.device == "cuda":
+            from . import b200
+
+            def grad_fn(a: "Tensor", b: "Tensor", grad):
+                ad, bd = a.data, b.data
+                if ad.ndim == 1 and bd.ndim == 1:  # vector . vector: no contraction left
+                    if a.requires_grad:
+                        a.apply_grad(grad * bd)
+                    if b.requires_grad:
+                        b.apply_grad(grad * ad)
+                    return
+                # lift vectors to matrices, contract on the device, drop the lifted axis again
+                a2 = ad.unsqueeze(0) if ad.ndim == 1 else ad
+                b2 = bd.unsqueeze(1) if bd.ndim == 1 else bd
+                g2 = grad
+                if ad.ndim == 1:
+                    g2 = g2.unsqueeze(-2)
+                if bd.ndim == 1:
+                    g2 = g2.unsqueeze(-1)
+                da, db = b200.matmul_backward(a2, b2, g2, a.requires_grad, b.requires_grad)
+                if da is not None:
+                    a.apply_grad(da.squeeze(-2) if ad.ndim == 1 else da)
+                if db is not None:
+                    b.apply_grad(db.squeeze(-1) if bd.ndim == 1 else db)
+        else:
+            def grad_fn(a: "Tensor", b: "Tensor", grad):
+                ad, bd = a.data, b.data
+                if ad.ndim > 1 and bd.ndim > 1:
+                    if a.requires_grad:
+                        a.apply_grad(np.matmul(grad, np.swapaxes(bd, -1, -2)))
+                    if b.requires_grad:
+                        b.apply_grad(np.matmul(np.swapaxes(ad, -1, -2), grad))
+                elif ad.ndim == 1 and bd.ndim == 1:
+                    if a.requires_grad:
+                        a.apply_grad(grad * bd)
+                    if b.requires_grad:
+                        b.apply_grad(grad * ad)
+                elif ad.ndim == 1:
+                    if a.requires_grad:
+                        a.apply_grad(np.matmul(grad, np.swapaxes(bd, -1, -2)))
+                    if b.requires_grad:
+                        b.apply_grad(np.outer(ad, grad))
+                else:
+                    if a.requires_grad:
+                        a.apply_grad(np.outer(grad, bd))
+                    if b.requires_grad:
+                        b.apply_grad(np.matmul(np.swapaxes(ad, -1, -2), grad))
+        out.grad_fn = grad_fn
+        return out
+
+    # ---- reductions ------------------------------------------------------------------------------
+    @staticmethod
+    def _axis_of(args, kwargs):
+        return kwargs.get("axis", None) if len(args) == 0 else args[0]
+
+    def _reduce(self, op, args, kwargs, scale_fn):
+        axis = self._axis_of(args, kwargs)
+        keepdims = kwargs.get("keepdims", args[1] if len(args) > 1 else False)
+        xp = self.xp
+        value = getattr(xp, op)(self.data, axis=axis, keepdims=keepdims)
+        out = Tensor._wrap(value, (self, axis), op, self.requires_grad, self.device)
+
+        def grad_fn(a: "Tensor", axis, grad):
+            if not a.requires_grad:
+                return
+            if grad.ndim != a.data.ndim and axis is not None:
+                grad = xp.expand_dims(grad, axis)
+            a.apply_grad(scale_fn(a, axis, xp.ones_like(a.data) * grad))
+        out.grad_fn = grad_fn
+        return out
+
+    @staticmethod
+    def _count(a, axis):
+        shape = a.data.shape
+        if axis is None:
+            return int(np.prod(shape))
+        axes = axis if isinstance(axis, (tuple, list)) else (axis,)
+        return int(np.prod([shape[i] for i in axes]))
+
+    def sum(self, *args, **kwargs):
+        return self._reduce("sum", args, kwargs, lambda a, axis, g: g)
+
+    def mean(self, *args, **kwargs):
+        return self._reduce("mean", args, kwargs, lambda a, axis, g: g / Tensor._count(a, axis))
+
+    def var(self, *args, **kwargs):  # ddof = 0
+        xp = self.xp
+        return self._reduce("var", args, kwargs,
+                            lambda a, axis, g: g * 2 * (a.data - xp.mean(a.data, axis=axis, keepdims=True))
+                            / Tensor._count(a, axis))
+
+    def _extremum(self, op, axis, keepdims):
+        xp = self.xp
+        fn = getattr(xp, op)
+        out = Tensor._wrap(fn(self.data, axis=axis, keepdims=keepdims), (self, axis), op, self.requires_grad, self.device)
+
+        def grad_fn(a: "Tensor", axis, grad):
+            if not a.requires_grad:
+                return
+            if grad.ndim != a.data.ndim and axis is not None:
+                grad = xp.expand_dims(grad, axis)
+            a.apply_grad(grad * (a.data == fn(a.data, axis=axis, keepdims=True)))
+        out.grad_fn = grad_fn
+        return out
+
+    def max(self, axis=None, keepdims=False):
+        return self._extremum("max", axis, keepdims)
+
+    def min(self, axis=None, keepdims=False):
+        return self._extremum("min", axis, keepdims)
+
+    # ---- element-wise math -------------------------------------------------------------------------
+    def sqrt(self):
+        return self._unary("sqrt", self.xp.sqrt(self.data), lambda a, g: g * 0.5 * a.data ** -0.5)
+
+    def log(self):
+        return self._unary("log", self.xp.log(self.data), lambda a, g: g * 1 / a.data)
+
+    def exp(self):
+        xp = self.xp
+        return self._unary("exp", xp.exp(self.data), lambda a, g: g * xp.exp(a.data))
+
+    def tanh(self):
+        xp = self.xp
+        return self._unary("tanh", xp.tanh(self.data), lambda a, g: g * (1 - xp.tanh(a.data) ** 2))
+
+    def sin(self):
+        xp = self.xp
+        return self._unary("sin", xp.sin(self.data), lambda a, g: g * xp.cos(a.data))
+
+    def cos(self):
+        xp = self.xp
+        return self._unary("cos", xp.cos(self.data), lambda a, g: g * -xp.sin(a.data))
+
+    def abs(self):
+        xp = self.xp
+        return self._unary("abs", xp.abs(self.data), lambda a, g: g * xp.sign(a.data))
+
+    def __neg__(self):
+        return self._unary("neg", -self.data, lambda a, g: -g)
+
+    def __pos__(self):
+        return self._unary("pos", self.data, lambda a, g: g)
+
+    # ---- shape ops -------------------------------------------------------------------------------------
+    def concatenate(self, *tensors, axis=0):
+        tensors = tuple(self.ensure_tensor(t) for t in tensors)
+        parts = (self,) + tensors
+        xp = self.xp
+        rg = any(p.requires_grad for p in parts)
+        out = Tensor._wrap(xp.concatenate([p.data for p in parts], axis=axis), parts + (axis,), "concatenate", rg,
+                           self.device)
+
+        def grad_fn(*args, grad):
+            *ins, ax = args
+            start = 0
+            for p in ins:
+                n = p.data.shape[ax]
+                if p.requires_grad:
+                    idx = [slice(None)] * grad.ndim
+                    idx[ax] = slice(start, start + n)
+                    p.apply_grad(grad[tuple(idx)])
+                start += n
+        out.grad_fn = grad_fn
+        return out
+
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 else shape
+        if isinstance(shape, int):
+            shape = (shape,)
+        out = Tensor._wrap(self.data.reshape(tuple(shape)), (self,), "reshape", self.requires_grad, self.device, cast=False)
+
+        def grad_fn(a: "Tensor", grad):
+            if a.requires_grad:
+                a.apply_grad(grad.reshape(tuple(a.data.shape)))
+        out.grad_fn = grad_fn
+        return out
+
+    def transpose(self, *axes):
+        axes = axes[0] if len(axes) == 1 else axes
+        if axes is None or (hasattr(axes, "__len__") and len(axes) == 0):
+            axes = tuple(range(self.data.ndim))[::-1]
+        axes = tuple(axes)
+        xp = self.xp
+        out = Tensor._wrap(xp.transpose(self.data, axes), (self, axes), "transpose", self.requires_grad, self.device)
+
+        def grad_fn(a: "Tensor", axes, grad):
+            # NB: like the reference (autograd.py:618-620) the gradient is permuted by `axes` again,
+            # which is the inverse permutation only for involutions such as (0,2,1,3)/(0,1,3,2).
+            if a.requires_grad:
+                a.apply_grad(xp.transpose(grad, axes))
+        out.grad_fn = grad_fn
+        return out
+
+    def swapaxes(self, axis1, axis2):
+        xp = self.xp
+        out = Tensor._wrap(xp.swapaxes(self.data, axis1, axis2), (self, axis1, axis2), "swapaxes", self.requires_grad,
+                           self.device)
+
+        def grad_fn(a: "Tensor", axis1, axis2, grad):
+            if a.requires_grad:
+                a.apply_grad(xp.swapaxes(grad, axis1, axis2))
+        out.grad_fn = grad_fn
+        return out
+
+    def flip(self, axis):
+        if axis is None:
+            axis = tuple(range(self.data.ndim))
+        xp = self.xp
+        out = Tensor._wrap(xp.flip(self.data, axis), (self, axis), "flip", self.requires_grad, self.device)
+
+        def grad_fn(a: "Tensor", axis, grad):
+            if a.requires_grad:
+                a.apply_grad(xp.flip(grad, axis))
+        out.grad_fn = grad_fn
+        return out
+
+    def where(self, condition, t):
+        """``where(condition, self, t)`` (autograd.py:658-684)."""
+        condition = self.ensure_tensor(condition)
+        t = self.ensure_tensor(t)
+        rg = self.requires_grad or t.requires_grad
+        xp = self.xp
+        cond = condition.data != 0 if self.device == "cuda" else condition.data
+        out = Tensor._wrap(xp.where(cond, self.data, t.data), (self, condition, t) if rg else None, "where", rg,
+                           self.device)
+        if rg:
+            def grad_fn(a: "Tensor", condition: "Tensor", b: "Tensor", grad):
+                c = condition.data != 0 if a.device == "cuda" else condition.data
+                if a.requires_grad:
+                    a.apply_grad(xp.where(c, grad, xp.zeros_like(grad)))
+                if b.requires_grad:
+                    b.apply_grad(xp.where(c, xp.zeros_like(grad), grad))
+            out.grad_fn = grad_fn
+        return out
+
+    # ---- comparisons (non-differentiable, float32 0/1 results like the reference) -----------------------
+    def _compare(self, t, op, fn):
+        t = self.ensure_tensor(t)
+        return Tensor._wrap(fn(self.data, t.data), None, op, False, self.device)
+
+    def equal(self, t): return self._compare(t, "equal", lambda a, b: a == b)
+    def not_equal(self, t): return self._compare(t, "not_equal", lambda a, b: a != b)
+    def greater(self, t): return self._compare(t, "greater", lambda a, b: a > b)
+    def greater_equal(self, t): return self._compare(t, "greater_equal", lambda a, b: a >= b)
+    def less(self, t): return self._compare(t, "less", lambda a, b: a < b)
+    def less_equal(self, t): return self._compare(t, "less_equal", lambda a, b: a <= b)
+    def logical_and(self, t): return self._compare(t, "logical_and", lambda a, b: self.xp.logical_and(a, b))
+    def logical_or(self, t): return self._compare(t, "logical_or", lambda a, b: self.xp.logical_or(a, b))
+    def logical_not(self): return Tensor._wrap(self.xp.logical_not(self.data), None, "logical_not", False, self.device)
+
+    __eq__ = equal  # type: ignore[assignment]
+    __ne__ = not_equal  # type: ignore[assignment]
+    __gt__ = greater
+    __ge__ = greater_equal
+    __lt__ = less
+    __le__ = less_equal
+    __and__ = logical_and
+    __or__ = logical_or
+    __hash__ = object.__hash__
+
+    def __invert__(self): return self.logical_not()
+    def __abs__(self): return self.abs()
+    def __add__(self, t): return self.add(t)
+    def __sub__(self, t): return self.sub(t)
+    def __mul__(self, t): return self.mul(t)
+    def __truediv__(self, t): return self.div(t)
+    def __matmul__(self, t): return self.matmul(t)
+    def __pow__(self, t): return self.power(t)
+    def __radd__(self, t): return self.ensure_tensor(t).add(self)
+    def __rsub__(self, t): return self.ensure_tensor(t).sub(self)
+    def __rmul__(self, t): return self.ensure_tensor(t).mul(self)
+    def __rtruediv__(self, t): return self.ensure_tensor(t).div(self)
+    def __rmatmul__(self, t): return self.ensure_tensor(t).matmul(self)
+    def __rpow__(self, t): return self.ensure_tensor(t).power(self)
+
+    def __repr__(self):
+        return f"Tensor({self.data}, requires_grad={self.requires_grad}, dtype={self.dtype}, device={self.device})"
+
+    # ---- indexing ------------------------------------------------------------------------------------------
+    def _index(self, index):
+        """Indices may contain Tensors / NumPy arrays; on "cuda" array indices are moved to the device."""
+        def conv(i):
+            if isinstance(i, Tensor):
+                i = i.data
+            if self.device == "cuda" and isinstance(i, np.ndarray):
+                i = self.xp.array(i, dtype=np.int64 if i.dtype != np.bool_ else np.bool_)
+            elif self.device == "cuda" and _be.is_device_array(i) and i.dtype not in (_be.torch.int64, _be.torch.bool):
+                i = i.to(_be.torch.int64)
+            elif self.device == "cpu" and isinstance(i, np.ndarray) and i.dtype.kind == "f":
+                i = i.astype(np.int64)
+            return i
+        if isinstance(index, tuple):
+            return tuple(conv(i) for i in index)
+        return conv(index)
+
+    def __getitem__(self, index):
+        index = self._index(index)
+        xp = self.xp
+        out = Tensor._wrap(self.data[index], (self, index), "getitem", self.requires_grad, self.device, cast=False)
+
+        def grad_fn(a: "Tensor", index, grad):
+            if a.requires_grad:
+                # assignment, not accumulation: duplicate indices keep the last write (autograd.py:909-910)
+                full = xp.zeros_like(a.data)
+                full[index] = grad
+                a.apply_grad(full)
+        out.grad_fn = grad_fn
+        return out
+
+    def __setitem__(self, key, value):
+        if self.requires_grad:
+            raise RuntimeError("Cannot assign values to a tensor with requires_grad=True")
+        value = self.ensure_tensor(value)
+        self.data[self._index(key)] = value.data
+
+    def __array__(self, dtype=None, copy=None):
+        host = _be.to_host(self.data)
+        return host.astype(dtype, copy=False) if dtype is not None else host
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    @property
+    def shape(self) -> tuple:
+        return tuple(self.data.shape)
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    @property
+    def dtype(self):
+        d = self.data.dtype
+        return d if isinstance(d, np.dtype) else _be.to_numpy_dtype(d)
+
+    @property
+    def ndim(self) -> int:
+        return self.data.ndim
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.data.shape))
+
+    # ---- backward --------------------------------------------------------------------------------------------
+    def backward(self, grad=None):
+        if not self.requires_grad:
+            return
+        xp = self.xp
+        if grad is None:
+            grad = xp.ones_like(self.data)
+        elif isinstance(grad, Tensor):
+            grad = grad.data
+        if not _is_arr(grad) or (self.device == "cuda" and isinstance(grad, np.ndarray)):
+            grad = xp.array(grad, dtype=self.dtype)
+        elif self.device == "cpu":
+            grad = np.array(grad, dtype=self.dtype)
+        self.apply_grad(grad)
+
+        # iterative post-order DFS over `.args` (the reference recurses, autograd.py:982-999)
+        tape, seen = [], {id(self)}
+        stack = [(self, 0)]
+        while stack:
+            node, i = stack.pop()
+            children = node.args if node.args is not None else ()
+            if node.args is None:
+                continue  # leaves never enter the tape
+            advanced = False
+            while i < len(children):
+                c = children[i]
+                i += 1
+                if isinstance(c, Tensor) and c.requires_grad and id(c) not in seen:
+                    seen.add(id(c))
+                    stack.append((node, i))
+                    stack.append((c, 0))
+                    advanced = True
+                    break
+            if not advanced:
+                tape.append(node)
+        for v in reversed(tape):
+            v.grad_fn(*v.args, grad=v.grad)
+
+
+def _no_grad_fn(*args, **kwargs):
+    return None

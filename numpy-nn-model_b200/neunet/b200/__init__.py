@@ -1,0 +1,521 @@
+"""ctypes binding of ``libneunet_b200.so`` (C-ABI: ``include/neunet_b200.h``) for torch CUDA tensors.
+
+This is the seam the reference's ``neunet/nn/experimental`` wrappers occupy
+(``experimental/utils.py:64-85`` ``load_cuda_function`` / ``to_pointer`` / ``call_cuda_function``):
+device pointers are taken from ``tensor.data_ptr()``, every output and scratch buffer is allocated
+here (torch caching allocator) and the current torch stream is passed as the trailing
+``cudaStream_t``. There is NO fallback: if the shared library is missing, was built for another
+architecture, or a call returns a non-zero status, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get(
+    "NEUNET_B200_LIB", os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libneunet_b200.so")))
+
+PREC_BF16, PREC_BF16X3 = 0, 1
+ACT_NONE, ACT_SWISH = 0, 1
+OPT_ADAM_L2, OPT_ADAMW = 0, 1
+
+_PREC_NAMES = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+_state = {"prec": _PREC_NAMES[os.environ.get("NEUNET_B200_PREC", "bf16x3").lower()], "weights_epoch": 0}
+
+
+def set_precision(name: str) -> None:
+    """"bf16": one bf16 tensor-core product (throughput mode, ~2e-3 rel. vs fp32);
+    "bf16x3": hi/lo split, three products (parity mode, ~1e-5 rel.)."""
+    _state["prec"] = _PREC_NAMES[name.lower()]
+
+
+def get_precision() -> str:
+    return {v: k for k, v in _PREC_NAMES.items()}[_state["prec"]]
+
+
+class precision:
+    """Context manager: ``with b200.precision("bf16"): ...``"""
+
+    def __init__(self, name):
+        self.name, self.prev = name, None
+
+    def __enter__(self):
+        self.prev = get_precision()
+        set_precision(self.name)
+
+    def __exit__(self, *exc):
+        set_precision(self.prev)
+
+
+class nnb_conv2d_desc(ctypes.Structure):
+    _fields_ = [("B", c_int64), ("Cin", c_int64), ("H", c_int64), ("W", c_int64), ("Cout", c_int64),
+                ("kh", c_int64), ("kw", c_int64), ("stride", c_int32 * 2), ("pad", c_int32 * 4),
+                ("dil", c_int32 * 2)]
+
+
+_I64x4 = c_int64 * 4
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "nnb_last_error": (c_char_p, []),
+    "nnb_version": (c_int, []),
+    "nnb_device_check": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "nnb_launch_count": (c_uint64, []),
+    "nnb_launch_count_reset": (None, []),
+    "nnb_linear_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
+    "nnb_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                   c_int, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "nnb_weight_staged_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "nnb_stage_weight": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "nnb_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
+    "nnb_matmul_forward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_int64,
+                                   c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_size_t,
+                                   c_void_p]),
+    "nnb_matmul_backward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_void_p,
+                                    c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int,
+                                    c_void_p, c_size_t, c_void_p]),
+    "nnb_conv2d_out_shape": (c_int, [POINTER(nnb_conv2d_desc), POINTER(c_int64), POINTER(c_int64)]),
+    "nnb_conv2d_workspace_bytes": (c_size_t, [POINTER(nnb_conv2d_desc), c_int, c_int]),
+    "nnb_conv2d_forward": (c_int, [POINTER(nnb_conv2d_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p, c_size_t, c_void_p]),
+    "nnb_conv2d_backward": (c_int, [POINTER(nnb_conv2d_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "nnb_swish_forward": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "nnb_swish_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "nnb_softmax_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "nnb_softmax_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "nnb_rmsnorm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                    c_float, c_void_p]),
+    "nnb_rmsnorm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "nnb_rmsnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "nnb_adamw_create": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(c_void_p),
+                                 POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_void_p]),
+    "nnb_adamw_set_grads": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
+    "nnb_adamw_step": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_int64, c_int,
+                               c_float, c_void_p]),
+    "nnb_adamw_destroy": (c_int, [c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_device_ok = set()
+
+
+def lib():
+    """Load (once) and return the ctypes library. Raises if it is missing -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libneunet_b200.so not found at {LIB_PATH}. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C numpy-nn-model_b200/csrc`. "
+                'device="cuda" has no fallback path.')
+        dll = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(dll, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = dll
+    return _lib
+
+
+def last_error() -> str:
+    return lib().nnb_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")
+
+
+def require_device():
+    """The kernels are sm_100a-only; anything else is an error, not a slow path."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('device="cuda" needs a CUDA device (B200); no CPU fallback exists')
+    dev = torch.cuda.current_device()
+    if dev not in _device_ok:
+        sm, ma, mi = c_int(), c_int(), c_int()
+        _check(lib().nnb_device_check(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)), "nnb_device_check")
+        _device_ok.add(dev)
+    return dev
+
+
+def launch_count() -> int:
+    return int(lib().nnb_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().nnb_launch_count_reset()
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _f32c(t):
+    """fp32, C-contiguous (the reference wrappers call ascontiguousarray, softmax.py:59-62)."""
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- workspace: one growing scratch buffer per (device, stream) -------------------------------
+_workspaces = {}
+
+
+def _workspace(nbytes: int):
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        # grow geometrically; stream-ordered reuse is safe because every kernel of a call is
+        # enqueued on this same stream before the next call touches the buffer
+        size = int(max(nbytes, 1 << 20) * (1.25 if buf is not None else 1.0))
+        buf = torch.empty(size, dtype=torch.uint8, device="cuda")
+        _workspaces[key] = buf
+    return buf
+
+
+# ---- weight staging cache ------------------------------------------------------------------------
+class _StagedWeight:
+    __slots__ = ("buf", "key")
+
+
+def weights_changed() -> None:
+    """Called by optimizers that update parameters through this library (torch's version counter
+    cannot see those writes)."""
+    _state["weights_epoch"] += 1
+
+
+def _staged_weight(owner, w2d: torch.Tensor, rows: int, cols: int):
+    """bf16 planes of a weight matrix, converted once per optimizer step. `owner` is the Parameter
+    (any object that can hold an attribute); None disables caching."""
+    prec = _state["prec"]
+    key = (w2d.data_ptr(), w2d._version, _state["weights_epoch"], prec, rows, cols)
+    cached = getattr(owner, "_b200_staged", None) if owner is not None else None
+    if cached is not None and cached.key == key:
+        return cached.buf
+    L = lib()
+    nbytes = L.nnb_weight_staged_bytes(rows, cols, prec)
+    if cached is not None and cached.buf.numel() >= nbytes:
+        buf = cached.buf
+    else:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _check(L.nnb_stage_weight(_ptr(w2d), rows, cols, prec, _ptr(buf), _stream()), "nnb_stage_weight")
+    if owner is not None:
+        sw = _StagedWeight()
+        sw.buf, sw.key = buf, key
+        try:
+            owner._b200_staged = sw
+        except AttributeError:
+            pass
+    return buf
+
+
+# ---- nn.Linear -------------------------------------------------------------------------------------
+def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=None):
+    """O = act(x . w^T + bias); x: (..., K), w: (N, K), bias: (1, N) or None.
+    Returns (O, Z) with Z the pre-activation when save_z (else None)."""
+    require_device()
+    L = lib()
+    N, K = w.shape
+    lead = tuple(x.shape[:-1])
+    x2 = _f32c(x).reshape(-1, K)
+    M = x2.shape[0]
+    w = _f32c(w)
+    out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    z = torch.empty((M, N), dtype=torch.float32, device="cuda") if save_z else None
+    b = _f32c(bias).reshape(-1) if bias is not None else None
+    prec = _state["prec"]
+    wst = _staged_weight(owner, w, N, K)
+    wsb = L.nnb_linear_workspace_bytes(M, K, N, prec, 0)
+    ws = _workspace(wsb)
+    _check(L.nnb_linear_forward(_ptr(x2), _ptr(w), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta), prec,
+                                _ptr(wst), _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward")
+    out = out.reshape(lead + (N,))
+    if z is not None:
+        z = z.reshape(lead + (N,))
+    return out, z
+
+
+def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, need_db=True, owner=None):
+    """Returns (dX like x, dW (N,K), db (1,N)) -- dX / db None when not requested."""
+    require_device()
+    L = lib()
+    N, K = w.shape
+    x2 = _f32c(x).reshape(-1, K)
+    M = x2.shape[0]
+    g2 = _f32c(grad).reshape(-1, N)
+    w = _f32c(w)
+    dx = torch.empty((M, K), dtype=torch.float32, device="cuda") if need_dx else None
+    dw = torch.empty((N, K), dtype=torch.float32, device="cuda")
+    db = torch.empty((1, N), dtype=torch.float32, device="cuda") if need_db else None
+    z2 = _f32c(z).reshape(-1, N) if z is not None else None
+    prec = _state["prec"]
+    wst = _staged_weight(owner, w, N, K) if need_dx else None
+    wsb = L.nnb_linear_workspace_bytes(M, K, N, prec, 1)
+    ws = _workspace(wsb)
+    _check(L.nnb_linear_backward(_ptr(x2), _ptr(w), _ptr(z2), _ptr(g2), _ptr(dx), _ptr(dw), _ptr(db), M, K, N, act,
+                                 float(beta), prec, _ptr(wst), _ptr(ws), ws.numel(), _stream()),
+           "nnb_linear_backward")
+    if dx is not None:
+        dx = dx.reshape(x.shape)
+    return dx, dw, db
+
+
+# ---- Tensor.matmul -----------------------------------------------------------------------------------
+def _as4(t, batch_shape):
+    """View an (..., R, C) tensor as 4-D [b0, b1, R, C] element strides, broadcasting leading dims to
+    `batch_shape` (stride 0). Copies only if more than two non-trivial batch dims cannot be merged."""
+    R, C = t.shape[-2], t.shape[-1]
+    lead = t.shape[:-2]
+    full = tuple(batch_shape)
+    exp = t.expand(full + (R, C)) if tuple(lead) != full else t
+    if len(full) > 2:
+        try:
+            exp = exp.view((-1,) + (R, C))  # succeeds when the batch dims are mergeable
+        except RuntimeError:
+            exp = exp.contiguous().view((-1, R, C))
+    while exp.ndim < 4:
+        exp = exp.unsqueeze(0)
+    return exp
+
+
+def _strides4(t):
+    return _I64x4(*[int(s) for s in t.stride()])
+
+
+def _matmul_norm(a, b):
+    """Normalise NumPy matmul operand ranks to 4-D batched views. Returns
+    (a4, b4, (b0, b1, M, K, N), out_shape)."""
+    a_vec, b_vec = a.ndim == 1, b.ndim == 1
+    if a_vec:
+        a = a.unsqueeze(0)
+    if b_vec:
+        b = b.unsqueeze(1)
+    if a.shape[-1] != b.shape[-2]:
+        raise ValueError(f"matmul: shapes {tuple(a.shape)} and {tuple(b.shape)} not aligned")
+    batch = torch.broadcast_shapes(a.shape[:-2], b.shape[:-2])
+    M, K, N = a.shape[-2], a.shape[-1], b.shape[-1]
+    a4, b4 = _as4(a, batch), _as4(b, batch)
+    out_shape = tuple(batch) + (M, N)
+    if a_vec:
+        out_shape = out_shape[:-2] + (N,)
+    if b_vec:
+        out_shape = out_shape[:-1] if not a_vec else out_shape[:-1]
+    return a4, b4, (a4.shape[0], a4.shape[1], M, K, N), out_shape, tuple(batch)
+
+
+def matmul(a, b, alpha=1.0):
+    """``xp.matmul`` for device arrays (neunet/autograd.py:199), any NumPy-legal rank combination."""
+    require_device()
+    L = lib()
+    a = a if a.dtype == torch.float32 else a.to(torch.float32)
+    b = b if b.dtype == torch.float32 else b.to(torch.float32)
+    if a.ndim == 0 or b.ndim == 0:
+        raise ValueError("matmul: scalar operands are not allowed")
+    a4, b4, (b0, b1, M, K, N), out_shape, _ = _matmul_norm(a, b)
+    out = torch.empty((b0, b1, M, N), dtype=torch.float32, device="cuda")
+    prec = _state["prec"]
+    ws = _workspace(L.nnb_matmul_workspace_bytes(b0, b1, M, K, N, prec, 0))
+    _check(L.nnb_matmul_forward(_ptr(a4), _strides4(a4), _ptr(b4), _strides4(b4), _ptr(out), b0, b1, M, K, N,
+                                float(alpha), prec, _ptr(ws), ws.numel(), _stream()), "nnb_matmul_forward")
+    return out.reshape(out_shape)
+
+
+def matmul_backward(a, b, grad, need_da=True, need_db=True, alpha=1.0):
+    """(dA, dB) for matrix x matrix operands, shaped like the BROADCAST operands (the caller's
+    apply_grad un-broadcasts, neunet/autograd.py:85-93, 948-962)."""
+    require_device()
+    L = lib()
+    a4, b4, (b0, b1, M, K, N), _, batch = _matmul_norm(a, b)
+    g4 = _f32c(grad).reshape(b0, b1, M, N)
+    da = torch.empty((b0, b1, M, K), dtype=torch.float32, device="cuda") if need_da else None
+    db = torch.empty((b0, b1, K, N), dtype=torch.float32, device="cuda") if need_db else None
+    prec = _state["prec"]
+    ws = _workspace(L.nnb_matmul_workspace_bytes(b0, b1, M, K, N, prec, 1))
+    _check(L.nnb_matmul_backward(_ptr(a4), _strides4(a4), _ptr(b4), _strides4(b4), _ptr(g4), _ptr(da), _ptr(db),
+                                 b0, b1, M, K, N, float(alpha), prec, _ptr(ws), ws.numel(), _stream()),
+           "nnb_matmul_backward")
+    if da is not None:
+        da = da.reshape(batch + (M, K))
+    if db is not None:
+        db = db.reshape(batch + (K, N))
+    return da, db
+
+
+# ---- nn.Conv2d -------------------------------------------------------------------------------------
+def _conv_desc(x_shape, w_shape, stride, pad4, dil):
+    d = nnb_conv2d_desc()
+    d.B, d.Cin, d.H, d.W = [int(v) for v in x_shape]
+    d.Cout, _, d.kh, d.kw = [int(v) for v in w_shape]
+    d.stride[0], d.stride[1] = int(stride[0]), int(stride[1])
+    for i in range(4):
+        d.pad[i] = int(pad4[i])
+    d.dil[0], d.dil[1] = int(dil[0]), int(dil[1])
+    return d
+
+
+def conv2d_out_hw(x_shape, w_shape, stride, pad4, dil):
+    d = _conv_desc(x_shape, w_shape, stride, pad4, dil)
+    ho, wo = c_int64(), c_int64()
+    _check(lib().nnb_conv2d_out_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)), "nnb_conv2d_out_shape")
+    return int(ho.value), int(wo.value)
+
+
+def conv2d_forward(x, w, bias, stride, pad4, dil):
+    require_device()
+    L = lib()
+    x, w = _f32c(x), _f32c(w)
+    if x.shape[1] != w.shape[1]:
+        raise ValueError(f"conv2d: input has {x.shape[1]} channels, weight expects {w.shape[1]}")
+    d = _conv_desc(x.shape, w.shape, stride, pad4, dil)
+    ho, wo = conv2d_out_hw(x.shape, w.shape, stride, pad4, dil)
+    out = torch.empty((x.shape[0], w.shape[0], ho, wo), dtype=torch.float32, device="cuda")
+    b = _f32c(bias).reshape(-1) if bias is not None else None
+    prec = _state["prec"]
+    ws = _workspace(L.nnb_conv2d_workspace_bytes(ctypes.byref(d), prec, 0))
+    _check(L.nnb_conv2d_forward(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(out), prec, _ptr(ws), ws.numel(),
+                                _stream()), "nnb_conv2d_forward")
+    return out
+
+
+def conv2d_backward(x, w, grad, stride, pad4, dil, need_dx=True, need_db=True):
+    require_device()
+    L = lib()
+    x, w, grad = _f32c(x), _f32c(w), _f32c(grad)
+    d = _conv_desc(x.shape, w.shape, stride, pad4, dil)
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty((w.shape[0],), dtype=torch.float32, device="cuda") if need_db else None
+    prec = _state["prec"]
+    ws = _workspace(L.nnb_conv2d_workspace_bytes(ctypes.byref(d), prec, 1))
+    _check(L.nnb_conv2d_backward(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(grad), _ptr(dx), _ptr(dw), _ptr(db), prec,
+                                 _ptr(ws), ws.numel(), _stream()), "nnb_conv2d_backward")
+    return dx, dw, db
+
+
+# ---- stand-alone epilogue ops ---------------------------------------------------------------------------
+def swish_forward(x, beta=1.0):
+    require_device()
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    if x.numel():
+        _check(lib().nnb_swish_forward(_ptr(x), _ptr(y), x.numel(), float(beta), _stream()), "nnb_swish_forward")
+    return y
+
+
+def swish_backward(x, grad, beta=1.0):
+    require_device()
+    x, grad = _f32c(x), _f32c(grad)
+    dx = torch.empty_like(x)
+    if x.numel():
+        _check(lib().nnb_swish_backward(_ptr(x), _ptr(grad), _ptr(dx), x.numel(), float(beta), _stream()),
+               "nnb_swish_backward")
+    return dx
+
+
+def _softmax_dims(shape, axis):
+    axis = axis % len(shape)
+    outer = int(np.prod(shape[:axis], dtype=np.int64))
+    inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    return outer, int(shape[axis]), inner
+
+
+def softmax_forward(x, axis=-1):
+    require_device()
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    outer, n, inner = _softmax_dims(x.shape, axis)
+    _check(lib().nnb_softmax_forward(_ptr(x), _ptr(y), outer, n, inner, _stream()), "nnb_softmax_forward")
+    return y
+
+
+def softmax_backward(y, grad, axis=-1):
+    require_device()
+    y, grad = _f32c(y), _f32c(grad)
+    dx = torch.empty_like(y)
+    outer, n, inner = _softmax_dims(y.shape, axis)
+    _check(lib().nnb_softmax_backward(_ptr(y), _ptr(grad), _ptr(dx), outer, n, inner, _stream()),
+           "nnb_softmax_backward")
+    return dx
+
+
+def rmsnorm_forward(x, w, b=None, eps=1e-6):
+    """Returns (Y, X_std) with X_std shaped (..., 1). X_norm is not materialised: the backward
+    recomputes X / X_std (one fewer [rows, cols] round-trip through HBM)."""
+    require_device()
+    x = _f32c(x)
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty_like(x)
+    std = torch.empty(x.shape[:-1] + (1,), dtype=torch.float32, device="cuda")
+    _check(lib().nnb_rmsnorm_forward(_ptr(x), _ptr(_f32c(w)), _ptr(_f32c(b)) if b is not None else None, _ptr(y),
+                                     _ptr(std), None, rows, cols, float(eps), _stream()), "nnb_rmsnorm_forward")
+    return y, std
+
+
+def rmsnorm_backward(grad, x, w, std, need_db=False):
+    require_device()
+    L = lib()
+    x, grad = _f32c(x), _f32c(grad)
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    dx = torch.empty_like(x)
+    dw = torch.empty((cols,), dtype=torch.float32, device="cuda")
+    db = torch.empty((cols,), dtype=torch.float32, device="cuda") if need_db else None
+    ws = _workspace(L.nnb_rmsnorm_workspace_bytes(rows, cols))
+    _check(L.nnb_rmsnorm_backward(_ptr(grad), _ptr(x), _ptr(_f32c(w)), _ptr(_f32c(std)), None, _ptr(dx), _ptr(dw),
+                                  _ptr(db), rows, cols, _ptr(ws), ws.numel(), _stream()), "nnb_rmsnorm_backward")
+    return dx, dw, db
+
+
+# ---- multi-tensor Adam / AdamW ---------------------------------------------------------------------------
+class FusedAdam:
+    """Owns an ``nnb_adamw`` handle for a fixed list of fp32 parameter tensors."""
+
+    def __init__(self, params, ms, vs):
+        require_device()
+        self.n = len(params)
+        self._keep = (list(params), list(ms), list(vs))  # keep storage alive
+        arr = c_void_p * self.n
+        self._p = arr(*[t.data_ptr() for t in params])
+        self._m = arr(*[t.data_ptr() for t in ms])
+        self._v = arr(*[t.data_ptr() for t in vs])
+        self._sizes = (c_int64 * self.n)(*[t.numel() for t in params])
+        self._h = c_void_p()
+        for t in list(params) + list(ms) + list(vs):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("FusedAdam: parameters and moments must be contiguous fp32")
+        _check(lib().nnb_adamw_create(ctypes.byref(self._h), self.n, self._p, None, self._m, self._v, self._sizes,
+                                      _stream()), "nnb_adamw_create")
+
+    def step(self, grads, lr, betas, eps, weight_decay, t, mode, grad_scale=1.0):
+        """grads: list of tensors or None (None = skipped, optim.py:21-22)."""
+        self._grads_keep = grads
+        arr = (c_void_p * self.n)(*[(g.data_ptr() if g is not None else None) for g in grads])
+        L = lib()
+        _check(L.nnb_adamw_set_grads(self._h, arr, _stream()), "nnb_adamw_set_grads")
+        _check(L.nnb_adamw_step(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                int(t), mode, float(grad_scale), _stream()), "nnb_adamw_step")
+        weights_changed()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().nnb_adamw_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,90 @@
+"""nn.Linear: Y = X . W^T + b  (reference: neunet/nn/layers/linear.py:13-61).
+
+On ``device="cuda"`` forward, dgrad, wgrad and the bias gradient run on the tcgen05 GEMM through
+``neunet.b200`` (the seam the reference's ``CUDALinear`` uses, experimental/linear/linear.py:122-215);
+``LinearSwish`` is the fused Linear+Swish layer (reference: ``CUDALinearSwish``,
+experimental/linear_swish/linear_swish_cutlass.py:198-278): Swish is the GEMM epilogue and
+swish' is folded into the staging of dO in backward.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ... import tensor as _tensor
+from ...autograd import Tensor
+from ..modules import Module
+from ..parameter import Parameter
+
+
+class _LinearTensor(Tensor):
+    """Result tensor with the static backward of linear.py:17-24."""
+
+    def __init__(self, data, args, op, device):
+        t = Tensor._wrap(data, args, op, True, device)
+        self.__dict__.update(t.__dict__)
+        self.grad_fn = _linear_grad_fn
+
+
+def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, grad):
+    if X.device == "cuda":
+        from ... import b200
+        dx, dw, db = b200.linear_backward(X.data, weight.data, grad, z=Z, act=act, beta=beta,
+                                          need_dx=X.requires_grad, need_db=bias is not None, owner=weight)
+        if dx is not None:
+            X.apply_grad(dx)
+        weight.apply_grad(dw)
+        if bias is not None:
+            bias.apply_grad(db)
+        return
+    if act:  # Swish backward on the saved pre-activation
+        s = 1 / (1 + np.exp(-beta * Z))
+        f = Z * s
+        grad = grad * (beta * f + s * (1 - beta * f))
+    X.apply_grad(np.matmul(grad, weight.data))
+    weight.apply_grad(np.swapaxes(np.matmul(np.swapaxes(X.data, -1, -2), grad), -1, -2))
+    if bias is not None:
+        bias.apply_grad(np.sum(grad, axis=0, keepdims=True))
+
+
+class Linear(Module):
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device="cpu"):
+        self.in_features = in_features
+        self.out_features = out_features
+        stdv = 1.0 / np.sqrt(in_features)
+        # same draws, same order, from the global np.random (linear.py:34-43)
+        self.weight = Parameter(_tensor(np.random.uniform(-stdv, stdv, (out_features, in_features)), dtype=np.float32))
+        self.bias = (Parameter(_tensor(np.random.uniform(-stdv, stdv, (1, out_features)), dtype=np.float32))
+                     if bias else None)
+        self.to(device)
+
+    _act, _beta = 0, 1.0
+
+    def forward(self, X: Tensor) -> Tensor:
+        if not isinstance(X, Tensor):
+            raise TypeError("Input must be a tensor")
+        if X.device != self.device:
+            raise ValueError("Tensors must be on the same device")
+        b = self.bias
+        if self.device == "cuda":
+            from ... import b200
+            O, Z = b200.linear_forward(X.data, self.weight.data, b.data if b is not None else None,
+                                       act=self._act, beta=self._beta, save_z=bool(self._act), owner=self.weight)
+        else:
+            Z = np.matmul(X.data, self.weight.data.T)
+            if b is not None:
+                Z = Z + b.data
+            O = Z / (1 + np.exp(-self._beta * Z)) if self._act else Z
+            if not self._act:
+                Z = None
+        return _LinearTensor(O, (X, self.weight, b, Z, self._act, self._beta), "linear", self.device)
+
+    def __call__(self, X):
+        return self.forward(X)
+
+
+class LinearSwish(Linear):
+    """Linear followed by Swish(beta) in one pass: ``swish(X . W^T + b)``."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, beta: float = 1.0, device="cpu"):
+        self._act, self._beta = 1, float(beta)
+        super().__init__(in_features, out_features, bias=bias, device=device)

@@ -1,0 +1,221 @@
+"""Layers that are NOT on the dense hot path but that the named examples need so they run
+unchanged: Embedding, Dropout, BatchNorm2d, MaxPool2d, Flatten, LayerNorm.
+They stay on the array back-end (NumPy / torch element-wise ops), as the reference keeps them on
+NumPy / CuPy. Semantics follow neunet/nn/layers/{embedding,dropout,batchnorm2d,maxpool2d,flatten,
+layernorm}.py, including the inverted BatchNorm momentum (batchnorm2d.py:87-88) and Embedding's
+assignment-style backward through ``__getitem__`` (autograd.py:909-910)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ... import tensor as _tensor
+from ...autograd import Tensor
+from ..modules import Module
+from ..parameter import Parameter
+
+
+class Embedding(Module):
+    def __init__(self, num_embeddings: int, embedding_dim: int, device="cpu"):
+        self.num_embeddings = num_embeddings
+        self.embedding_dim = embedding_dim
+        self.weight = Parameter(_tensor(np.random.randn(num_embeddings, embedding_dim), dtype=np.float32))
+        self.to(device)
+
+    def forward(self, X: Tensor) -> Tensor:
+        idx = X.data if isinstance(X, Tensor) else X
+        if isinstance(idx, np.ndarray):
+            idx = idx.astype(np.int32)
+        return self.weight[idx]
+
+    def __call__(self, X):
+        return self.forward(X)
+
+
+class _StaticTensor(Tensor):
+    """Generic result tensor carrying a hand-written grad_fn."""
+
+    def __init__(self, data, args, op, device, grad_fn):
+        t = Tensor._wrap(data, args, op, True, device)
+        self.__dict__.update(t.__dict__)
+        self.grad_fn = grad_fn
+
+
+def _dropout_grad(X: Tensor, mask, grad):
+    X.apply_grad(grad * mask)
+
+
+class Dropout(Module):
+    def __init__(self, p: float = 0.5):
+        self.p = p
+        self.scale = 1 / (1 - p)
+        self.training = True
+
+    def forward(self, X: Tensor) -> Tensor:
+        if not isinstance(X, Tensor):
+            raise TypeError("Input must be a tensor")
+        if self.training:
+            mask = X.xp.random.binomial(1, 1 - self.p, size=tuple(X.data.shape))
+            mask = (mask.astype(np.float32) if isinstance(mask, np.ndarray) else mask) * self.scale
+        else:
+            mask = 1
+        return _StaticTensor(X.data * mask, (X, mask), "dropout", X.device, _dropout_grad)
+
+    def __call__(self, X):
+        return self.forward(X)
+
+    def train(self, mode=True):
+        self.training = mode
+
+    def eval(self):
+        self.training = False
+
+
+def _bn2d_grad(X: Tensor, weight, bias, xc, inv, affine, grad):
+    xp = X.xp
+    n = X.data.shape[0] * X.data.shape[2] * X.data.shape[3]
+    ax = (0, 2, 3)
+    inv4 = inv.reshape(1, -1, 1, 1)
+    xhat = xc * inv4
+    w4 = weight.data.reshape(1, -1, 1, 1) if affine else 1
+    dxh = w4 * grad
+    # d/dx of (x - mean) * inv with batch statistics (batchnorm2d.py:20-43)
+    s1 = xp.sum(dxh, axis=ax, keepdims=True)
+    s2 = xp.sum(dxh * xhat, axis=ax, keepdims=True)
+    X.apply_grad(inv4 * (dxh - s1 / n - xhat * s2 / n))
+    if affine:
+        weight.apply_grad(xp.sum(grad * xhat, axis=ax).reshape(tuple(weight.data.shape)))
+        bias.apply_grad(xp.sum(grad, axis=ax).reshape(tuple(bias.data.shape)))
+
+
+class BatchNorm2d(Module):
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, affine: bool = True, device="cpu"):
+        self.num_features = num_features
+        self.eps = eps
+        self.momentum = momentum
+        self.affine = affine
+        self.running_mean = Parameter(_tensor(np.zeros((1, num_features)), dtype=np.float32), requires_grad=False)
+        self.running_var = Parameter(_tensor(np.ones((1, num_features)), dtype=np.float32), requires_grad=False)
+        self.weight = Parameter(_tensor(np.ones((1, num_features)), dtype=np.float32)) if affine else None
+        self.bias = Parameter(_tensor(np.zeros((1, num_features)), dtype=np.float32)) if affine else None
+        self.training = True
+        self.to(device)
+
+    def forward(self, X: Tensor) -> Tensor:
+        if not isinstance(X, Tensor):
+            raise TypeError("Input must be a tensor")
+        if X.device != self.device:
+            raise ValueError("Tensors must be on the same device")
+        xp = X.xp
+        if self.training:
+            mean = xp.mean(X.data, axis=(0, 2, 3))
+            var = xp.var(X.data, axis=(0, 2, 3))
+            # reference convention: momentum weights the OLD value (batchnorm2d.py:87-88)
+            self.running_mean.data = self.momentum * self.running_mean.data + (1 - self.momentum) * mean
+            self.running_var.data = self.momentum * self.running_var.data + (1 - self.momentum) * var
+        else:
+            mean = self.running_mean.data.reshape(-1)
+            var = self.running_var.data.reshape(-1)
+        xc = X.data - mean.reshape(1, -1, 1, 1)
+        inv = 1 / xp.sqrt(var + self.eps)
+        O = xc * inv.reshape(1, -1, 1, 1)
+        if self.affine:
+            O = self.weight.data.reshape(1, -1, 1, 1) * O + self.bias.data.reshape(1, -1, 1, 1)
+        return _StaticTensor(O, (X, self.weight, self.bias, xc, inv, self.affine), "batchnorm2d", self.device, _bn2d_grad)
+
+    def __call__(self, X):
+        return self.forward(X)
+
+    def train(self, mode=True):
+        self.training = mode
+
+    def eval(self):
+        self.training = False
+
+
+def _pair(v):
+    return v if isinstance(v, tuple) else (v, v)
+
+
+def _maxpool_grad(X: Tensor, idx, out_shape, grad):
+    xp = X.xp
+    B, C, H, W = X.data.shape
+    flat = xp.zeros((B * C, H * W), dtype=np.float32)
+    g = grad.reshape(B * C, -1)
+    if X.device == "cuda":
+        flat.scatter_add_(1, idx.reshape(B * C, -1), g)
+    else:
+        np.add.at(flat, (np.arange(B * C)[:, None], idx.reshape(B * C, -1)), g)
+    X.apply_grad(flat.reshape(B, C, H, W))
+
+
+class MaxPool2d(Module):
+    def __init__(self, kernel_size, stride=None, padding=0, dilation=1):
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride) if stride else self.kernel_size
+        self.padding = _pair(padding)
+        self.dilation = _pair(dilation)
+
+    def forward(self, X: Tensor) -> Tensor:
+        B, C, H, W = X.shape
+        kh, kw = self.kernel_size
+        s, p, d = self.stride, self.padding, self.dilation
+        ho = (H + 2 * p[0] - d[0] * (kh - 1) - 1) // s[0] + 1
+        wo = (W + 2 * p[1] - d[1] * (kw - 1) - 1) // s[1] + 1
+        if X.device == "cuda":
+            import torch.nn.functional as F
+            out, idx = F.max_pool2d(X.data, self.kernel_size, s, p, d, return_indices=True)
+        else:
+            xpad = np.pad(X.data, ((0, 0), (0, 0), (p[0], p[0]), (p[1], p[1])), constant_values=-np.inf)
+            out = np.full((B, C, ho, wo), -np.inf, dtype=np.float32)
+            idx = np.zeros((B, C, ho, wo), dtype=np.int64)
+            oy, ox = np.arange(ho)[:, None] * s[0], np.arange(wo)[None, :] * s[1]
+            for k in range(kh):
+                for l in range(kw):
+                    win = xpad[:, :, k * d[0]: k * d[0] + (ho - 1) * s[0] + 1: s[0], l * d[1]: l * d[1] + (wo - 1) * s[1] + 1: s[1]]
+                    better = win > out
+                    out = np.where(better, win, out)
+                    flat = (oy + k * d[0] - p[0]) * W + (ox + l * d[1] - p[1])
+                    idx = np.where(better, flat[None, None], idx)
+        return _StaticTensor(out, (X, idx, (ho, wo)), "maxpool2d", X.device, _maxpool_grad)
+
+    def __call__(self, X):
+        return self.forward(X)
+
+
+class Flatten(Module):
+    def __init__(self, start_dim=1, end_dim=-1):
+        self.start_dim, self.end_dim = start_dim, end_dim
+
+    def forward(self, X: Tensor) -> Tensor:
+        shape = X.shape
+        end = self.end_dim % len(shape)
+        return X.reshape(*shape[: self.start_dim], int(np.prod(shape[self.start_dim: end + 1])), *shape[end + 1:])
+
+    def __call__(self, X):
+        return self.forward(X)
+
+
+class LayerNorm(Module):
+    """y = (x - mean) / sqrt(var + eps) * w + b over the trailing `normalized_shape` dims, written
+    with differentiable Tensor ops (dynamic backward)."""
+
+    def __init__(self, normalized_shape, eps: float = 1e-5, elementwise_affine: bool = True, bias: bool = True, device="cpu"):
+        self.normalized_shape = (normalized_shape,) if isinstance(normalized_shape, int) else tuple(normalized_shape)
+        self.eps = eps
+        self.weight = Parameter(_tensor(np.ones(self.normalized_shape), dtype=np.float32)) if elementwise_affine else None
+        self.bias = Parameter(_tensor(np.zeros(self.normalized_shape), dtype=np.float32)) if elementwise_affine and bias else None
+        self.to(device)
+
+    def forward(self, X: Tensor) -> Tensor:
+        axes = tuple(range(-len(self.normalized_shape), 0))
+        mean = X.mean(axis=axes, keepdims=True)
+        var = X.var(axis=axes, keepdims=True)
+        out = (X - mean) / (var + self.eps).sqrt()
+        if self.weight is not None:
+            out = out * self.weight
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+    def __call__(self, X):
+        return self.forward(X)

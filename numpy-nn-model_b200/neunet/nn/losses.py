@@ -1,0 +1,103 @@
+"""Losses (not contractions; they stay on the array back-end as differentiable Tensor ops).
+Semantics: neunet/nn/losses.py -- MSELoss 8-22, BCELoss 25-56, CrossEntropyLoss = LogSoftmax(axis=1)
++ NLLLoss 59-126 (ignore_index, class weights, mean over non-ignored targets), L1Loss 129-148."""
+from __future__ import annotations
+
+import numpy as np
+
+from ..autograd import Tensor
+from .activations import LogSoftmax
+from .modules import Module
+
+
+def _check(y_pred, y_true):
+    if not isinstance(y_pred, Tensor) or not isinstance(y_true, Tensor):
+        raise TypeError("Input values must be tensors")
+    if y_pred.device != y_true.device:
+        raise ValueError("Tensors must be on the same device")
+
+
+class MSELoss(Module):
+    def __init__(self):
+        pass
+
+    def forward(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
+        _check(y_pred, y_true)
+        return y_pred.sub(y_true).power(2).sum().div(int(np.prod(y_pred.shape)))
+
+
+class L1Loss(Module):
+    def __init__(self, reduction="mean"):
+        self.reduction = reduction
+
+    def forward(self, y_pred, y_true):
+        _check(y_pred, y_true)
+        loss = y_pred.sub(y_true).abs()
+        return loss.mean() if self.reduction == "mean" else loss.sum() if self.reduction == "sum" else loss
+
+
+class BCELoss(Module):
+    def __init__(self, weight=None, reduction="mean"):
+        self.weight = weight
+        self.reduction = reduction
+
+    def forward(self, y_pred, y_true):
+        _check(y_pred, y_true)
+        loss = y_true.mul(y_pred.log()).add((1.0 - y_true).mul((1.0 - y_pred).log()))
+        if self.weight is not None:
+            loss = loss.mul(self.weight)
+        loss = loss.mul(-1)
+        return loss.mean() if self.reduction == "mean" else loss.sum() if self.reduction == "sum" else loss
+
+
+class NLLLoss(Module):
+    def __init__(self, weight=None, ignore_index=-100, reduction="mean"):
+        self.weight = weight
+        self.ignore_index = ignore_index
+        self.reduction = reduction
+
+    def forward(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
+        _check(y_pred, y_true)
+        if y_true.dtype not in (np.int16, np.int32, np.int64):
+            raise TypeError("Target must be of int dtype")
+        xp = y_pred.xp
+        n_cls = y_pred.shape[1]
+        w = self.weight if self.weight is not None else xp.ones((n_cls,), dtype=np.float32)
+        if isinstance(w, Tensor):
+            w = w.data
+        if tuple(w.shape) != (n_cls,):
+            raise ValueError("Weight shape must be equal to number of classes")
+        if y_pred.ndim == 2:
+            y_pred = y_pred[..., None]
+        tgt = y_true.data
+        if tgt.ndim == 1:
+            tgt = tgt[..., None]
+        if y_pred.device == "cuda":
+            tgt = tgt.to(dtype=__import__("torch").int64)
+        keep = tgt != self.ignore_index
+        safe = xp.where(keep, tgt, xp.zeros_like(tgt))
+        # pick y_pred[b, tgt[b, ...], ...] (losses.py:107-110)
+        lead = xp.arange(tgt.shape[0], dtype=np.int64).reshape((-1,) + (1,) * (tgt.ndim - 1))
+        rest = [xp.arange(s, dtype=np.int64).reshape((1,) * (i + 1) + (-1,) + (1,) * (tgt.ndim - i - 2))
+                for i, s in enumerate(tgt.shape[1:])]
+        picked = y_pred[(lead, safe, *rest)]
+        wk = w[safe] * keep
+        loss = -picked * Tensor._wrap(wk, None, None, False, y_pred.device)
+        if self.reduction == "mean":
+            return (loss / float(xp.sum(wk))).sum() if y_pred.device == "cpu" else (loss / Tensor._wrap(xp.sum(wk), None, None, False, "cuda")).sum()
+        if self.reduction == "sum":
+            return loss.sum()
+        return loss
+
+
+class CrossEntropyLoss(Module):
+    def __init__(self, weight=None, ignore_index=-100, reduction="mean"):
+        self.weight = weight
+        self.ignore_index = ignore_index
+        self.reduction = reduction
+        self.log_softmax = LogSoftmax(axis=1)
+        self.nll_loss = NLLLoss(weight, ignore_index, reduction)
+
+    def forward(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
+        _check(y_pred, y_true)
+        return self.nll_loss(self.log_softmax(y_pred), y_true)
