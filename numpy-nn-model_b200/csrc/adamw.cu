@@ -20,7 +20,7 @@ struct nnb_adamw {
     long long* d_sizes = nullptr;
     int* d_blk_tensor = nullptr;
     int* d_blk_chunk = nullptr;
-    std::vector<const float*> h_g;
+    const float** h_g = nullptr;  // pinned: the table upload must be capturable in a CUDA graph
 };
 
 namespace nnb {
@@ -114,8 +114,8 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     nnb_adamw* o = new nnb_adamw();
     o->n = n;
     o->nblocks = (int)bt.size();
-    o->h_g.assign(n, nullptr);
-    if (g) for (int i = 0; i < n; ++i) o->h_g[i] = g[i];
+    NNB_CUDA_OK(cudaHostAlloc((void**)&o->h_g, n * sizeof(float*), cudaHostAllocDefault));
+    for (int i = 0; i < n; ++i) o->h_g[i] = g ? g[i] : nullptr;
     NNB_CUDA_OK(cudaMalloc(&o->d_p, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_g, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_m, n * sizeof(float*)));
@@ -124,7 +124,7 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_tensor, bt.size() * sizeof(int)));
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_chunk, bc.size() * sizeof(int)));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_p, p, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
-    NNB_CUDA_OK(cudaMemcpyAsync(o->d_g, o->h_g.data(), n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaMemcpyAsync(o->d_g, o->h_g, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_m, m, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_v, v, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_sizes, sz.data(), n * sizeof(long long), cudaMemcpyHostToDevice, stream));
@@ -141,8 +141,8 @@ int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stre
     for (int i = 0; i < opt->n; ++i) same = same && (opt->h_g[i] == g[i]);
     if (same) return NNB_OK;
     for (int i = 0; i < opt->n; ++i) opt->h_g[i] = g[i];
-    // h_g stays alive in the handle; pageable-source async copies are staged by the driver at call time
-    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_g, opt->h_g.data(), opt->n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    // h_g is pinned and lives in the handle, so this copy is legal inside stream capture
+    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_g, opt->h_g, opt->n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     return NNB_OK;
 }
 
@@ -179,6 +179,7 @@ int nnb_adamw_destroy(nnb_adamw* opt) {
     if (!opt) return NNB_OK;
     cudaFree(opt->d_p); cudaFree((void*)opt->d_g); cudaFree(opt->d_m); cudaFree(opt->d_v);
     cudaFree(opt->d_sizes); cudaFree(opt->d_blk_tensor); cudaFree(opt->d_blk_chunk);
+    cudaFreeHost((void*)opt->h_g);
     delete opt;
     return NNB_OK;
 }

@@ -298,7 +298,7 @@ using namespace nnb;
 extern "C" {
 
 int nnb_conv2d_out_shape(const nnb_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
-    Geo g;
+    Geo g{};
     int rc = make_geo(d, &g);
     if (rc) return rc;
     if (Ho) *Ho = g.Ho;
@@ -307,7 +307,7 @@ int nnb_conv2d_out_shape(const nnb_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
 }
 
 size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backward) {
-    Geo g;
+    Geo g{};
     if (make_geo(d, &g)) return 0;
     if (use_direct(g)) return 256;
     const size_t p = planes(prec);
@@ -332,7 +332,7 @@ int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt
                        cudaStream_t stream) {
     NNB_REQUIRE(X && Wt && O, "nnb_conv2d_forward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_forward: bad prec");
-    Geo g;
+    Geo g{};
     int rc = make_geo(d, &g);
     if (rc) return rc;
     if (use_direct(g)) {
@@ -373,7 +373,7 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
                         size_t workspace_bytes, cudaStream_t stream) {
     NNB_REQUIRE(X && Wt && dO && dW, "nnb_conv2d_backward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_backward: bad prec");
-    Geo g;
+    Geo g{};
     int rc = make_geo(d, &g);
     if (rc) return rc;
     const int64_t HWo = (int64_t)g.Ho * g.Wo;

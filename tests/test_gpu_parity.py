@@ -34,7 +34,7 @@ def host(a):
 
 
 def relerr(got, ref):
-    got, ref = host(got).astype(np.float64), np.asarray(ref, dtype=np.float64)
+    got, ref = host(got).astype(np.float64), host(ref).astype(np.float64)
     assert got.shape == ref.shape, (got.shape, ref.shape)
     return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
 
