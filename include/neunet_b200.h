@@ -71,16 +71,24 @@ void nnb_launch_count_reset(void);
  * bias, Z, dX, db may be NULL (dX NULL skips the dgrad GEMM).
  * W_staged: NULL, or a buffer filled by nnb_stage_weight() for the CURRENT contents of W
  * (lets the caller convert weights to bf16 once per optimizer step instead of once per call).
+ * X_staged_out (forward): NULL, or a 256-byte aligned buffer of nnb_weight_staged_bytes(M, K, prec)
+ * bytes that receives the bf16 planes of X; hand it back as X_staged to nnb_linear_backward to skip
+ * re-converting X there (X itself may then be NULL). nnb_stage_weight() converts ANY row-major
+ * fp32 matrix, not only weights; nnb_linear_forward_staged() runs the GEMM on two staged operands.
  */
 size_t nnb_linear_workspace_bytes(int64_t M, int64_t K, int64_t N, int prec, int backward);
 int nnb_linear_forward(const float* X, const float* W, const float* bias, float* O, float* Z,
                        int64_t M, int64_t K, int64_t N, int act, float beta, int prec,
-                       const void* W_staged, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream);
+                       const void* W_staged, void* X_staged_out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+int nnb_linear_forward_staged(const void* X_staged, const void* W_staged, const float* bias, float* O,
+                              float* Z, int64_t M, int64_t K, int64_t N, int act, float beta,
+                              int prec, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream);
 int nnb_linear_backward(const float* X, const float* W, const float* Z, const float* dO,
                         float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
-                        float beta, int prec, const void* W_staged, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream);
+                        float beta, int prec, const void* W_staged, const void* X_staged,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t nnb_weight_staged_bytes(int64_t rows, int64_t cols, int prec);
 int nnb_stage_weight(const float* W, int64_t rows, int64_t cols, int prec, void* dst,
                      cudaStream_t stream);
@@ -157,7 +165,7 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
  * nnb_adamw_create uploads the pointer table ONCE (the reference re-uploads it every step,
  * fused_adamw_multitensor.cu:288-291); p/g/m/v are arrays of n device pointers, sizes in elements.
  * Tensors whose g[i] is NULL are skipped, like `if param.grad is None: continue` (optim.py:21-22).
- * step: 1-based step count t. Hyper-parameters are doubles: 1-beta, 1-beta^t and lr*wd are formed in
+ * step: 1-based step count t (or 0, see nnb_adamw_set_step). Hyper-parameters are doubles: 1-beta, 1-beta^t and lr*wd are formed in
  * double on the host and rounded once to fp32, exactly where the reference forms them as Python
  * floats before NumPy casts them to the array dtype. grad_scale multiplies every gradient first (1/world_size after
  * a sum all-reduce; 1.0 otherwise).
@@ -169,6 +177,10 @@ int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stre
 int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, int mode, float grad_scale,
                    cudaStream_t stream);
+/* CUDA-graph support: pass step = 0 to nnb_adamw_step to use (and first advance) a step counter
+ * kept in device memory, so replaying a captured step keeps the bias corrections moving;
+ * nnb_adamw_set_step() seeds that counter (number of steps already taken). */
+int nnb_adamw_set_step(nnb_adamw* opt, int64_t step, cudaStream_t stream);
 int nnb_adamw_destroy(nnb_adamw* opt);
 
 #ifdef __cplusplus

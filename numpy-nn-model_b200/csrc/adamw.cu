@@ -5,6 +5,7 @@
 // HBM-bound: per element 16 B read (p, g, m, v) + 12 B written (p, m, v), 16-byte accesses.
 // The pointer tables and the block -> (tensor, chunk) map live on the device and are uploaded once
 // at create time; only the gradient pointer table is refreshed when gradients move.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -21,6 +22,7 @@ struct nnb_adamw {
     int* d_blk_tensor = nullptr;
     int* d_blk_chunk = nullptr;
     const float** h_g = nullptr;  // pinned: the table upload must be capturable in a CUDA graph
+    long long* d_t = nullptr;     // device-resident step counter (CUDA-graph replays advance it)
 };
 
 namespace nnb {
@@ -31,6 +33,7 @@ constexpr int ADAM_CHUNK = ADAM_THREADS * 4 * 4;  // 8192 elements per block: 4 
 
 struct AdamScalars {
     float lr, b1, b2, one_m_b1, one_m_b2, bc1, bc2, eps, lr_wd, wd, gscale;
+    double beta1, beta2;  // for the device-side bias correction
     int mode;
 };
 
@@ -52,7 +55,21 @@ __global__ void __launch_bounds__(ADAM_THREADS)
 adamw_multi_kernel(float* const* __restrict__ P, const float* const* __restrict__ G,
                    float* const* __restrict__ Mm, float* const* __restrict__ V,
                    const long long* __restrict__ sizes, const int* __restrict__ blk_tensor,
-                   const int* __restrict__ blk_chunk, const AdamScalars s) {
+                   const int* __restrict__ blk_chunk, AdamScalars s,
+                   const long long* __restrict__ d_t) {
+    if (d_t != nullptr) {
+        // graph mode: the step count lives on the device, so a replayed graph keeps advancing the
+        // bias corrections 1 - beta^t (formed in double, rounded once, like the host path)
+        __shared__ float bc[2];
+        if (threadIdx.x == 0) {
+            const double tt = (double)(*d_t);
+            bc[0] = (float)(1.0 - pow(s.beta1, tt));
+            bc[1] = (float)(1.0 - pow(s.beta2, tt));
+        }
+        __syncthreads();
+        s.bc1 = bc[0];
+        s.bc2 = bc[1];
+    }
     const int t = blk_tensor[blockIdx.x];
     const float* g = G[t];
     if (g == nullptr) return;  // `if param.grad is None: continue` (optim.py:21-22)
@@ -90,6 +107,8 @@ adamw_multi_kernel(float* const* __restrict__ P, const float* const* __restrict_
     }
 }
 
+__global__ void adam_advance_step_kernel(long long* d_t) { *d_t += 1; }
+
 }  // namespace
 }  // namespace nnb
 
@@ -121,6 +140,8 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     NNB_CUDA_OK(cudaMalloc(&o->d_m, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_v, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_sizes, n * sizeof(long long)));
+    NNB_CUDA_OK(cudaMalloc(&o->d_t, sizeof(long long)));
+    NNB_CUDA_OK(cudaMemsetAsync(o->d_t, 0, sizeof(long long), stream));
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_tensor, bt.size() * sizeof(int)));
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_chunk, bc.size() * sizeof(int)));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_p, p, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
@@ -150,7 +171,7 @@ int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double
                    double weight_decay, int64_t step, int mode, float grad_scale,
                    cudaStream_t stream) {
     NNB_REQUIRE(opt, "nnb_adamw_step: null handle");
-    NNB_REQUIRE(step >= 1, "nnb_adamw_step: step must be >= 1");
+    NNB_REQUIRE(step >= 0, "nnb_adamw_step: step must be >= 1, or 0 to use the device-resident counter");
     NNB_REQUIRE(mode == NNB_OPT_ADAM_L2 || mode == NNB_OPT_ADAMW, "nnb_adamw_step: bad mode");
     AdamScalars s;
     // Scalars are formed in double exactly where the reference forms them in Python floats, then
@@ -160,18 +181,33 @@ int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double
     s.b2 = (float)beta2;
     s.one_m_b1 = (float)(1.0 - beta1);
     s.one_m_b2 = (float)(1.0 - beta2);
-    s.bc1 = (float)(1.0 - std::pow(beta1, (double)step));
-    s.bc2 = (float)(1.0 - std::pow(beta2, (double)step));
+    s.bc1 = (float)(1.0 - std::pow(beta1, (double)std::max<int64_t>(step, 1)));
+    s.bc2 = (float)(1.0 - std::pow(beta2, (double)std::max<int64_t>(step, 1)));
+    s.beta1 = beta1;
+    s.beta2 = beta2;
     s.eps = (float)eps;
     s.lr_wd = (float)(lr * weight_decay);
     s.wd = (float)weight_decay;
     s.gscale = grad_scale;
     s.mode = mode;
+    if (step == 0) {
+        adam_advance_step_kernel<<<1, 1, 0, stream>>>(opt->d_t);
+        count_launch();
+    }
     adamw_multi_kernel<<<opt->nblocks, ADAM_THREADS, 0, stream>>>(opt->d_p, opt->d_g, opt->d_m, opt->d_v,
                                                                   opt->d_sizes, opt->d_blk_tensor,
-                                                                  opt->d_blk_chunk, s);
+                                                                  opt->d_blk_chunk, s,
+                                                                  step == 0 ? opt->d_t : nullptr);
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_adamw_set_step(nnb_adamw* opt, int64_t step, cudaStream_t stream) {
+    NNB_REQUIRE(opt && step >= 0, "nnb_adamw_set_step: bad arguments");
+    const long long v = step;
+    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_t, &v, sizeof(v), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaStreamSynchronize(stream));
     return NNB_OK;
 }
 
@@ -180,6 +216,7 @@ int nnb_adamw_destroy(nnb_adamw* opt) {
     cudaFree(opt->d_p); cudaFree((void*)opt->d_g); cudaFree(opt->d_m); cudaFree(opt->d_v);
     cudaFree(opt->d_sizes); cudaFree(opt->d_blk_tensor); cudaFree(opt->d_blk_chunk);
     cudaFreeHost((void*)opt->h_g);
+    cudaFree(opt->d_t);
     delete opt;
     return NNB_OK;
 }

@@ -79,8 +79,8 @@ size_t nnb_linear_workspace_bytes(int64_t M, int64_t K, int64_t N, int prec, int
 
 int nnb_linear_forward(const float* X, const float* W, const float* bias, float* O, float* Z,
                        int64_t M, int64_t K, int64_t N, int act, float beta, int prec,
-                       const void* W_staged, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream) {
+                       const void* W_staged, void* X_staged_out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
     NNB_REQUIRE(X && W && O, "nnb_linear_forward: null X/W/O");
     NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_forward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_forward: bad prec");
@@ -88,8 +88,16 @@ int nnb_linear_forward(const float* X, const float* W, const float* bias, float*
     Bump ws(workspace, workspace_bytes);
     GemmProblem g;
     g.M = M; g.N = N; g.K = K;
-    int rc = stage_into(ws, view2d(X, M, K, K), prec, STAGE_COPY, nullptr, 0.f, nullptr, stream, &g.A.st);
-    if (rc) return rc;
+    int rc;
+    if (X_staged_out) {  // stage X into the caller's buffer so the backward pass can reuse it
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(X_staged_out) & 255) == 0, "nnb_linear_forward: X_staged_out must be 256-byte aligned");
+        rc = nnb_stage_weight(X, M, K, prec, X_staged_out, stream);
+        if (rc) return rc;
+        g.A.st = weight_view(X_staged_out, M, K, prec);
+    } else {
+        rc = stage_into(ws, view2d(X, M, K, K), prec, STAGE_COPY, nullptr, 0.f, nullptr, stream, &g.A.st);
+        if (rc) return rc;
+    }
     if (W_staged) {
         g.B.st = weight_view(W_staged, N, K, prec);
     } else {
@@ -103,11 +111,30 @@ int nnb_linear_forward(const float* X, const float* W, const float* bias, float*
     return gemm(g, stream);
 }
 
+int nnb_linear_forward_staged(const void* X_staged, const void* W_staged, const float* bias, float* O,
+                              float* Z, int64_t M, int64_t K, int64_t N, int act, float beta,
+                              int prec, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream) {
+    NNB_REQUIRE(X_staged && W_staged && O, "nnb_linear_forward_staged: null pointer");
+    NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_forward_staged: non-positive dimension");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_forward_staged: bad prec");
+    Bump ws(workspace, workspace_bytes);
+    GemmProblem g;
+    g.M = M; g.N = N; g.K = K;
+    g.A.st = weight_view(X_staged, M, K, prec);
+    g.B.st = weight_view(W_staged, N, K, prec);
+    g.D = O; g.ldd = N;
+    g.epi.bias = bias; g.epi.Z = Z; g.epi.act = act; g.epi.beta = beta;
+    g.splitk_ws_bytes = ws.remaining();
+    g.splitk_ws = static_cast<float*>(ws.take(g.splitk_ws_bytes));
+    return gemm(g, stream);
+}
+
 int nnb_linear_backward(const float* X, const float* W, const float* Z, const float* dO,
                         float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
-                        float beta, int prec, const void* W_staged, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream) {
-    NNB_REQUIRE(X && W && dO && dW, "nnb_linear_backward: null X/W/dO/dW");
+                        float beta, int prec, const void* W_staged, const void* X_staged,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NNB_REQUIRE((X || X_staged) && W && dO && dW, "nnb_linear_backward: null X/W/dO/dW");
     NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_backward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_backward: bad prec");
     NNB_REQUIRE(act == NNB_ACT_NONE || (act == NNB_ACT_SWISH && Z), "nnb_linear_backward: Swish needs Z");
@@ -117,8 +144,12 @@ int nnb_linear_backward(const float* X, const float* W, const float* Z, const fl
     int rc = stage_into(ws, view2d(dO, M, N, N), prec, act == NNB_ACT_SWISH ? STAGE_SWISH_BWD : STAGE_COPY,
                         Z, beta, db, stream, &gs);
     if (rc) return rc;
-    rc = stage_into(ws, view2d(X, M, K, K), prec, STAGE_COPY, nullptr, 0.f, nullptr, stream, &xs);
-    if (rc) return rc;
+    if (X_staged) {
+        xs = weight_view(X_staged, M, K, prec);
+    } else {
+        rc = stage_into(ws, view2d(X, M, K, K), prec, STAGE_COPY, nullptr, 0.f, nullptr, stream, &xs);
+        if (rc) return rc;
+    }
     if (dX) {
         if (W_staged) {
             wsd = weight_view(W_staged, N, K, prec);

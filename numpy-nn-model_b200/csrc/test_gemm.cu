@@ -88,8 +88,8 @@ static void test_linear(int64_t M, int64_t K, int64_t N, int prec, int act, unsi
     void* ws; CK(cudaMalloc(&ws, wsb));
     void* wst; CK(cudaMalloc(&wst, nnb_weight_staged_bytes(N, K, prec)));
     NK(nnb_stage_weight(dW, N, K, prec, wst, 0));
-    NK(nnb_linear_forward(dX, dW, db, dO, act ? dZ : nullptr, M, K, N, act, beta, prec, wst, ws, wsb, 0));
-    NK(nnb_linear_backward(dX, dW, act ? dZ : nullptr, dG, dgX, dgW, dgb, M, K, N, act, beta, prec, nullptr, ws, wsb, 0));
+    NK(nnb_linear_forward(dX, dW, db, dO, act ? dZ : nullptr, M, K, N, act, beta, prec, wst, nullptr, ws, wsb, 0));
+    NK(nnb_linear_backward(dX, dW, act ? dZ : nullptr, dG, dgX, dgW, dgb, M, K, N, act, beta, prec, nullptr, nullptr, ws, wsb, 0));
     CK(cudaDeviceSynchronize());
     auto O = host(dO, M * N), gX = host(dgX, M * K), gW = host(dgW, N * K), gb = host(dgb, N);
     std::vector<float> Z;

@@ -68,9 +68,11 @@ _SIGNATURES = {
     "nnb_launch_count_reset": (None, []),
     "nnb_linear_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
     "nnb_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                                   c_int, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                   c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_linear_forward_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                          c_int64, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "nnb_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_int64, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
     "nnb_weight_staged_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "nnb_stage_weight": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
@@ -101,6 +103,7 @@ _SIGNATURES = {
     "nnb_adamw_set_grads": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
     "nnb_adamw_step": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_int64, c_int,
                                c_float, c_void_p]),
+    "nnb_adamw_set_step": (c_int, [c_void_p, c_int64, c_void_p]),
     "nnb_adamw_destroy": (c_int, [c_void_p]),
 }
 
@@ -225,9 +228,10 @@ def _staged_weight(owner, w2d: torch.Tensor, rows: int, cols: int):
 
 
 # ---- nn.Linear -------------------------------------------------------------------------------------
-def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=None):
+def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=None, keep_x_staged=False):
     """O = act(x . w^T + bias); x: (..., K), w: (N, K), bias: (1, N) or None.
-    Returns (O, Z) with Z the pre-activation when save_z (else None)."""
+    Returns (O, Z, x_staged): Z is the pre-activation when save_z (else None); x_staged holds the
+    bf16 planes of x for the backward pass when keep_x_staged (else None)."""
     require_device()
     L = lib()
     N, K = w.shape
@@ -242,15 +246,20 @@ def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=
     wst = _staged_weight(owner, w, N, K)
     wsb = L.nnb_linear_workspace_bytes(M, K, N, prec, 0)
     ws = _workspace(wsb)
+    xst = None
+    if keep_x_staged:
+        xst = torch.empty(L.nnb_weight_staged_bytes(M, K, prec), dtype=torch.uint8, device="cuda")
+        xst._b200_prec = prec
     _check(L.nnb_linear_forward(_ptr(x2), _ptr(w), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta), prec,
-                                _ptr(wst), _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward")
+                                _ptr(wst), _ptr(xst), _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward")
     out = out.reshape(lead + (N,))
     if z is not None:
         z = z.reshape(lead + (N,))
-    return out, z
+    return out, z, xst
 
 
-def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, need_db=True, owner=None):
+def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, need_db=True, owner=None,
+                    x_staged=None):
     """Returns (dX like x, dW (N,K), db (1,N)) -- dX / db None when not requested."""
     require_device()
     L = lib()
@@ -265,14 +274,43 @@ def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, ne
     z2 = _f32c(z).reshape(-1, N) if z is not None else None
     prec = _state["prec"]
     wst = _staged_weight(owner, w, N, K) if need_dx else None
+    if x_staged is not None and getattr(x_staged, "_b200_prec", None) != prec:
+        x_staged = None  # precision changed between forward and backward: convert again
     wsb = L.nnb_linear_workspace_bytes(M, K, N, prec, 1)
     ws = _workspace(wsb)
     _check(L.nnb_linear_backward(_ptr(x2), _ptr(w), _ptr(z2), _ptr(g2), _ptr(dx), _ptr(dw), _ptr(db), M, K, N, act,
-                                 float(beta), prec, _ptr(wst), _ptr(ws), ws.numel(), _stream()),
+                                 float(beta), prec, _ptr(wst), _ptr(x_staged), _ptr(ws), ws.numel(), _stream()),
            "nnb_linear_backward")
     if dx is not None:
         dx = dx.reshape(x.shape)
     return dx, dw, db
+
+
+def time_linear_forward_gemm(x, w, bias=None, act=ACT_NONE, beta=1.0):
+    """Milliseconds (CUDA events on the launching stream) of the forward GEMM ALONE: both operands
+    are staged to bf16 first, then one nnb_linear_forward_staged launch is timed. Used by
+    bench.py's roofline probe."""
+    require_device()
+    L = lib()
+    N, K = w.shape
+    x2 = _f32c(x).reshape(-1, K)
+    M = x2.shape[0]
+    prec = _state["prec"]
+    xs = torch.empty(L.nnb_weight_staged_bytes(M, K, prec), dtype=torch.uint8, device="cuda")
+    wsd = torch.empty(L.nnb_weight_staged_bytes(N, K, prec), dtype=torch.uint8, device="cuda")
+    _check(L.nnb_stage_weight(_ptr(x2), M, K, prec, _ptr(xs), _stream()), "nnb_stage_weight")
+    _check(L.nnb_stage_weight(_ptr(_f32c(w)), N, K, prec, _ptr(wsd), _stream()), "nnb_stage_weight")
+    out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    z = torch.empty((M, N), dtype=torch.float32, device="cuda") if act else None
+    b = _f32c(bias).reshape(-1) if bias is not None else None
+    ws = _workspace(L.nnb_linear_workspace_bytes(M, K, N, prec, 0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _check(L.nnb_linear_forward_staged(_ptr(xs), _ptr(wsd), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta),
+                                       prec, _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward_staged")
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1)
 
 
 # ---- Tensor.matmul -----------------------------------------------------------------------------------
@@ -482,6 +520,58 @@ def rmsnorm_backward(grad, x, w, std, need_db=False):
     return dx, dw, db
 
 
+# ---- whole-step CUDA graphs ---------------------------------------------------------------------------------
+class GraphedStep:
+    """Capture ``fn(*inputs)`` -- typically one whole training step (forward, loss, backward,
+    optimizer.step) -- into a CUDA graph and replay it with new input VALUES.
+
+    B200 runs the named small configs (MLP 784-128-10, conv classifier) in a few microseconds per
+    kernel; the Python tape would otherwise be 10-100x slower than the GPU. ``inputs`` are neunet
+    Tensors on "cuda" whose storage becomes the graph's static input buffers; ``__call__`` copies
+    new host/device data into them and replays. Everything the step launches goes to the capturing
+    stream because every C-ABI call takes torch's current stream. Optimizers must be created (and
+    have taken their first eager step during warm-up) before capture.
+    """
+
+    def __init__(self, fn, inputs, optimizer=None, warmup=3):
+        require_device()
+        self.inputs = list(inputs)
+        self.fn = fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if optimizer is not None and getattr(optimizer, "_fused", None) is not None:
+            optimizer._fused.set_step(optimizer.t)
+        self.optimizer = optimizer
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.inputs)
+        if optimizer is not None:
+            optimizer.t -= 1  # the capture pass itself launched nothing
+
+    def load(self, *arrays, non_blocking=True):
+        """Copy new values (pinned torch tensors / device tensors / NumPy arrays) into the static inputs."""
+        for dst, src in zip(self.inputs, arrays):
+            if isinstance(src, np.ndarray):
+                src = torch.from_numpy(src)
+            dst.data.copy_(src, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        if self.optimizer is not None:
+            self.optimizer.t += 1
+        return self.outputs
+
+    def __call__(self, *arrays):
+        if arrays:
+            self.load(*arrays)
+        return self.replay()
+
+
 # ---- multi-tensor Adam / AdamW ---------------------------------------------------------------------------
 class FusedAdam:
     """Owns an ``nnb_adamw`` handle for a fixed list of fp32 parameter tensors."""
@@ -508,9 +598,15 @@ class FusedAdam:
         arr = (c_void_p * self.n)(*[(g.data_ptr() if g is not None else None) for g in grads])
         L = lib()
         _check(L.nnb_adamw_set_grads(self._h, arr, _stream()), "nnb_adamw_set_grads")
+        if torch.cuda.is_current_stream_capturing():
+            t = 0  # captured step: use the device-resident counter so replays keep advancing it
         _check(L.nnb_adamw_step(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                 int(t), mode, float(grad_scale), _stream()), "nnb_adamw_step")
         weights_changed()
+
+    def set_step(self, t):
+        """Seed the device-resident step counter (steps already taken) before capturing a graph."""
+        _check(lib().nnb_adamw_set_step(self._h, int(t), _stream()), "nnb_adamw_set_step")
 
     def __del__(self):
         try:

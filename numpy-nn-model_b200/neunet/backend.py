@@ -125,6 +125,12 @@ class TorchXP:
             if copy and out.data_ptr() == data.data_ptr():
                 out = out.clone()
             return out
+        if isinstance(data, (bool, int, float, np.generic)) or (isinstance(data, np.ndarray) and data.ndim == 0):
+            # scalars become a device fill (no host->device copy, so it is legal inside graph capture)
+            val = data.item() if hasattr(data, "item") else data
+            if td is None:
+                td = torch.float64 if isinstance(val, float) else (torch.bool if isinstance(val, bool) else torch.int64)
+            return torch.full((), val, dtype=td, device=self.device)
         if isinstance(data, np.ndarray):
             arr = data
         else:
@@ -178,6 +184,8 @@ class TorchXP:
         if isinstance(a, torch.Tensor):
             return a
         dt = like.dtype if isinstance(like, torch.Tensor) else torch.float32
+        if isinstance(a, (bool, int, float)):
+            return torch.full((), a, dtype=dt, device=self.device)
         return torch.as_tensor(a, dtype=dt, device=self.device)
 
     def exp(self, a): return torch.exp(a)

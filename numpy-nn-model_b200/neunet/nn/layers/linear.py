@@ -25,11 +25,12 @@ class _LinearTensor(Tensor):
         self.grad_fn = _linear_grad_fn
 
 
-def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, grad):
+def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, x_staged, grad):
     if X.device == "cuda":
         from ... import b200
         dx, dw, db = b200.linear_backward(X.data, weight.data, grad, z=Z, act=act, beta=beta,
-                                          need_dx=X.requires_grad, need_db=bias is not None, owner=weight)
+                                          need_dx=X.requires_grad, need_db=bias is not None, owner=weight,
+                                          x_staged=x_staged)
         if dx is not None:
             X.apply_grad(dx)
         weight.apply_grad(dw)
@@ -67,16 +68,22 @@ class Linear(Module):
         b = self.bias
         if self.device == "cuda":
             from ... import b200
-            O, Z = b200.linear_forward(X.data, self.weight.data, b.data if b is not None else None,
-                                       act=self._act, beta=self._beta, save_z=bool(self._act), owner=self.weight)
+            # the bf16 planes of X made for the forward GEMM are kept for wgrad (dW = dZ^T . X)
+            O, Z, xst = b200.linear_forward(X.data, self.weight.data, b.data if b is not None else None,
+                                            act=self._act, beta=self._beta, save_z=bool(self._act), owner=self.weight,
+                                            keep_x_staged=self.training_mode())
         else:
+            xst = None
             Z = np.matmul(X.data, self.weight.data.T)
             if b is not None:
                 Z = Z + b.data
             O = Z / (1 + np.exp(-self._beta * Z)) if self._act else Z
             if not self._act:
                 Z = None
-        return _LinearTensor(O, (X, self.weight, b, Z, self._act, self._beta), "linear", self.device)
+        return _LinearTensor(O, (X, self.weight, b, Z, self._act, self._beta, xst), "linear", self.device)
+
+    def training_mode(self):
+        return getattr(self, "training", True)
 
     def __call__(self, X):
         return self.forward(X)

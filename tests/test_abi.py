@@ -57,7 +57,7 @@ def test_no_compute_entry_points(dll):
     # argument validation happens before any CUDA call
     dll.nnb_linear_forward.restype = ctypes.c_int
     assert dll.nnb_linear_forward(None, None, None, None, None, ctypes.c_int64(1), ctypes.c_int64(1), ctypes.c_int64(1),
-                                  0, ctypes.c_float(1), 0, None, None, ctypes.c_size_t(0), None) == 1
+                                  0, ctypes.c_float(1), 0, None, None, None, ctypes.c_size_t(0), None) == 1
     assert b"null" in dll.nnb_last_error()
 
 
