@@ -27,12 +27,14 @@ constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int UMMA_K = 16;
 constexpr int MAX_SEG = 3;
 constexpr int NUM_THREADS = 256;
-constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;
+constexpr int EPI_SCRATCH_BYTES = 4 * 8192;  // per epilogue warp: two 4 KB TMA-store tiles (or the 32x33 transpose scratch)
 constexpr int SMEM_BUDGET = 200 * 1024;  // operand ring budget
 
 struct GemmMaps {
     CUtensorMap a[MAX_SEG];
     CUtensorMap b[MAX_SEG];
+    CUtensorMap d;  // fp32 output, box 32 x 32, 128B swizzle (TMA-store epilogue)
+    CUtensorMap z;  // fp32 pre-activation side output
 };
 
 struct KArgs {
@@ -57,6 +59,8 @@ struct KArgs {
     __nv_bfloat16* D16;
     long long ldd16;
     float* ws;  // split-K partials [split][out_batch][M][N]
+    int tma_store;  // 1: epilogue writes D/Z through TMA (needs 16-byte aligned rows)
+    int bias_vec;   // 1: bias pointer 16-byte aligned (float4 loads)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
@@ -112,6 +116,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
         for (int s = 0; s < p.nseg; ++s) {
             ptx::tma_prefetch_desc(&maps.a[s]);
             ptx::tma_prefetch_desc(&maps.b[s]);
+        }
+        if (p.tma_store) {
+            ptx::tma_prefetch_desc(&maps.d);
+            if (p.Z != nullptr) ptx::tma_prefetch_desc(&maps.z);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -234,7 +242,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp - 4;  // TMEM lane quarter this warp may read
-        float* scratch = epi_scratch + q * (32 * 33);
+        float* scratch = epi_scratch + q * (8192 / 4);
+        uint8_t* tile0 = reinterpret_cast<uint8_t*>(scratch);  // two 1024B-aligned 4 KB tiles
+        int store_parity = 0;
         int local_iter = 0;
         for (int w = blockIdx.x; w < work; w += gridDim.x, ++local_iter) {
             const int split = w / tiles;
@@ -267,6 +277,65 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                     // accumulator fully drained into registers: hand the TMEM buffer back
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                if (p.tma_store && p.splits == 1) {
+                    // ---- fast path: registers -> swizzled smem tile -> TMA store (coalescing, tail
+                    // clipping and the fp32 writes are done by the copy engine, not by LSU traffic)
+                    float x[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = p.alpha * __uint_as_float(v[j]);
+                    if (p.bias != nullptr) {
+                        if (p.bias_per_row) {
+                            const int row = row_base + lane;
+                            const float rb = row < p.M ? p.bias[row] : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] += rb;
+                        } else if (p.bias_vec && col0 + 32 <= p.N) {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldg(b4 + j);
+                                x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
+                        }
+                    }
+                    const bool has_z = p.Z != nullptr;
+                    // with a Z side-output each chunk uses both tiles (wait for all reads);
+                    // otherwise the two tiles double-buffer the D stores
+                    uint8_t* tile_d = has_z ? tile0 : tile0 + store_parity * 4096;
+                    uint8_t* tile_z = tile0 + 4096;
+                    if (lane == 0) {
+                        if (has_z) ptx::tma_store_wait_read<0>(); else ptx::tma_store_wait_read<1>();
+                    }
+                    __syncwarp();
+                    const uint32_t sw = (uint32_t)(lane & 7);
+                    if (has_z) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(tile_z + lane * 128 + ((j ^ sw) << 4)) =
+                                make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                    }
+                    if (p.act != NNB_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act, p.beta);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(tile_d + lane * 128 + ((j ^ sw) << 4)) =
+                            make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_3d(&maps.d, tile_d, col0, row_base, ob);
+                        if (has_z) ptx::tma_store_3d(&maps.z, tile_z, col0, row_base, ob);
+                        ptx::tma_store_commit();
+                    }
+                    store_parity ^= 1;
+                    continue;
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
@@ -310,6 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                 __syncwarp();
             }
         }
+        if (lane == 0) ptx::tma_store_wait_read<0>();  // smem tiles must outlive the bulk stores
     }
 
     ptx::tc_fence_before();
@@ -389,6 +459,23 @@ int encode_map(CUtensorMap* m, const __nv_bfloat16* ptr, int64_t inner, int64_t 
     return NNB_OK;
 }
 
+// fp32 output map for the TMA-store epilogue: box 32 cols x 32 rows x 1 batch.
+int encode_out_map(CUtensorMap* m, const float* ptr, int64_t cols, int64_t rows, int64_t ld,
+                   int64_t batch, int64_t batch_stride) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(NNB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t bs = (batch > 1) ? (cuuint64_t)batch_stride * 4 : (cuuint64_t)rows * ld * 4;
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, bs};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NNB_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+    return NNB_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch(const GemmMaps& maps, const KArgs& ka, int grid, cudaStream_t stream) {
     using C = Cfg<BN>;
@@ -440,25 +527,49 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     const int64_t red_batches = reduce_batch ? g.batch : 1;
     const int sms = num_sms();
 
-    // ---- tile shape: maximise (MMA efficiency of the tile width) x (fill of the last wave)
-    int bn;
-    if (g.force_bn) {
-        bn = g.force_bn;
-    } else {
+    // ---- tile width and split-K factor from a small cycle model (constants from the measured
+    // B200/B300 pacing: UMMA 128xNx16 = max(N/2, 40) cycles, ~100 B/cycle/SM operand fill,
+    // TMA-store epilogue ~160 cycles per 32-column chunk, HBM ~3400 B/cycle chip-wide)
+    const int64_t total_iters_all = ceil_div(g.K, BK) * red_batches;
+    const int nseg_h = x3 ? 3 : 1;
+    const bool tma_ok_h = g.col_group == 0 && (g.ldd % 4) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0;
+    int bn = 0;
+    int64_t splits = 1;
+    {
         const int cands[4] = {256, 128, 64, 32};
-        const double eff[4] = {1.0, 0.92, 0.62, 0.36};
-        double best = -1.0;
-        bn = b_mn ? 64 : 32;
-        for (int i = 0; i < 4; ++i) {
-            const int c = cands[i];
+        const int scand[12] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+        double best = 1e300;
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c = cands[ci];
+            if (g.force_bn && c != g.force_bn) continue;
             if (b_mn && c < 64) continue;
-            if (c > 32 && c / 2 >= g.N) continue;  // half the width already covers N
+            if (!g.force_bn && c > 32 && c / 2 >= g.N && !(b_mn && c == 64)) continue;  // half the width covers N
             const int64_t t = ceil_div(g.M, BM) * ceil_div(g.N, c) * out_batches;
-            double fill = (double)t / (double)(ceil_div(t, sms) * sms);
-            if (t * 2 <= sms) fill = 0.9;  // split-K will spread the reduction instead
-            const double used = (double)g.N / (double)(ceil_div(g.N, c) * c);
-            const double score = eff[i] * fill * used;
-            if (score > best) { best = score; bn = c; }
+            for (int si = 0; si < 12; ++si) {
+                const int64_t sp = scand[si];
+                if (g.force_splits && sp != g.force_splits) continue;
+                if (sp > 1 && (sp > total_iters_all || total_iters_all / sp < 2)) continue;
+                if (sp > 1) {
+                    const size_t need = (size_t)sp * out_batches * g.M * g.N * 4;
+                    if (g.splitk_ws == nullptr || g.splitk_ws_bytes < need) continue;
+                }
+                const double waves = (double)ceil_div(t * sp, sms);
+                const double iters = (double)ceil_div(total_iters_all, sp) * nseg_h;
+                const double mma = iters * 4.0 * std::max(c / 2.0, 40.0);
+                const double fill = iters * (16384.0 + c * 128.0) / 100.0;
+                const double epi = (c / 32) * ((tma_ok_h && sp == 1) ? 160.0 : 1300.0) + 300.0;
+                double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0;
+                if (sp > 1) {
+                    const double out_bytes = (double)g.M * g.N * out_batches * 4.0;
+                    cyc += (2.0 * sp + 1.0) * out_bytes / 3400.0 + 4000.0;
+                }
+                if (cyc < best) { best = cyc; bn = c; splits = sp; }
+            }
+        }
+        if (bn == 0) {
+            if (g.force_splits > 1)
+                return fail(NNB_ERR_WORKSPACE, "gemm: split-K workspace too small for %d splits", g.force_splits);
+            return fail(NNB_ERR_UNSUPPORTED, "gemm: no tile configuration for this problem");
         }
     }
     NNB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad BN %d", bn);
@@ -468,31 +579,8 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     const int64_t tiles = num_m * num_n * out_batches;
     const int64_t kblocks = ceil_div(g.K, BK);
     const int64_t total_iters = kblocks * red_batches;
-
-    // ---- split-K
-    int64_t splits = 1;
-    if (g.force_splits > 0) {
-        splits = g.force_splits;
-    } else if (tiles * 2 <= sms && total_iters >= 8) {
-        splits = std::min<int64_t>(sms / tiles, total_iters / 4);
-        splits = std::min<int64_t>(splits, 64);
-    }
-    splits = std::max<int64_t>(1, std::min(splits, total_iters));
     int64_t ips = ceil_div(total_iters, splits);
     splits = ceil_div(total_iters, ips);
-    if (splits > 1) {
-        const size_t need = (size_t)splits * out_batches * g.M * g.N * 4;
-        if (g.splitk_ws == nullptr || g.splitk_ws_bytes < need) {
-            if (g.force_splits > 0)
-                return fail(NNB_ERR_WORKSPACE, "gemm: split-K workspace too small (%zu < %zu)",
-                            g.splitk_ws_bytes, need);
-            // shrink to what fits
-            splits = g.splitk_ws ? (int64_t)(g.splitk_ws_bytes / ((size_t)out_batches * g.M * g.N * 4)) : 1;
-            splits = std::max<int64_t>(1, splits);
-            ips = ceil_div(total_iters, splits);
-            splits = ceil_div(total_iters, ips);
-        }
-    }
 
     // ---- tensor maps
     GemmMaps maps;
@@ -554,6 +642,20 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     ka.ws = g.splitk_ws;
     if (g.col_group > 0) { ka.col_group = (int)g.col_group; ka.group_stride = g.group_stride; }
     ka.bias_per_row = g.bias_per_row ? 1 : 0;
+    ka.bias_vec = g.epi.bias && (reinterpret_cast<uintptr_t>(g.epi.bias) & 15) == 0;
+    {
+        auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        const int64_t bsd = reduce_batch ? 0 : g.batch_stride_d;
+        bool tma = splits == 1 && g.col_group == 0 && g.epi.D16 == nullptr && ok16(g.D) &&
+                   (g.ldd % 4) == 0 && (out_batches == 1 || (bsd % 4) == 0) &&
+                   (g.epi.Z == nullptr || ok16(g.epi.Z));
+        if (tma) {
+            int rc2 = encode_out_map(&maps.d, g.D, g.N, g.M, g.ldd, out_batches, bsd);
+            if (!rc2 && g.epi.Z) rc2 = encode_out_map(&maps.z, g.epi.Z, g.N, g.M, g.ldd, out_batches, bsd);
+            if (rc2) return rc2;
+        }
+        ka.tma_store = tma ? 1 : 0;
+    }
 
     const int64_t work = tiles * splits;
     const int grid = (int)std::min<int64_t>(work, sms);

@@ -31,12 +31,18 @@ struct StageArgs {
     float* partial;              // [gridDim.z * gridDim.y][cols] column partial sums, or null
     int rows_per_block;
     int vec_ok;
+    int tx;  // threads along columns (power of two <= 128)
 };
 
-// thread -> 4 consecutive columns; block.y loops over a chunk of rows; blockIdx.z = batch.
+// Block = 128 threads arranged as TX (columns, 4 elements each) x TY (rows): wide matrices use
+// TX = 128, narrow ones (e.g. the 4096 x 10 logits gradient) fold rows into the block so no lane
+// idles. blockIdx.y owns a chunk of rows, blockIdx.z = batch. Column partial sums (bias gradient)
+// are reduced over TY in shared memory and written once per block.
 template <bool X3, int OP>
 __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
-    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int TX = a.tx, TY = 128 / a.tx;
+    const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x / TX;
+    const long long c = ((long long)blockIdx.x * TX + tx) * 4;
     const int bz = blockIdx.z;
     const int i0 = bz / (int)a.v.b1, i1 = bz - i0 * (int)a.v.b1;
     const float* src = a.v.ptr + i0 * a.v.s_b0 + i1 * a.v.s_b1;
@@ -46,7 +52,7 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < a.v.cols) {
         const bool full = c + 3 < a.v.cols;
-        for (long long r = r0; r < r1; ++r) {
+        for (long long r = r0 + ty; r < r1; r += TY) {
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             if (full && a.vec_ok) {
                 const float4 t = *reinterpret_cast<const float4*>(src + r * a.v.s_r + c);
@@ -86,11 +92,22 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
                 }
             }
         }
-        if (a.partial != nullptr) {
+    }
+    if (a.partial != nullptr) {
+        __shared__ float red[128 * 4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[(ty * TX + tx) * 4 + j] = cs[j];
+        __syncthreads();
+        if (ty == 0 && c < a.v.cols) {
             float* prow = a.partial + ((long long)blockIdx.z * gridDim.y + blockIdx.y) * a.v.cols;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (c + j < a.v.cols) prow[c + j] = cs[j];
+            for (int j = 0; j < 4; ++j) {
+                if (c + j < a.v.cols) {
+                    float sum = 0.f;
+                    for (int y = 0; y < TY; ++y) sum += red[(y * TX + tx) * 4 + j];
+                    prow[c + j] = sum;
+                }
+            }
         }
     }
 }
@@ -106,7 +123,7 @@ __global__ void colsum_reduce_kernel(const float* partial, int nparts, long long
 }  // namespace
 
 size_t stage_colsum_scratch_bytes(int64_t cols) {
-    return (size_t)round_up(cols * 4 * 1024, 256);  // <= 1024 row chunks
+    return (size_t)round_up(cols * 4 * 64, 256);  // <= 64 row chunks per column
 }
 
 int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst_hi,
@@ -136,13 +153,18 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
                al16(src.ptr) && (aux == nullptr || al16(aux));
 
     const int threads = 128;
-    const int64_t gx = ceil_div(src.cols, threads * 4);
+    int tx = 128;
+    while (tx > 1 && (tx / 2) * 4 >= src.cols) tx >>= 1;  // smallest power of two covering the columns
+    a.tx = tx;
+    const int ty = threads / tx;
+    const int64_t gx = ceil_div(src.cols, (int64_t)tx * 4);
     const int sms = num_sms();
     int64_t want_y = std::max<int64_t>(1, (int64_t)sms * 16 / std::max<int64_t>(1, gx * batch));
     want_y = std::min<int64_t>(want_y, 1024);
-    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(want_y, 1024 / batch));
-    NNB_REQUIRE(!colsum || batch <= 1024, "stage_operand: colsum with batch > 1024");
-    int64_t rpb = std::max<int64_t>(1, ceil_div(src.rows, want_y));
+    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(want_y, 64 / batch));
+    NNB_REQUIRE(!colsum || batch <= 64, "stage_operand: colsum with batch > 64");
+    int64_t rpb = std::max<int64_t>(ty, ceil_div(src.rows, want_y));
+    rpb = round_up(rpb, ty);
     const int64_t gy = ceil_div(src.rows, rpb);
     NNB_REQUIRE(batch <= 65535 && gy <= 65535, "stage_operand: grid too large");
     a.rows_per_block = (int)rpb;
