@@ -158,6 +158,25 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
                          int64_t cols, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
 
+/* ---- fused CrossEntropyLoss (row N3 of SURVEY.md 8f, first half) --------------------------------
+ * LogSoftmax(axis=1) + NLLLoss with unit class weights (neunet/nn/losses.py:59-126); native analogue
+ * in the reference: cudaCrossEntropyForwardBackward (experimental/losses/cross_entropy_loss/
+ * cross_entropy.cu:249-292, which overwrites the logits in place; here dlogits is a separate buffer
+ * and the upstream gradient is applied in the same pass).
+ * logits[rows, C] fp32, targets[rows] int32; rows whose target == ignore_index contribute 0.
+ * reduction: 0 none (row_loss is the result), 1 mean over kept rows, 2 sum.
+ * forward writes row_loss[rows], lse[rows] (log-sum-exp, kept for backward) and, for mean/sum, the
+ * scalar loss_out and inv_denom (1/kept-rows or 1). backward: dlogits = (softmax - onehot) * keep *
+ * inv_denom * upstream, upstream being one device scalar or (upstream_per_row) a [rows] vector.
+ */
+int nnb_cross_entropy_forward(const float* logits, const int32_t* targets, int64_t rows, int64_t C,
+                              int64_t ignore_index, int reduction, float* row_loss, float* lse,
+                              float* loss_out, float* inv_denom, cudaStream_t stream);
+int nnb_cross_entropy_backward(const float* logits, const int32_t* targets, const float* lse,
+                               const float* inv_denom, const float* upstream, int upstream_per_row,
+                               int64_t rows, int64_t C, int64_t ignore_index, float* dlogits,
+                               cudaStream_t stream);
+
 /* ---- multi-tensor Adam / AdamW ---------------------------------------------------------------
  * Replaces the per-tensor Python loops of neunet/optim.py:17-33 (Adam) and 52-69 (AdamW) and the
  * reference's CreateFusedOptimizer / FusedAdamWStep / DestroyFusedOptimizer

@@ -21,8 +21,10 @@ struct nnb_adamw {
     long long* d_sizes = nullptr;
     int* d_blk_tensor = nullptr;
     int* d_blk_chunk = nullptr;
-    const float** h_g = nullptr;  // pinned: the table upload must be capturable in a CUDA graph
+    std::vector<const float*> h_g;  // pageable on purpose: the driver stages such async copies at call
+                                    // time, so the next eager step may overwrite it immediately
     long long* d_t = nullptr;     // device-resident step counter (CUDA-graph replays advance it)
+    std::vector<const float**> snapshots;  // pinned pointer tables owned by captured graphs
 };
 
 namespace nnb {
@@ -133,8 +135,8 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     nnb_adamw* o = new nnb_adamw();
     o->n = n;
     o->nblocks = (int)bt.size();
-    NNB_CUDA_OK(cudaHostAlloc((void**)&o->h_g, n * sizeof(float*), cudaHostAllocDefault));
-    for (int i = 0; i < n; ++i) o->h_g[i] = g ? g[i] : nullptr;
+    o->h_g.assign(n, nullptr);
+    if (g) for (int i = 0; i < n; ++i) o->h_g[i] = g[i];
     NNB_CUDA_OK(cudaMalloc(&o->d_p, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_g, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_m, n * sizeof(float*)));
@@ -145,7 +147,7 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_tensor, bt.size() * sizeof(int)));
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_chunk, bc.size() * sizeof(int)));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_p, p, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
-    NNB_CUDA_OK(cudaMemcpyAsync(o->d_g, o->h_g, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaMemcpyAsync(o->d_g, o->h_g.data(), n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_m, m, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_v, v, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NNB_CUDA_OK(cudaMemcpyAsync(o->d_sizes, sz.data(), n * sizeof(long long), cudaMemcpyHostToDevice, stream));
@@ -158,12 +160,27 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
 
 int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stream) {
     NNB_REQUIRE(opt && g, "nnb_adamw_set_grads: bad arguments");
-    bool same = true;
-    for (int i = 0; i < opt->n; ++i) same = same && (opt->h_g[i] == g[i]);
-    if (same) return NNB_OK;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NNB_CUDA_OK(cudaStreamIsCapturing(stream, &cap));
+    if (cap == cudaStreamCaptureStatusActive) {
+        // A captured copy re-reads its pinned source on every replay, so it gets a private
+        // snapshot of the table: later eager steps must not be able to change what the graph uploads.
+        const float** snap = nullptr;
+        // allocation calls are illegal under global capture mode: switch this thread to relaxed
+        // mode just for the pinned allocation
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+        NNB_CUDA_OK(cudaThreadExchangeStreamCaptureMode(&mode));
+        const cudaError_t ae = cudaHostAlloc((void**)&snap, opt->n * sizeof(float*), cudaHostAllocDefault);
+        NNB_CUDA_OK(cudaThreadExchangeStreamCaptureMode(&mode));
+        NNB_CUDA_OK(ae);
+        for (int i = 0; i < opt->n; ++i) snap[i] = g[i];
+        opt->snapshots.push_back(snap);
+        NNB_CUDA_OK(cudaMemcpyAsync(opt->d_g, snap, opt->n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+        return NNB_OK;
+    }
+    // eager: always upload -- a graph replay in between may have rewritten the device table
     for (int i = 0; i < opt->n; ++i) opt->h_g[i] = g[i];
-    // h_g is pinned and lives in the handle, so this copy is legal inside stream capture
-    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_g, opt->h_g, opt->n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_g, opt->h_g.data(), opt->n * sizeof(float*), cudaMemcpyHostToDevice, stream));
     return NNB_OK;
 }
 
@@ -215,7 +232,7 @@ int nnb_adamw_destroy(nnb_adamw* opt) {
     if (!opt) return NNB_OK;
     cudaFree(opt->d_p); cudaFree((void*)opt->d_g); cudaFree(opt->d_m); cudaFree(opt->d_v);
     cudaFree(opt->d_sizes); cudaFree(opt->d_blk_tensor); cudaFree(opt->d_blk_chunk);
-    cudaFreeHost((void*)opt->h_g);
+    for (auto* sn : opt->snapshots) cudaFreeHost((void*)sn);
     cudaFree(opt->d_t);
     delete opt;
     return NNB_OK;

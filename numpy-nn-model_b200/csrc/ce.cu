@@ -1,0 +1,158 @@
+// Fused CrossEntropyLoss = LogSoftmax(axis=1) + NLLLoss (neunet/nn/losses.py:59-126,
+// neunet/nn/activations.py:462-491) for 2-D logits and unit class weights; the reference's
+// native analogue is cudaCrossEntropyForwardBackward (experimental/losses/cross_entropy_loss/
+// cross_entropy.cu:18-292). Forward reads the logits once (online max/sum per row) and keeps the
+// per-row log-sum-exp; backward writes dlogits = (softmax - onehot) * keep / denom * upstream in one
+// pass. The GPT example's 15 000-wide logits are the largest activation of the model, so the
+// ~40 element-wise launches of the composed form are replaced by three kernels.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace nnb {
+namespace {
+
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+    const float mm = fmaxf(m, m2);
+    s = s * expf(m - mm) + s2 * expf(m2 - mm);
+    m = mm;
+}
+
+// one warp (C <= 2048) or one block per row
+template <int THREADS>
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const float* __restrict__ logits, const int* __restrict__ targets, long long rows, int C,
+               int ignore_index, float* __restrict__ row_loss, float* __restrict__ lse_out) {
+    constexpr bool WARP = THREADS == 32;
+    const long long row = WARP ? ((long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) : blockIdx.x;
+    const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;
+    const int stride = WARP ? 32 : THREADS;
+    if (row >= rows) return;
+    const float* x = logits + row * C;
+    float m = -FLT_MAX, s = 0.f;
+    for (int i = lane; i < C; i += stride) {
+        const float v = x[i];
+        if (v > m) { s *= expf(m - v); m = v; }
+        s += expf(v - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        online_merge(m, s, m2, s2);
+    }
+    if (!WARP) {
+        __shared__ float sm[THREADS / 32], ss[THREADS / 32];
+        if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            m = threadIdx.x < THREADS / 32 ? sm[threadIdx.x] : -FLT_MAX;
+            s = threadIdx.x < THREADS / 32 ? ss[threadIdx.x] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+                online_merge(m, s, m2, s2);
+            }
+        }
+    }
+    if (lane == 0) {
+        const float lse = m + logf(s);
+        lse_out[row] = lse;
+        const int t = targets[row];
+        row_loss[row] = (t == ignore_index) ? 0.f : (lse - x[t]);   // -log_softmax[target]
+    }
+}
+
+// fixed-order single-block finish: loss = sum(row_loss) (/ count of kept rows), inv_denom for backward
+__global__ void __launch_bounds__(1024)
+ce_finish_kernel(const float* __restrict__ row_loss, const int* __restrict__ targets, long long rows,
+                 int ignore_index, int reduction, float* __restrict__ loss_out, float* __restrict__ inv_denom) {
+    __shared__ float ssum[1024];
+    __shared__ float scnt[1024];
+    float s = 0.f, c = 0.f;
+    for (long long i = threadIdx.x; i < rows; i += 1024) {
+        s += row_loss[i];
+        c += (targets[i] != ignore_index) ? 1.f : 0.f;
+    }
+    ssum[threadIdx.x] = s;
+    scnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float inv = (reduction == 1) ? 1.0f / scnt[0] : 1.0f;
+        *inv_denom = inv;
+        *loss_out = ssum[0] * inv;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ce_backward_kernel(const float* __restrict__ logits, const int* __restrict__ targets,
+                   const float* __restrict__ lse, const float* __restrict__ inv_denom,
+                   const float* __restrict__ upstream, int upstream_per_row, long long rows, int C,
+                   int ignore_index, float* __restrict__ dlogits) {
+    const long long total = rows * C;
+    const float inv = inv_denom ? *inv_denom : 1.0f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / C;
+        const int c = (int)(idx - r * C);
+        const int t = targets[r];
+        float g = 0.f;
+        if (t != ignore_index) {
+            const float up = upstream_per_row ? upstream[r] : upstream[0];
+            g = (expf(logits[idx] - lse[r]) - (c == t ? 1.f : 0.f)) * inv * up;
+        }
+        dlogits[idx] = g;
+    }
+}
+
+}  // namespace
+}  // namespace nnb
+
+using namespace nnb;
+
+extern "C" {
+
+int nnb_cross_entropy_forward(const float* logits, const int32_t* targets, int64_t rows, int64_t C,
+                              int64_t ignore_index, int reduction, float* row_loss, float* lse,
+                              float* loss_out, float* inv_denom, cudaStream_t stream) {
+    NNB_REQUIRE(logits && targets && row_loss && lse, "nnb_cross_entropy_forward: null pointer");
+    NNB_REQUIRE(rows > 0 && C > 0 && C < (1ll << 31), "nnb_cross_entropy_forward: bad shape");
+    NNB_REQUIRE(reduction >= 0 && reduction <= 2, "nnb_cross_entropy_forward: bad reduction");
+    NNB_REQUIRE(reduction == 0 || (loss_out && inv_denom), "nnb_cross_entropy_forward: reduction needs loss_out/inv_denom");
+    if (C <= 2048) {
+        const int wpb = 8;
+        ce_rows_kernel<32><<<(unsigned)ceil_div(rows, wpb), 32 * wpb, 0, stream>>>(logits, targets, rows, (int)C,
+                                                                                     (int)ignore_index, row_loss, lse);
+    } else {
+        ce_rows_kernel<256><<<(unsigned)rows, 256, 0, stream>>>(logits, targets, rows, (int)C, (int)ignore_index,
+                                                                row_loss, lse);
+    }
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    if (reduction != 0) {
+        ce_finish_kernel<<<1, 1024, 0, stream>>>(row_loss, targets, rows, (int)ignore_index, reduction, loss_out, inv_denom);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+    }
+    return NNB_OK;
+}
+
+int nnb_cross_entropy_backward(const float* logits, const int32_t* targets, const float* lse,
+                               const float* inv_denom, const float* upstream, int upstream_per_row,
+                               int64_t rows, int64_t C, int64_t ignore_index, float* dlogits,
+                               cudaStream_t stream) {
+    NNB_REQUIRE(logits && targets && lse && upstream && dlogits, "nnb_cross_entropy_backward: null pointer");
+    NNB_REQUIRE(rows > 0 && C > 0 && C < (1ll << 31), "nnb_cross_entropy_backward: bad shape");
+    const long long total = rows * C;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 16));
+    ce_backward_kernel<<<blocks, 256, 0, stream>>>(logits, targets, lse, inv_denom, upstream, upstream_per_row, rows,
+                                                   (int)C, (int)ignore_index, dlogits);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+}  // extern "C"

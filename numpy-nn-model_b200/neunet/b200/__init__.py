@@ -98,6 +98,10 @@ _SIGNATURES = {
     "nnb_rmsnorm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "nnb_rmsnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "nnb_cross_entropy_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]),
+    "nnb_cross_entropy_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                           c_int64, c_void_p, c_void_p]),
     "nnb_adamw_create": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(c_void_p),
                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_void_p]),
     "nnb_adamw_set_grads": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
@@ -520,6 +524,41 @@ def rmsnorm_backward(grad, x, w, std, need_db=False):
     return dx, dw, db
 
 
+# ---- fused CrossEntropyLoss ---------------------------------------------------------------------------------------
+_REDUCTION = {"none": 0, "mean": 1, "sum": 2}
+
+
+def cross_entropy_forward(logits, targets, ignore_index=-100, reduction="mean"):
+    """Returns (loss, saved) -- loss is a 0-d tensor (mean/sum) or [rows]; saved feeds the backward."""
+    require_device()
+    logits = _f32c(logits)
+    rows, C = logits.shape
+    tgt = targets.reshape(-1)
+    if tgt.dtype != torch.int32:
+        tgt = tgt.to(torch.int32)
+    tgt = tgt.contiguous()
+    row_loss = torch.empty(rows, dtype=torch.float32, device="cuda")
+    lse = torch.empty(rows, dtype=torch.float32, device="cuda")
+    red = _REDUCTION[reduction]
+    scal = torch.empty(2, dtype=torch.float32, device="cuda") if red else None
+    _check(lib().nnb_cross_entropy_forward(_ptr(logits), _ptr(tgt), rows, C, int(ignore_index), red, _ptr(row_loss),
+                                           _ptr(lse), _ptr(scal[0:1]) if red else None,
+                                           _ptr(scal[1:2]) if red else None, _stream()), "nnb_cross_entropy_forward")
+    loss = scal[0] if red else row_loss
+    return loss, (logits, tgt, lse, scal[1:2] if red else None, int(ignore_index))
+
+
+def cross_entropy_backward(saved, upstream):
+    logits, tgt, lse, inv, ignore_index = saved
+    rows, C = logits.shape
+    up = _f32c(upstream).reshape(-1)
+    per_row = 1 if up.numel() == rows and rows > 1 and inv is None else 0
+    d = torch.empty_like(logits)
+    _check(lib().nnb_cross_entropy_backward(_ptr(logits), _ptr(tgt), _ptr(lse), _ptr(inv), _ptr(up), per_row, rows, C,
+                                            ignore_index, _ptr(d), _stream()), "nnb_cross_entropy_backward")
+    return d
+
+
 # ---- whole-step CUDA graphs ---------------------------------------------------------------------------------
 class GraphedStep:
     """Capture ``fn(*inputs)`` -- typically one whole training step (forward, loss, backward,
@@ -552,6 +591,7 @@ class GraphedStep:
             self.outputs = fn(*self.inputs)
         if optimizer is not None:
             optimizer.t -= 1  # the capture pass itself launched nothing
+        self._dev_t = optimizer.t if optimizer is not None else 0  # value of the device step counter
 
     def load(self, *arrays, non_blocking=True):
         """Copy new values (pinned torch tensors / device tensors / NumPy arrays) into the static inputs."""
@@ -561,9 +601,13 @@ class GraphedStep:
             dst.data.copy_(src, non_blocking=non_blocking)
 
     def replay(self):
+        opt = self.optimizer
+        if opt is not None and opt.t != self._dev_t and getattr(opt, "_fused", None) is not None:
+            opt._fused.set_step(opt.t)  # eager steps were interleaved: re-sync the device counter
         self.graph.replay()
-        if self.optimizer is not None:
-            self.optimizer.t += 1
+        if opt is not None:
+            opt.t += 1
+            self._dev_t = opt.t
         return self.outputs
 
     def __call__(self, *arrays):

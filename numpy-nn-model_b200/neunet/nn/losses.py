@@ -100,4 +100,23 @@ class CrossEntropyLoss(Module):
 
     def forward(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
         _check(y_pred, y_true)
+        if y_pred.device == "cuda" and self.weight is None and y_pred.ndim == 2 and y_true.ndim == 1:
+            # fused LogSoftmax + NLL on the device (three kernels instead of ~40 element-wise launches)
+            if y_true.dtype not in (np.int16, np.int32, np.int64):
+                raise TypeError("Target must be of int dtype")
+            from .. import b200
+            loss, saved = b200.cross_entropy_forward(y_pred.data, y_true.data, self.ignore_index, self.reduction)
+            return _FusedCETensor(loss, (y_pred, saved), "cross_entropy", y_pred.device)
         return self.nll_loss(self.log_softmax(y_pred), y_true)
+
+
+class _FusedCETensor(Tensor):
+    def __init__(self, data, args, op, device):
+        t = Tensor._wrap(data, args, op, True, device)
+        self.__dict__.update(t.__dict__)
+        self.grad_fn = _fused_ce_grad
+
+
+def _fused_ce_grad(y_pred: Tensor, saved, grad):
+    from .. import b200
+    y_pred.apply_grad(b200.cross_entropy_backward(saved, grad))
