@@ -76,6 +76,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
            ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Grouped tile order: walk GROUP_M row-blocks under each column-block before moving on, so the
+// CTAs of one wave share a [GROUP_M*128 x K] slab of A and a few B slabs that stay L2-resident.
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int r, int num_m, int num_n, int& m_blk, int& n_blk) {
+    const int per_group = GROUP_M * num_n;
+    const int g = r / per_group;
+    const int first_m = g * GROUP_M;
+    const int gm = min(num_m - first_m, GROUP_M);
+    const int in_g = r - g * per_group;
+    n_blk = in_g / gm;
+    m_blk = first_m + (in_g - n_blk * gm);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act, float beta) {
     if (act == NNB_ACT_SWISH) return x / (1.0f + __expf(-beta * x));
     return x;
@@ -154,8 +167,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                 const int t = w - split * tiles;
                 const int ob = t / tiles_per_batch;
                 const int r = t - ob * tiles_per_batch;
-                const int m0 = (r % p.num_m) * BM;
-                const int n0 = (r / p.num_m) * BN;
+                int m_blk, n_blk;
+                tile_coords(r, p.num_m, p.num_n, m_blk, n_blk);
+                const int m0 = m_blk * BM;
+                const int n0 = n_blk * BN;
                 const int it0 = split * p.iters_per_split;
                 const int it1 = min(it0 + p.iters_per_split, total_iters);
                 for (int it = it0; it < it1; ++it) {
@@ -251,8 +266,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
             const int t = w - split * tiles;
             const int ob = t / tiles_per_batch;
             const int r = t - ob * tiles_per_batch;
-            const int m0 = (r % p.num_m) * BM;
-            const int n0 = (r / p.num_m) * BN;
+            int m_blk, n_blk;
+            tile_coords(r, p.num_m, p.num_n, m_blk, n_blk);
+            const int m0 = m_blk * BM;
+            const int n0 = n_blk * BN;
             const int acc = local_iter & 1;
             const uint32_t acc_phase = (local_iter >> 1) & 1;
             ptx::mbar_wait(&tmem_full[acc], acc_phase, 4);

@@ -183,6 +183,12 @@ static void bench_gemm(int64_t M, int64_t K, int64_t N, int prec, int iters) {
 }
 
 int main(int argc, char** argv) {
+    if (argc >= 6 && !strcmp(argv[1], "bench")) {  // test_gemm bench M K N prec [iters]
+        int sms0, maj0, min0;
+        NK(nnb_device_check(&sms0, &maj0, &min0));
+        bench_gemm(atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 20);
+        return 0;
+    }
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
     int sms, maj, min;
     NK(nnb_device_check(&sms, &maj, &min));
