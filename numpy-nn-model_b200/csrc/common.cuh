@@ -116,6 +116,8 @@ struct GemmProblem {
     size_t splitk_ws_bytes = 0;
     int force_bn = 0;      // 0 = heuristic
     int force_splits = 0;  // 0 = heuristic
+    int force_cg = 0;      // 0 = heuristic, 1 / 2 = CTAs per tile (tcgen05 cta_group)
+    unsigned long long* clk_out = nullptr;  // optional device buffer [2]: {SM cycles, ns} of CTA 0 (clock probe)
 };
 
 size_t gemm_splitk_ws_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);

@@ -12,6 +12,7 @@
 //   * BF16X3 precision = three (A,B) segment pairs accumulated into one TMEM tile
 //   * split-K / reduce-over-batch for wgrad-shaped problems (tiny output, huge reduction)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -61,6 +62,9 @@ struct KArgs {
     float* ws;  // split-K partials [split][out_batch][M][N]
     int tma_store;  // 1: epilogue writes D/Z through TMA (needs 16-byte aligned rows)
     int bias_vec;   // 1: bias pointer 16-byte aligned (float4 loads)
+    unsigned long long* clk_out;  // optional: CTA 0 writes {SM cycles, ns} of its lifetime (clock probe)
+    int stages;     // operand ring depth actually used (<= Cfg::STAGES; experiments only)
+    int debug;      // profiling experiments only (NNB_GEMM_DEBUG): 1 = epilogue skips the stores, 2 = also skips the TMEM loads
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
@@ -70,10 +74,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
-    // kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, int m) {
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, M = 128 (cta_group::1) or 256 (cta_group::2).
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
-           ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Grouped tile order: walk GROUP_M row-blocks under each column-block before moving on, so the
@@ -94,20 +98,27 @@ __device__ __forceinline__ float apply_act(float x, int act, float beta) {
     return x;
 }
 
-template <int BN>
+// CG = CTAs per tile (tcgen05 cta_group): with CG == 2 a CTA pair computes a 256 x BN tile, each CTA
+// holding its own 128 rows of A and HALF of the B tile; the UMMA reads both halves, so operand fill
+// and shared-memory reads per SM drop from (16 + BN/8) KB to (16 + BN/16) KB per k-block.
+template <int BN, int CG>
 struct Cfg {
+    static constexpr int BNL = BN / CG;  // B rows (or columns, MN-major) staged by this CTA
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = BNL * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES + 256 + 1024;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
+    constexpr int BNL = C::BNL;
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -124,6 +135,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    unsigned long long clk0 = 0, ns0 = 0;
+    if (p.clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        clk0 = clock64();
+        ns0 = ptx::globaltimer_ns();
+    }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nseg; ++s) {
@@ -137,18 +153,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&full_bar[i], CG);  // one arrival per CTA of the pair (leader's copy is used)
             ptx::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], 128);
+            ptx::mbar_init(&tmem_empty[i], 128 * CG);  // epilogue threads of every CTA of the pair
         }
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    if (warp == 2) {
+        if (CG == 2) ptx::tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot); else ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -156,21 +174,25 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
     const int tiles = tiles_per_batch * p.out_batches;
     const int work = tiles * p.splits;
     const int total_iters = p.red_batches * p.kblocks;
+    const int worker = blockIdx.x / CG, num_workers = gridDim.x / CG;  // a worker = one CTA or one CTA pair
+    const int nstages = (p.stages > 0 && p.stages < STAGES) ? p.stages : STAGES;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // elect.sync (not `lane == 0`): ptxas then knows the region is single-threaded and keeps the
+        // TMA / barrier operands in uniform registers instead of wrapping each issue in a waterfall loop
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < work; w += gridDim.x) {
+            for (int w = worker; w < work; w += num_workers) {
                 const int split = w / tiles;
                 const int t = w - split * tiles;
                 const int ob = t / tiles_per_batch;
                 const int r = t - ob * tiles_per_batch;
                 int m_blk, n_blk;
                 tile_coords(r, p.num_m, p.num_n, m_blk, n_blk);
-                const int m0 = m_blk * BM;
-                const int n0 = n_blk * BN;
+                const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM;
+                const int n0 = n_blk * BN + (int)cta_rank * BNL;  // this CTA's share of the B tile
                 const int it0 = split * p.iters_per_split;
                 const int it1 = min(it0 + p.iters_per_split, total_iters);
                 for (int it = it0; it < it1; ++it) {
@@ -181,26 +203,27 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                     const int bb = p.b_bcast ? 0 : bidx;
                     for (int s = 0; s < p.nseg; ++s) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        // all transaction bytes of the pair are counted on the LEADER's barrier
+                        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
+                        else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
                         uint8_t* sa = smem_a + stage * C::A_BYTES;
                         uint8_t* sb = smem_b + stage * C::B_BYTES;
+                        uint64_t* fb = &full_bar[stage];
                         if (!A_MN) {
-                            ptx::tma_load_3d(sa, &maps.a[s], &full_bar[stage], k0, m0, ba);
+                            ptx::tma_load_3d_cg<CG>(sa, &maps.a[s], fb, k0, m0, ba);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i)
-                                ptx::tma_load_3d(sa + i * (BK * 128), &maps.a[s], &full_bar[stage],
-                                                 m0 + i * 64, k0, ba);
+                                ptx::tma_load_3d_cg<CG>(sa + i * (BK * 128), &maps.a[s], fb, m0 + i * 64, k0, ba);
                         }
                         if (!B_MN) {
-                            ptx::tma_load_3d(sb, &maps.b[s], &full_bar[stage], k0, n0, bb);
+                            ptx::tma_load_3d_cg<CG>(sb, &maps.b[s], fb, k0, n0, bb);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < BN / 64; ++i)
-                                ptx::tma_load_3d(sb + i * (BK * 128), &maps.b[s], &full_bar[stage],
-                                                 n0 + i * 64, k0, bb);
+                            for (int i = 0; i < BNL / 64; ++i)
+                                ptx::tma_load_3d_cg<CG>(sb + i * (BK * 128), &maps.b[s], fb, n0 + i * 64, k0, bb);
                         }
-                        if (++stage == STAGES) {
+                        if (++stage == nstages) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -208,9 +231,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN, BM * CG);
         // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
         // MN-major: atoms of [64 mn x 8 k] = 1024 B; SBO = stride between 8-k groups (1024 B),
         //           LBO = stride between 64-wide mn atoms (BK * 128 B).
@@ -220,7 +243,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
         int stage = 0;
         uint32_t phase = 0;
         int local_iter = 0;
-        for (int w = blockIdx.x; w < work; w += gridDim.x, ++local_iter) {
+        for (int w = worker; w < work; w += num_workers, ++local_iter) {
             const int split = w / tiles;
             const int it0 = split * p.iters_per_split;
             const int it1 = min(it0 + p.iters_per_split, total_iters);
@@ -233,22 +256,30 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
             for (int i = 0; i < n_pipe; ++i) {
                 ptx::mbar_wait(&full_bar[stage], phase, 3);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     const uint64_t da =
                         make_smem_desc(ptx::smem_u32(smem_a + stage * C::A_BYTES), A_LBO, 1024);
                     const uint64_t db =
                         make_smem_desc(ptx::smem_u32(smem_b + stage * C::B_BYTES), B_LBO, 1024);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * A_KSTEP),
-                                         db + (uint64_t)(k * B_KSTEP), idesc,
-                                         (i > 0 || k > 0) ? 1u : 0u);
+                        if (CG == 2)
+                            ptx::umma_f16_ss_2sm(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP),
+                                                 idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        else
+                            ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP),
+                                             idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (i == n_pipe - 1) ptx::umma_commit(&tmem_full[acc]);
+                    if (CG == 2) {  // completion is signalled to the same barrier in BOTH CTAs
+                        ptx::umma_commit_2sm(&empty_bar[stage], 0b11);
+                        if (i == n_pipe - 1) ptx::umma_commit_2sm(&tmem_full[acc], 0b11);
+                    } else {
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (i == n_pipe - 1) ptx::umma_commit(&tmem_full[acc]);
+                    }
                 }
                 __syncwarp();
-                if (++stage == STAGES) {
+                if (++stage == nstages) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -261,14 +292,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
         uint8_t* tile0 = reinterpret_cast<uint8_t*>(scratch);  // two 1024B-aligned 4 KB tiles
         int store_parity = 0;
         int local_iter = 0;
-        for (int w = blockIdx.x; w < work; w += gridDim.x, ++local_iter) {
+        for (int w = worker; w < work; w += num_workers, ++local_iter) {
             const int split = w / tiles;
             const int t = w - split * tiles;
             const int ob = t / tiles_per_batch;
             const int r = t - ob * tiles_per_batch;
             int m_blk, n_blk;
             tile_coords(r, p.num_m, p.num_n, m_blk, n_blk);
-            const int m0 = m_blk * BM;
+            const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM;
             const int n0 = n_blk * BN;
             const int acc = local_iter & 1;
             const uint32_t acc_phase = (local_iter >> 1) & 1;
@@ -283,18 +314,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                 if (col0 >= p.N || !rows_live) {
                     if (c == NCHUNK - 1) {
                         ptx::tc_fence_before();
-                        ptx::mbar_arrive(&tmem_empty[acc]);
+                        if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); else ptx::mbar_arrive(&tmem_empty[acc]);
                     }
                     continue;
                 }
                 uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-                ptx::tmem_ld_wait();
+                if (p.debug < 2) {
+                    ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+                    ptx::tmem_ld_wait();
+                }
                 if (c == NCHUNK - 1) {
                     // accumulator fully drained into registers: hand the TMEM buffer back
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&tmem_empty[acc]);
+                    if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); else ptx::mbar_arrive(&tmem_empty[acc]);
                 }
+                if (p.debug >= 1) continue;
                 if (p.tma_store && p.splits == 1) {
                     // ---- fast path: registers -> swizzled smem tile -> TMA store (coalescing, tail
                     // clipping and the fp32 writes are done by the copy engine, not by LSU traffic)
@@ -346,7 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                             make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {
                         ptx::tma_store_3d(&maps.d, tile_d, col0, row_base, ob);
                         if (has_z) ptx::tma_store_3d(&maps.z, tile_z, col0, row_base, ob);
                         ptx::tma_store_commit();
@@ -400,8 +434,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+    if (p.clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        p.clk_out[0] = clock64() - clk0;
+        p.clk_out[1] = ptx::globaltimer_ns() - ns0;
+    }
+    if (warp == 2) {
+        if (CG == 2) ptx::tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base); else ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
 }
 
 // Sum split-K partials and apply the epilogue.
@@ -493,32 +533,42 @@ int encode_out_map(CUtensorMap* m, const float* ptr, int64_t cols, int64_t rows,
     return NNB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 int launch(const GemmMaps& maps, const KArgs& ka, int grid, cudaStream_t stream) {
-    using C = Cfg<BN>;
-    auto kfn = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+    using C = Cfg<BN, CG>;
+    auto kfn = gemm_tcgen05_kernel<BN, A_MN, B_MN, CG>;
     static bool configured = false;  // per instantiation
     if (!configured) {
-        NNB_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES));
+        NNB_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    kfn<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, ka);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (CG == 2) ? 1 : 0;
+    NNB_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, maps, ka));
     count_launch();
-    NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_major(bool a_mn, bool b_mn, const GemmMaps& maps, const KArgs& ka, int grid,
                  cudaStream_t stream) {
-    if (!a_mn && !b_mn) return launch<BN, false, false>(maps, ka, grid, stream);
-    if (a_mn && !b_mn) return launch<BN, true, false>(maps, ka, grid, stream);
-    if constexpr (BN >= 64) {
-        if (!a_mn && b_mn) return launch<BN, false, true>(maps, ka, grid, stream);
-        return launch<BN, true, true>(maps, ka, grid, stream);
+    if (!a_mn && !b_mn) return launch<BN, false, false, CG>(maps, ka, grid, stream);
+    if (a_mn && !b_mn) return launch<BN, true, false, CG>(maps, ka, grid, stream);
+    if constexpr (BN / CG >= 64) {
+        if (!a_mn && b_mn) return launch<BN, false, true, CG>(maps, ka, grid, stream);
+        return launch<BN, true, true, CG>(maps, ka, grid, stream);
     } else {
-        return fail(NNB_ERR_UNSUPPORTED, "MN-major B needs BN >= 64");
+        return fail(NNB_ERR_UNSUPPORTED, "MN-major B needs >= 64 columns per CTA");
     }
 }
 
@@ -550,38 +600,60 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     const int64_t total_iters_all = ceil_div(g.K, BK) * red_batches;
     const int nseg_h = x3 ? 3 : 1;
     const bool tma_ok_h = g.col_group == 0 && (g.ldd % 4) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0;
-    int bn = 0;
+    int bn = 0, cg = 1;
     int64_t splits = 1;
     {
+        static const int env_cg = [] { const char* e = getenv("NNB_GEMM_CG"); return e ? atoi(e) : 0; }();
+        static const int verbose = [] { const char* e = getenv("NNB_GEMM_VERBOSE"); return e ? atoi(e) : 0; }();
+        static const int env_bn = [] { const char* e = getenv("NNB_GEMM_BN"); return e ? atoi(e) : 0; }();
+        int force_cg = g.force_cg ? g.force_cg : env_cg;
+        int force_bn = g.force_bn ? g.force_bn : env_bn;
+        if (force_cg == 2 && g.M <= BM) force_cg = 1;  // a single row-block cannot use a CTA pair
+      retry_search:
         const int cands[4] = {256, 128, 64, 32};
         const int scand[12] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
         double best = 1e300;
-        for (int ci = 0; ci < 4; ++ci) {
-            const int c = cands[ci];
-            if (g.force_bn && c != g.force_bn) continue;
-            if (b_mn && c < 64) continue;
-            if (!g.force_bn && c > 32 && c / 2 >= g.N && !(b_mn && c == 64)) continue;  // half the width covers N
-            const int64_t t = ceil_div(g.M, BM) * ceil_div(g.N, c) * out_batches;
-            for (int si = 0; si < 12; ++si) {
-                const int64_t sp = scand[si];
-                if (g.force_splits && sp != g.force_splits) continue;
-                if (sp > 1 && (sp > total_iters_all || total_iters_all / sp < 2)) continue;
-                if (sp > 1) {
-                    const size_t need = (size_t)sp * out_batches * g.M * g.N * 4;
-                    if (g.splitk_ws == nullptr || g.splitk_ws_bytes < need) continue;
+        for (int cgi = 1; cgi <= 2; ++cgi) {
+            if (force_cg && cgi != force_cg) continue;
+            if (cgi == 2 && (g.M <= BM || sms < 2)) continue;  // a pair needs two row-blocks to be useful
+            for (int ci = 0; ci < 4; ++ci) {
+                const int c = cands[ci];
+                if (force_bn && c != force_bn) continue;
+                if (cgi == 2 && c < 128) continue;
+                if (b_mn && c / cgi < 64) continue;
+                if (!force_bn && c > 32 && c / 2 >= g.N && !(b_mn && c / cgi == 64)) continue;  // half the width covers N
+                const int64_t t = ceil_div(g.M, BM * cgi) * ceil_div(g.N, c) * out_batches;
+                for (int si = 0; si < 12; ++si) {
+                    const int64_t sp = scand[si];
+                    if (g.force_splits && sp != g.force_splits) continue;
+                    if (sp > 1 && (sp > total_iters_all || total_iters_all / sp < 2)) continue;
+                    if (sp > 1) {
+                        const size_t need = (size_t)sp * out_batches * g.M * g.N * 4;
+                        if (g.splitk_ws == nullptr || g.splitk_ws_bytes < need) continue;
+                    }
+                    const double waves = (double)ceil_div(t * sp, sms / cgi);
+                    const double iters = (double)ceil_div(total_iters_all, sp) * nseg_h;
+                    const double mma = iters * 4.0 * std::max(c / 2.0, 40.0);
+                    // shared-memory traffic per k-block: TMA fill + UMMA operand reads of the local tiles
+                    const double fill = iters * 2.0 * (16384.0 + (c / cgi) * 128.0) / 128.0;
+                    const double epi = (c / 32) * ((tma_ok_h && sp == 1) ? 160.0 : 1300.0) + 300.0;
+                    double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0 + (cgi == 2 ? 800.0 : 0.0);
+                    if (sp > 1) {
+                        const double out_bytes = (double)g.M * g.N * out_batches * 4.0;
+                        cyc += (2.0 * sp + 1.0) * out_bytes / 3400.0 + 4000.0;
+                    }
+                    if (cyc < best) { best = cyc; bn = c; splits = sp; cg = cgi; }
                 }
-                const double waves = (double)ceil_div(t * sp, sms);
-                const double iters = (double)ceil_div(total_iters_all, sp) * nseg_h;
-                const double mma = iters * 4.0 * std::max(c / 2.0, 40.0);
-                const double fill = iters * (16384.0 + c * 128.0) / 100.0;
-                const double epi = (c / 32) * ((tma_ok_h && sp == 1) ? 160.0 : 1300.0) + 300.0;
-                double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0;
-                if (sp > 1) {
-                    const double out_bytes = (double)g.M * g.N * out_batches * 4.0;
-                    cyc += (2.0 * sp + 1.0) * out_bytes / 3400.0 + 4000.0;
-                }
-                if (cyc < best) { best = cyc; bn = c; splits = sp; }
             }
+        }
+        if (verbose)
+            fprintf(stderr, "[nnb gemm] M=%lld N=%lld K=%lld batch=%lld majors=%d%d x3=%d -> BN=%d CG=%d splits=%lld (model %.0f cycles)\n",
+                    (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, (int)a_mn, (int)b_mn, (int)x3, bn, cg,
+                    (long long)splits, best);
+        if (bn == 0 && (env_cg || env_bn) && !g.force_cg && !g.force_bn && force_cg + force_bn != 0) {
+            force_cg = 0;  // environment overrides are best-effort: fall back to the model's choice
+            force_bn = 0;
+            goto retry_search;
         }
         if (bn == 0) {
             if (g.force_splits > 1)
@@ -590,9 +662,9 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
         }
     }
     NNB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad BN %d", bn);
-    NNB_REQUIRE(!(b_mn && bn < 64), "gemm: MN-major B needs BN >= 64");
+    NNB_REQUIRE(!(b_mn && bn / cg < 64), "gemm: MN-major B needs >= 64 columns per CTA");
 
-    const int64_t num_m = ceil_div(g.M, BM), num_n = ceil_div(g.N, bn);
+    const int64_t num_m = ceil_div(g.M, BM * cg), num_n = ceil_div(g.N, bn);
     const int64_t tiles = num_m * num_n * out_batches;
     const int64_t kblocks = ceil_div(g.K, BK);
     const int64_t total_iters = kblocks * red_batches;
@@ -632,7 +704,7 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
         if (!b_mn) {
             NNB_REQUIRE(g.B.st.rows == g.N && g.B.st.cols == g.K, "gemm: B staged shape mismatch");
             rc = encode_map(&maps.b[s], b_planes[s], g.K, g.N, g.B.st.ld, b_bcast ? 1 : g.batch,
-                            g.B.st.batch_stride, bn);
+                            g.B.st.batch_stride, bn / cg);
         } else {
             NNB_REQUIRE(g.B.st.rows == g.K && g.B.st.cols == g.N, "gemm: B staged shape mismatch (MN)");
             rc = encode_map(&maps.b[s], b_planes[s], g.N, g.K, g.B.st.ld, b_bcast ? 1 : g.batch,
@@ -659,6 +731,13 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     ka.ws = g.splitk_ws;
     if (g.col_group > 0) { ka.col_group = (int)g.col_group; ka.group_stride = g.group_stride; }
     ka.bias_per_row = g.bias_per_row ? 1 : 0;
+    {
+        static const int dbg = [] { const char* e = getenv("NNB_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+        ka.debug = dbg;
+        static const int st = [] { const char* e = getenv("NNB_GEMM_STAGES"); return e ? atoi(e) : 0; }();
+        ka.stages = st;
+        ka.clk_out = g.clk_out;
+    }
     ka.bias_vec = g.epi.bias && (reinterpret_cast<uintptr_t>(g.epi.bias) & 15) == 0;
     {
         auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -675,13 +754,18 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     }
 
     const int64_t work = tiles * splits;
-    const int grid = (int)std::min<int64_t>(work, sms);
+    const int grid = (int)std::min<int64_t>(work, sms / cg) * cg;
     int rc;
-    switch (bn) {
-        case 32: rc = launch_major<32>(a_mn, b_mn, maps, ka, grid, stream); break;
-        case 64: rc = launch_major<64>(a_mn, b_mn, maps, ka, grid, stream); break;
-        case 128: rc = launch_major<128>(a_mn, b_mn, maps, ka, grid, stream); break;
-        default: rc = launch_major<256>(a_mn, b_mn, maps, ka, grid, stream); break;
+    if (cg == 2) {
+        if (bn == 128) rc = launch_major<128, 2>(a_mn, b_mn, maps, ka, grid, stream);
+        else rc = launch_major<256, 2>(a_mn, b_mn, maps, ka, grid, stream);
+    } else {
+        switch (bn) {
+            case 32: rc = launch_major<32, 1>(a_mn, b_mn, maps, ka, grid, stream); break;
+            case 64: rc = launch_major<64, 1>(a_mn, b_mn, maps, ka, grid, stream); break;
+            case 128: rc = launch_major<128, 1>(a_mn, b_mn, maps, ka, grid, stream); break;
+            default: rc = launch_major<256, 1>(a_mn, b_mn, maps, ka, grid, stream); break;
+        }
     }
     if (rc) return rc;
     if (splits > 1) {

@@ -155,6 +155,24 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// cta_group-generic 3-D load. With CG == 2 the copy lands in THIS CTA's shared memory but its
+// transaction bytes are signalled on the barrier at the same offset in the pair's leader CTA
+// (peer bit 24 of the shared::cluster address cleared).
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_cg(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                               int32_t c0, int32_t c1, int32_t c2) {
+    if (CG == 1) {
+        tma_load_3d(smem_dst, map, bar, c0, c1, c2);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+              "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    }
+}
+
 // 2-CTA variant: data lands in this CTA's smem, the transaction bytes are signalled on the
 // barrier at the same offset in the *leader* CTA (bar address must be a shared::cluster
 // address mapped to the leader; see mapa_u32()).

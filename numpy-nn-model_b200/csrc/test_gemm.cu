@@ -160,13 +160,14 @@ static void bench_gemm(int64_t M, int64_t K, int64_t N, int prec, int iters) {
     float* out; CK(cudaMalloc(&out, std::max({M * N, M * K, N * K}) * 4));
     size_t skb = 256 << 20; float* sk; CK(cudaMalloc(&sk, skb));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    unsigned long long* clk; CK(cudaMalloc(&clk, 16));
     const char* names[3] = {"fwd  X.W^T", "dgrad g.W ", "wgrad g^T.X"};
     for (int form = 0; form < 3; ++form) {
         GemmProblem g;
         if (form == 0) { g.M = M; g.N = N; g.K = K; g.A.st = xs; g.B.st = wsd; g.ldd = N; }
         if (form == 1) { g.M = M; g.N = K; g.K = N; g.A.st = gs; g.B.st = wsd; g.B.mn_major = true; g.ldd = K; }
         if (form == 2) { g.M = N; g.N = K; g.K = M; g.A.st = gs; g.A.mn_major = true; g.B.st = xs; g.B.mn_major = true; g.ldd = K; }
-        g.D = out; g.splitk_ws = sk; g.splitk_ws_bytes = skb;
+        g.D = out; g.splitk_ws = sk; g.splitk_ws_bytes = skb; g.clk_out = clk;
         for (int i = 0; i < 3; ++i) NK(gemm(g, 0));
         CK(cudaEventRecord(e0));
         for (int i = 0; i < iters; ++i) NK(gemm(g, 0));
@@ -174,8 +175,13 @@ static void bench_gemm(int64_t M, int64_t K, int64_t N, int prec, int iters) {
         CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         const double t = ms / iters * 1e-3;
-        printf("  gemm %s M=%lld K=%lld N=%lld %s: %.1f us  %.1f TFLOP/s (algorithmic 2MKN)\n", names[form],
-               (long long)M, (long long)K, (long long)N, prec ? "bf16x3" : "bf16", t * 1e6, 2.0 * M * K * N / t * 1e-12);
+        unsigned long long hclk[2];
+        CK(cudaMemcpy(hclk, clk, 16, cudaMemcpyDeviceToHost));
+        const double mhz = hclk[1] ? (double)hclk[0] / (double)hclk[1] * 1e3 : 0.0;
+        const double peak = 148.0 * 8192.0 * mhz * 1e6 * 1e-12;  // TFLOP/s at the observed SM clock
+        printf("  gemm %s M=%lld K=%lld N=%lld %s: %.1f us  %.1f TFLOP/s (algorithmic 2MKN)  [SM clock %.0f MHz -> tensor peak %.0f TFLOP/s, %.0f%%]\n", names[form],
+               (long long)M, (long long)K, (long long)N, prec ? "bf16x3" : "bf16", t * 1e6, 2.0 * M * K * N / t * 1e-12,
+               mhz, peak, peak > 0 ? 100.0 * (2.0 * M * K * N / t * 1e-12) / peak : 0.0);
     }
     cudaFree(dX); cudaFree(dW); cudaFree(dG); cudaFree(out); cudaFree(sk);
     cudaFree((void*)xs.hi); cudaFree((void*)wsd.hi); cudaFree((void*)gs.hi);
