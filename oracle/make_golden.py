@@ -216,5 +216,85 @@ def main():
          dw1=l1.weight.grad, dw2=l2.weight.grad)
 
 
+def model_goldens():
+    """Whole-model fixtures: the SAME model definitions (tests/models.py) run on the reference."""
+    neunet, nn, optim = import_reference()
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    import models as M
+    f32 = np.float32
+
+    def save(name, **arrs):
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+        print(f"{name}: " + ", ".join(f"{k}{tuple(np.shape(v))}" for k, v in arrs.items()))
+
+    def flat_params(model):
+        return {f"p{i}": p.data.copy() for i, p in enumerate(model.parameters())}
+
+    # ---- GPT (examples/gpt.ipynb architecture), eval mode (dropout off), 2 Adam steps -------------
+    np.random.seed(0)
+    model = M.build_gpt(neunet, nn)
+    model.eval()
+    init = flat_params(model)
+    opt = optim.Adam(model.parameters(), lr=1.5e-4, betas=(0.9, 0.98), eps=1e-9)
+    rng = np.random.RandomState(1)
+    batch = rng.randint(3, 50, (3, 11))
+    batch[0, 8:] = 0  # padding in one row (ignore_index / pad mask path)
+    losses, first_logits, grads = [], None, None
+    for step in range(2):
+        opt.zero_grad()
+        loss, logits = M.gpt_train_step(neunet, nn, model, opt, batch)
+        losses.append(float(loss.data))
+        if step == 0:
+            first_logits = logits.data.copy()
+            grads = {f"g{i}": (p.grad.copy() if p.grad is not None else np.zeros(0, f32))
+                     for i, p in enumerate(model.parameters())}
+    after = {f"a{i}": p.data.copy() for i, p in enumerate(model.parameters())}
+    save("model_gpt", batch=batch, losses=np.array(losses), logits=first_logits, **init, **grads, **after)
+
+    # ---- conv digits classifier, train mode (BatchNorm batch statistics), 2 Adam steps ------------
+    np.random.seed(0)
+    net = M.build_conv_classifier(neunet, nn)
+    init = flat_params(net)
+    opt = optim.Adam(net.parameters(), lr=1e-3)
+    x = rng.uniform(-1, 1, (6, 1, 12, 12)).astype(f32)
+    y = np.eye(10, dtype=f32)[rng.randint(0, 10, 6)]
+    losses = []
+    for step in range(2):
+        opt.zero_grad()
+        out = net(neunet.tensor(x))
+        loss = nn.MSELoss()(out, neunet.tensor(y))
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.data))
+        if step == 0:
+            first_out = out.data.copy()
+            grads = {f"g{i}": p.grad.copy() for i, p in enumerate(net.parameters())}
+    after = {f"a{i}": p.data.copy() for i, p in enumerate(net.parameters())}
+    save("model_conv_classifier", x=x, y=y, losses=np.array(losses), out=first_out,
+         running_mean=net.bn.running_mean.data.copy(), **init, **grads, **after)
+
+    # ---- two-level DDPM-style UNet, train mode, 1 Adam step -------------------------------------
+    np.random.seed(0)
+    unet = M.build_unet(neunet, nn)
+    init = flat_params(unet)
+    opt = optim.Adam(unet.parameters(), lr=2e-4)
+    x = rng.uniform(-1, 1, (2, 3, 8, 8)).astype(f32)
+    temb = rng.randn(2, 8).astype(f32)
+    noise = rng.randn(2, 3, 8, 8).astype(f32)
+    opt.zero_grad()
+    out = unet(neunet.tensor(x), neunet.tensor(temb))
+    loss = nn.MSELoss()(out, neunet.tensor(noise))
+    loss.backward()
+    opt.step()
+    grads = {f"g{i}": p.grad.copy() for i, p in enumerate(unet.parameters())}
+    after = {f"a{i}": p.data.copy() for i, p in enumerate(unet.parameters())}
+    save("model_unet", x=x, temb=temb, noise=noise, loss=np.array(float(loss.data)), out=out.data.copy(),
+         **init, **grads, **after)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "models":
+        model_goldens()
+    else:
+        main()
+        model_goldens()

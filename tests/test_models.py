@@ -1,0 +1,155 @@
+"""Whole-model parity against fixtures produced by running the SAME model definitions
+(tests/models.py) on the unmodified reference: GPT (examples/gpt.ipynb architecture), the conv
+digits classifier and a two-level DDPM-style UNet. Checks loss, outputs, every parameter gradient
+and the post-Adam parameters -- on "cpu" (host mirror) and, marked gpu, on "cuda" (sm_100a kernels)."""
+import numpy as np
+import pytest
+
+import models as M
+import neunet
+import neunet.nn as nn
+from conftest import load_golden
+from neunet.optim import Adam
+
+
+def _host(a):
+    return a if isinstance(a, np.ndarray) else a.detach().cpu().numpy()
+
+
+def _rel(got, ref):
+    got, ref = _host(got).astype(np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-12))
+
+
+def _load_params(model, g):
+    for i, p in enumerate(model.parameters()):
+        assert tuple(p.shape) == g[f"p{i}"].shape
+        p.data = p.xp.array(g[f"p{i}"]) if p.device == "cuda" else g[f"p{i}"].copy()
+
+
+def _noise_only(g, i, gmax):
+    """A conv/linear bias that feeds straight into BatchNorm has an analytically ZERO gradient; what
+    both implementations compute there is round-off (~1e-9), which Adam then normalises to +-lr. Such
+    tensors carry no signal and are excluded from gradient / post-step comparisons."""
+    ref = g[f"g{i}"]
+    return ref.size > 0 and np.abs(ref).max() < 1e-4 * gmax
+
+
+def _gmax(g):
+    return max(np.abs(v).max() for k, v in g.items() if k[0] == "g" and k[1:].isdigit() and v.size)
+
+
+def _check_grads_and_params(model, g, tol, after=True):
+    gmax = _gmax(g)
+    for i, p in enumerate(model.parameters()):
+        ref = g[f"g{i}"]
+        if ref.size == 0 or _noise_only(g, i, gmax):
+            continue
+        assert _rel(p.grad, ref) < tol, f"grad {i}"
+    if after:
+        for i, p in enumerate(model.parameters()):
+            if not _noise_only(g, i, gmax):
+                assert _rel(p.data, g[f"a{i}"]) < tol, f"param {i}"
+
+
+def _gpt(device, tol):
+    g = load_golden("model_gpt")
+    np.random.seed(0)
+    model = M.build_gpt(neunet, nn, device=device)
+    model.eval()
+    _load_params(model, g)
+    opt = Adam(model.parameters(), lr=1.5e-4, betas=(0.9, 0.98), eps=1e-9)
+    grads_checked = False
+    for step in range(2):
+        opt.zero_grad()
+        loss, logits = M.gpt_train_step(neunet, nn, model, opt, g["batch"])
+        np.testing.assert_allclose(float(loss.item()), g["losses"][step], rtol=max(tol, 1e-5))
+        if step == 0:
+            assert _rel(logits.data, g["logits"]) < tol
+            # unused cross_attn parameters never receive a gradient (skipped by Adam, optim.py:21-22)
+            none = [i for i, p in enumerate(model.parameters()) if p.grad is None]
+            assert len(none) == 2 * 8 and all(g[f"g{i}"].size == 0 for i in none)
+            _check_grads_and_params(model, g, tol, after=False)
+            grads_checked = True
+    assert grads_checked
+    for i, p in enumerate(model.parameters()):
+        assert _rel(p.data, g[f"a{i}"]) < tol
+
+
+def _conv_classifier(device, tol):
+    g = load_golden("model_conv_classifier")
+    np.random.seed(0)
+    net = M.build_conv_classifier(neunet, nn, device=device)
+    _load_params(net, g)
+    opt = Adam(net.parameters(), lr=1e-3)
+    for step in range(2):
+        opt.zero_grad()
+        out = net(neunet.tensor(g["x"], device=device))
+        loss = nn.MSELoss()(out, neunet.tensor(g["y"], device=device))
+        loss.backward()
+        if step == 0:
+            assert _rel(out.data, g["out"]) < tol
+            _check_grads_and_params(net, g, tol * 5, after=False)
+        opt.step()
+        np.testing.assert_allclose(float(loss.item()), g["losses"][step], rtol=max(tol, 1e-5))
+    # running mean sees the conv bias that Adam moved by +-lr on a pure round-off gradient: atol = 2 lr
+    np.testing.assert_allclose(_host(net.bn.running_mean.data), g["running_mean"], rtol=1e-3, atol=2.5e-3)
+    gmax = _gmax(g)
+    for i, p in enumerate(net.parameters()):
+        if not _noise_only(g, i, gmax):
+            assert _rel(p.data, g[f"a{i}"]) < tol * 5
+
+
+def _unet(device, tol):
+    g = load_golden("model_unet")
+    np.random.seed(0)
+    unet = M.build_unet(neunet, nn, device=device)
+    _load_params(unet, g)
+    opt = Adam(unet.parameters(), lr=2e-4)
+    opt.zero_grad()
+    out = unet(neunet.tensor(g["x"], device=device), neunet.tensor(g["temb"], device=device))
+    loss = nn.MSELoss()(out, neunet.tensor(g["noise"], device=device))
+    loss.backward()
+    opt.step()
+    np.testing.assert_allclose(float(loss.item()), float(g["loss"]), rtol=max(tol, 1e-5))
+    assert _rel(out.data, g["out"]) < tol
+    _check_grads_and_params(unet, g, tol * 10)
+
+
+def test_gpt_cpu():
+    _gpt("cpu", 2e-5)
+
+
+def test_conv_classifier_cpu():
+    _conv_classifier("cpu", 2e-5)
+
+
+def test_unet_cpu():
+    _unet("cpu", 5e-5)
+
+
+@pytest.fixture
+def _gpu():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neunet import b200
+    b200.set_precision("bf16x3")
+    yield
+    torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+def test_gpt_gpu(_gpu):
+    _gpt("cuda", 1e-4)
+
+
+@pytest.mark.gpu
+def test_conv_classifier_gpu(_gpu):
+    _conv_classifier("cuda", 1e-4)
+
+
+@pytest.mark.gpu
+def test_unet_gpu(_gpu):
+    _unet("cuda", 2e-4)
