@@ -501,7 +501,10 @@ class Tensor:
             if a.requires_grad:
                 # assignment, not accumulation: duplicate indices keep the last write (autograd.py:909-910)
                 full = xp.zeros_like(a.data)
-                full[index] = grad
+                if a.device == "cuda" and _be.is_device_array(index) and index.dtype == _be.torch.int64:
+                    _assign_last_wins(full, index, grad)
+                else:
+                    full[index] = grad
                 a.apply_grad(full)
         out.grad_fn = grad_fn
         return out
@@ -577,6 +580,24 @@ class Tensor:
                 tape.append(node)
         for v in reversed(tape):
             v.grad_fn(*v.args, grad=v.grad)
+
+
+def _assign_last_wins(full, index, grad):
+    """``full[index] = grad`` for one integer index tensor over the first axis, with NumPy's
+    deterministic semantics for duplicate indices (the LAST occurrence wins). A plain device
+    index_put with duplicates is non-deterministic; the reference's CPU path (the parity oracle)
+    keeps the last write (autograd.py:909-910)."""
+    torch = _be.torch
+    flat = index.reshape(-1)
+    n = flat.numel()
+    rows = full.shape[0]
+    flat = torch.where(flat < 0, flat + rows, flat)
+    order = torch.arange(n, device=flat.device)
+    last = torch.full((rows,), -1, dtype=torch.int64, device=flat.device)
+    last.scatter_reduce_(0, flat, order, reduce="amax", include_self=True)
+    hit = last >= 0
+    g2 = grad.reshape((n,) + tuple(full.shape[1:]))
+    full[hit] = g2[last[hit]]
 
 
 def _no_grad_fn(*args, **kwargs):

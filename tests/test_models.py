@@ -48,9 +48,25 @@ def _check_grads_and_params(model, g, tol, after=True):
             continue
         assert _rel(p.grad, ref) < tol, f"grad {i}"
     if after:
-        for i, p in enumerate(model.parameters()):
-            if not _noise_only(g, i, gmax):
-                assert _rel(p.data, g[f"a{i}"]) < tol, f"param {i}"
+        _check_params_after(model, g, tol)
+
+
+def _check_params_after(model, g, tol, lr_atol=2.5e-3):
+    """Post-Adam parameters. Adam's first steps move every element by ~lr * sign(grad), so elements
+    whose gradient is round-off-sized may legitimately differ by up to ~2 lr; all other elements must
+    agree to `tol` (relative to the tensor's max)."""
+    gmax = _gmax(g)
+    for i, p in enumerate(model.parameters()):
+        ref_g, ref_a = g[f"g{i}"], g[f"a{i}"]
+        got = _host(p.data).astype(np.float64)
+        if ref_g.size == 0:
+            assert _rel(got, ref_a) < tol, f"param {i} (no grad)"
+            continue
+        solid = np.abs(ref_g) >= 1e-4 * gmax
+        scale = max(np.abs(ref_a).max(), 1e-12)
+        err = np.abs(got - ref_a)
+        assert (err[solid] / scale).max(initial=0.0) < tol, f"param {i}"
+        assert err[~solid].max(initial=0.0) < lr_atol, f"param {i} (round-off gradient elements)"
 
 
 def _gpt(device, tol):
@@ -73,8 +89,7 @@ def _gpt(device, tol):
             _check_grads_and_params(model, g, tol, after=False)
             grads_checked = True
     assert grads_checked
-    for i, p in enumerate(model.parameters()):
-        assert _rel(p.data, g[f"a{i}"]) < tol
+    _check_params_after(model, g, tol, lr_atol=4e-4)
 
 
 def _conv_classifier(device, tol):
@@ -95,10 +110,7 @@ def _conv_classifier(device, tol):
         np.testing.assert_allclose(float(loss.item()), g["losses"][step], rtol=max(tol, 1e-5))
     # running mean sees the conv bias that Adam moved by +-lr on a pure round-off gradient: atol = 2 lr
     np.testing.assert_allclose(_host(net.bn.running_mean.data), g["running_mean"], rtol=1e-3, atol=2.5e-3)
-    gmax = _gmax(g)
-    for i, p in enumerate(net.parameters()):
-        if not _noise_only(g, i, gmax):
-            assert _rel(p.data, g[f"a{i}"]) < tol * 5
+    _check_params_after(net, g, tol * 5)
 
 
 def _unet(device, tol):
