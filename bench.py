@@ -35,6 +35,13 @@ for p in (os.path.join(ROOT, "numpy-nn-model_b200"), ROOT):
 import numpy as np  # noqa: E402
 
 MLP = dict(name="mlp_784_128_10", d_in=784, d_hid=128, d_out=10, batch=4096, lr=1e-3)
+# examples/gpt.ipynb cells 8, 11: V=15000, d=512, 8 heads, d_ff=2048, 8 layers, Adam(1.5e-4, (0.9, 0.98), 1e-9);
+# synthetic tokens in [3, V) (ids 0/1/2 are pad/sos/eos), T=64, 64 sequences per GPU
+GPT = dict(name="gpt_small", vocab=15000, d_model=512, heads=8, d_ff=2048, layers=8, seq=64, batch=64,
+           lr=1.5e-4, betas=(0.9, 0.98), eps=1e-9, dropout=0.1)
+for _p in (os.path.join(ROOT, "examples"),):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 
 def peaks():
@@ -81,6 +88,22 @@ def cpu_mlp_run(cfg, steps, warmup, batch=None, seed=0):
     return dict(samples_per_s=B * steps / dt, ms_per_step=dt / steps * 1e3, batch=B, steps=steps)
 
 
+def cpu_gpt_run(cfg, steps, warmup, batch=8, seed=0):
+    """Oracle port of the GPT step (oracle/gpt_numpy.py) on a bounded sample: `batch` sequences."""
+    from oracle import gpt_numpy as G
+    ps = G.init_params(cfg["vocab"], cfg["d_model"], cfg["d_ff"], cfg["layers"], seed=seed)
+    ms, vs = [np.zeros_like(p) for p in ps], [np.zeros_like(p) for p in ps]
+    rng = np.random.RandomState(seed)
+    data = rng.randint(3, cfg["vocab"], (batch, cfg["seq"] + 1))
+    for t in range(1, warmup + 1):
+        G.train_step(ps, ms, vs, t, data, cfg["heads"], lr=cfg["lr"], betas=cfg["betas"], eps=cfg["eps"])
+    t0 = time.perf_counter()
+    for t in range(warmup + 1, warmup + steps + 1):
+        G.train_step(ps, ms, vs, t, data, cfg["heads"], lr=cfg["lr"], betas=cfg["betas"], eps=cfg["eps"])
+    dt = time.perf_counter() - t0
+    return dict(samples_per_s=batch * steps / dt, ms_per_step=dt / steps * 1e3, batch=batch, steps=steps)
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -90,23 +113,36 @@ def host_threads():
     return max(n, 1), len(os.sched_getaffinity(0))
 
 
+def workload_label(args):
+    if args.workload == "gpt":
+        c = GPT
+        return c, (f"{c['name']} V={c['vocab']} d={c['d_model']} h={c['heads']} ff={c['d_ff']} L={c['layers']} T={c['seq']}, "
+                   f"batch {c['batch']}/GPU (BASELINE.json configs[3], examples/gpt.ipynb dims)")
+    c = MLP
+    return c, f"{c['name']} batch {c['batch']}/GPU, Linear fwd/bwd + fused Swish + fused AdamW (BASELINE.json configs[1])"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = MLP
+    cfg, label = workload_label(args)
     steps = max(args.steps, 1)
-    r = cpu_mlp_run(cfg, steps=steps, warmup=max(args.warmup, 1))
+    if args.workload == "gpt":
+        steps = min(steps, 5)
+        r = cpu_gpt_run(cfg, steps=steps, warmup=1, batch=8)
+        sample = f"{steps} steps of 8 sequences x T={cfg['seq']} (oracle/gpt_numpy.py; cost is linear in batch)"
+    else:
+        r = cpu_mlp_run(cfg, steps=steps, warmup=max(args.warmup, 1))
+        sample = f"{steps} steps of batch {cfg['batch']} (oracle/restated.py)"
     blas, cores = host_threads()
     line = {
         "impl": "reference", "metric": "training samples/sec", "value": r["samples_per_s"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']} batch {cfg['batch']} (BASELINE.json configs[1]), reference CPU path",
-                   "global_batch": cfg["batch"]},
+        "config": {"workload": label + " -- reference CPU path (NumPy/OpenBLAS oracle port)", "global_batch": r["batch"]},
         "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": blas, "kind": "port",
-                         "sample": f"{steps} steps of batch {cfg['batch']} (oracle/restated.py, NumPy/OpenBLAS, "
-                                   f"{cores} cores visible)"},
+                         "sample": sample + f", NumPy/OpenBLAS, {cores} cores visible"},
         "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,14 +193,119 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+class MlpWorkload:
+    """BASELINE configs[1]: LinearSwish(784,128) -> Linear(128,10) -> CrossEntropy, AdamW."""
+
+    def __init__(self, neunet, nn, optim, rank):
+        c = self.cfg = MLP
+        self.B = c["batch"]
+        np.random.seed(0)  # identical init on every rank
+        self.l1 = nn.LinearSwish(c["d_in"], c["d_hid"]).to("cuda")
+        self.l2 = nn.Linear(c["d_hid"], c["d_out"]).to("cuda")
+        self.params = self.l1.parameters() + self.l2.parameters()
+        self.opt = optim.AdamW(self.params, lr=c["lr"])
+        self.loss_fn = nn.CrossEntropyLoss()
+        import torch
+        rng = np.random.RandomState(1000 + rank)
+        self.host = [(torch.from_numpy(rng.randn(self.B, c["d_in"]).astype(np.float32)).pin_memory(),
+                      torch.from_numpy(rng.randint(0, c["d_out"], self.B).astype(np.int32)).pin_memory()) for _ in range(8)]
+        self.inputs = [neunet.tensor(self.host[0][0].numpy(), device="cuda"),
+                       neunet.tensor(self.host[0][1].numpy(), dtype=np.int32, device="cuda")]
+
+    def forward_loss(self, x, y):
+        return self.loss_fn(self.l2(self.l1(x)), y)
+
+    def roofline(self, pk, b200):
+        """Dominant kernel = layer-1 forward GEMM (4096 x 784 x 128 + bias + Swish, Z and O written)."""
+        import torch
+        c = self.cfg
+        B, K, N = c["batch"], c["d_in"], c["d_hid"]
+        ms = _probe_gemm(b200, B, K, N, act=b200.ACT_SWISH)
+        alg = B * K * 2 + N * K * 2 + 2 * B * N * 4
+        ach = alg / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "gemm_tcgen05_kernel: Linear-1 forward 4096x784x128 + bias + Swish epilogue",
+                "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "us_per_launch": ms * 1e3, "algorithmic_bytes": alg, "flops_per_launch": 2 * B * K * N,
+                "peak_source": pk["source"] + " hbm_gbs"}
+
+    def cpu(self):
+        r = cpu_mlp_run(self.cfg, steps=150, warmup=3)
+        return r, f"{r['steps']} steps of batch {r['batch']} (oracle/restated.py)"
+
+
+class GptWorkload:
+    """BASELINE configs[3]: examples/gpt.ipynb model (examples/models.py), Adam, CrossEntropy(ignore pad)."""
+
+    def __init__(self, neunet, nn, optim, rank):
+        import models as M
+        import torch
+        c = self.cfg = GPT
+        self.B, self.T = c["batch"], c["seq"]
+        np.random.seed(0)
+        self.model = M.build_gpt(neunet, nn, vocab=c["vocab"], d_model=c["d_model"], n_heads=c["heads"], d_ff=c["d_ff"],
+                                 n_layers=c["layers"], pad_idx=0, device="cuda", dropout=c["dropout"])
+        self.model.train()
+        self.params = self.model.parameters()
+        self.opt = optim.Adam(self.params, lr=c["lr"], betas=c["betas"], eps=c["eps"])
+        self.loss_fn = nn.CrossEntropyLoss(ignore_index=0)
+        rng = np.random.RandomState(1000 + rank)
+        self.host = []
+        for _ in range(8):
+            tok = rng.randint(3, c["vocab"], (self.B, self.T + 1))
+            self.host.append((torch.from_numpy(tok[:, :-1].astype(np.int32)).pin_memory(),
+                              torch.from_numpy(tok[:, 1:].reshape(-1).astype(np.int32)).pin_memory()))
+        # no padding in synthetic data -> the mask is the causal mask (built once, like GPT.get_sub_mask)
+        causal = np.logical_not(np.triu(np.ones((self.T, self.T)), k=1).astype(int)).astype(np.int32)
+        self.mask = neunet.tensor(np.broadcast_to(causal, (self.B, self.T, self.T)).copy(), dtype=np.int32, device="cuda")
+        self.inputs = [neunet.tensor(self.host[0][0].numpy(), dtype=np.int32, device="cuda"),
+                       neunet.tensor(self.host[0][1].numpy(), dtype=np.int32, device="cuda")]
+
+    def forward_loss(self, ids, tgt):
+        out, _ = self.model.decoder(ids, self.mask)
+        return self.loss_fn(out.reshape(out.shape[0] * out.shape[1], out.shape[2]), tgt)
+
+    def roofline(self, pk, b200):
+        """Dominant kernel class = the FFN GEMMs; probe fc_1 forward: (B*T) x 512 x 2048 (+bias)."""
+        c = self.cfg
+        M_, K, N = c["batch"] * c["seq"], c["d_model"], c["d_ff"]
+        ms = _probe_gemm(b200, M_, K, N, act=b200.ACT_NONE)
+        fl = 2.0 * M_ * K * N
+        ach = fl / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel: FFN fc_1 forward {M_}x{K}x{N} + bias",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "us_per_launch": ms * 1e3,
+                "flops_per_launch": fl, "algorithmic_bytes": M_ * K * 2 + N * K * 2 + M_ * N * 4,
+                "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
+
+    def cpu(self):
+        r = cpu_gpt_run(self.cfg, steps=3, warmup=1, batch=8)
+        return r, f"{r['steps']} steps of 8 sequences x T={self.cfg['seq']} (oracle/gpt_numpy.py; cost is linear in batch)"
+
+
+def _probe_gemm(b200, M_, K, N, act):
+    """Median CUDA-event time (ms) of ONE forward GEMM launch on staged operands, L2 flushed before each."""
+    import torch
+    x = torch.randn(M_, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    bias = torch.zeros(1, N, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    times = []
+    for it in range(23):
+        flush.zero_()
+        t = b200.time_linear_forward_gemm(x, w, bias, act=act)
+        if it >= 3:
+            times.append(t)
+    return float(np.median(times))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import neunet
     import neunet.nn as nn
-    from neunet import b200
-    from neunet.optim import AdamW
+    from neunet import b200, optim
+    from neunet.distributed import GradBucket
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,33 +318,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     b200.require_device()
     b200.set_precision("bf16")
-    cfg = MLP
-    B = cfg["batch"]
+    torch.manual_seed(1234 + rank)
     pk = peaks()
+    _, label = workload_label(args)
+    wl = (GptWorkload if args.workload == "gpt" else MlpWorkload)(neunet, nn, optim, rank)
+    B, opt, params = wl.B, wl.opt, wl.params
 
-    # ---- model (identical init on every rank), per-rank synthetic data ---------------------------
-    np.random.seed(0)
-    l1 = nn.LinearSwish(cfg["d_in"], cfg["d_hid"]).to("cuda")
-    l2 = nn.Linear(cfg["d_hid"], cfg["d_out"]).to("cuda")
-    params = l1.parameters() + l2.parameters()
-    opt = AdamW(params, lr=cfg["lr"])
-    loss_fn = nn.CrossEntropyLoss()
-    rng = np.random.RandomState(1000 + rank)
-    n_host = 8  # distinct host batches cycled through (pinned)
-    hx = [torch.from_numpy(rng.randn(B, cfg["d_in"]).astype(np.float32)).pin_memory() for _ in range(n_host)]
-    hy = [torch.from_numpy(rng.randint(0, cfg["d_out"], B).astype(np.int32)).pin_memory() for _ in range(n_host)]
-    x = neunet.tensor(hx[0].numpy(), device="cuda")
-    y = neunet.tensor(hy[0].numpy(), dtype=np.int32, device="cuda")
-
-    from neunet.distributed import GradBucket
     bucket = GradBucket(params) if world > 1 else None
     if bucket is not None:
         bucket.broadcast_parameters()
         opt.grad_scale = 1.0 / world
 
-    def train_step(xb, yb):
+    def train_step(*inputs):
         opt.zero_grad()
-        loss = loss_fn(l2(l1(xb)), yb)
+        loss = wl.forward_loss(*inputs)
         loss.backward()
         if bucket is not None:
             bucket.all_reduce()  # the one collective: sum of gradients over NVLink (NCCL)
@@ -211,29 +339,33 @@ def run_ours(args):
         return loss
 
     # ---- warm-up (eager) then capture the whole step as a CUDA graph ------------------------------
-    for _ in range(max(args.warmup, 3)):
-        train_step(x, y)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        train_step(*wl.inputs)
     torch.cuda.synchronize()
     graphed, graph_err = None, None
     if not args.no_graph:
         try:
-            graphed = b200.GraphedStep(train_step, [x, y], optimizer=opt, warmup=2)
+            graphed = b200.GraphedStep(train_step, wl.inputs, optimizer=opt, warmup=2)
         except Exception as e:  # report, never hide
-            graph_err = f"{type(e).__name__}: {e}"
+            graph_err = f"{type(e).__name__}: {e}"[:300]
             graphed = None
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # 2x L2: evicts the working set
 
     def one_step():
-        return graphed.replay() if graphed is not None else train_step(x, y)
+        return graphed.replay() if graphed is not None else train_step(*wl.inputs)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(W):
         flush.zero_()
         one_step()
     barrier()
@@ -241,8 +373,6 @@ def run_ours(args):
     # ---- timed: K steps, each bracketed by CUDA events, L2 flushed in between ---------------------
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    b200.reset_launch_count()
-    launches_before = b200.launch_count()
     with ClockSampler(local) as clk:
         barrier()
         wall0 = time.perf_counter()
@@ -253,11 +383,16 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         wall = time.perf_counter() - wall0
+        # keep the GPU busy a little longer so nvidia-smi (100 ms period) sees clocks under this load
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end:
+            one_step()
+        torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_s = sum(step_ms) / 1e3
     # launches per step: count one eager step (graph replays do not pass through the counter)
     b200.reset_launch_count()
-    train_step(x, y)
+    train_step(*wl.inputs)
     torch.cuda.synchronize()
     launches_per_step = b200.launch_count()
     t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
@@ -267,15 +402,17 @@ def run_ours(args):
     value = B * world * K / dev_s
 
     # ---- e2e: host batches through the public API, H2D + D2H inside the timed region --------------
+    n_host = len(wl.host)
+
     def e2e_step(i):
-        hb, yb = hx[i % n_host], hy[i % n_host]
+        hb = wl.host[i % n_host]
         if graphed is not None:
-            graphed.load(hb, yb)
+            graphed.load(*hb)
             loss = graphed.replay()
         else:
-            x.data.copy_(hb, non_blocking=True)
-            y.data.copy_(yb, non_blocking=True)
-            loss = train_step(x, y)
+            for dst, src in zip(wl.inputs, hb):
+                dst.data.copy_(src, non_blocking=True)
+            loss = train_step(*wl.inputs)
         return loss.item()  # device -> host read of the step's result
 
     for i in range(3):
@@ -290,23 +427,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world * K / float(t.item())
-    h2d = hx[0].numel() * 4 + hy[0].numel() * 4
+    h2d = sum(h.numel() * h.element_size() for h in wl.host[0])
     d2h = 4
 
-    # ---- roofline of the dominant kernel: layer-1 forward GEMM (tcgen05), timed alone ---------------
-    roof = roofline_probe(cfg, pk)
+    roof = wl.roofline(pk, b200)
 
-    line = None
     if rank == 0:
-        cpu = cpu_mlp_run(cfg, steps=150, warmup=3)
+        cpu, cpu_sample = wl.cpu()
         blas, cores = host_threads()
         line = {
             "metric": "training samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_s / K * 1e3, "higher_is_better": True,
+            "warmup": W, "ms_per_step": dev_s / K * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']} batch {B}/GPU, Linear fwd/bwd + fused Swish + fused AdamW "
-                                   "(BASELINE.json configs[1])",
-                       "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": label, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "flushed (256 MiB write) between timed steps",
                        "step_execution": "cuda-graph replay of the public-API step" if graphed is not None else "eager",
                        "graph_error": graph_err, "precision": b200.get_precision(),
@@ -316,8 +449,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * K,
             "roofline": roof,
             "cpu_baseline": {"value": cpu["samples_per_s"], "unit": "samples/s", "cores": blas, "kind": "port",
-                             "sample": f"{cpu['steps']} steps of batch {cpu['batch']} (oracle/restated.py, "
-                                       f"NumPy/OpenBLAS, {cores} cores visible)"},
+                             "sample": cpu_sample + f", NumPy/OpenBLAS, {cores} cores visible"},
             "final_loss": last_loss,
         }
         print(json.dumps(line))
@@ -327,41 +459,13 @@ def run_ours(args):
     return 0
 
 
-def roofline_probe(cfg, pk):
-    """Times the dominant kernel of the step alone: the layer-1 forward GEMM
-    (4096 x 784 x 128, bf16 operands already staged, fp32 Z and Swish(Z) written by the epilogue).
-    Algorithmic bytes = X bf16 + W bf16 + Z fp32 + O fp32; bound = HBM."""
-    import torch
-
-    from neunet import b200
-    B, K, N = cfg["batch"], cfg["d_in"], cfg["d_hid"]
-    x = torch.randn(B, K, device="cuda")
-    w = torch.randn(N, K, device="cuda") / K ** 0.5
-    bias = torch.zeros(1, N, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    iters = 20
-    times = []
-    for it in range(iters + 3):
-        flush.zero_()
-        t = b200.time_linear_forward_gemm(x, w, bias, act=b200.ACT_SWISH)
-        if it >= 3:
-            times.append(t)
-    ms = float(np.median(times))
-    alg_bytes = B * K * 2 + N * K * 2 + 2 * B * N * 4
-    achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "gemm_tcgen05_kernel (Linear-1 forward + bias + Swish epilogue)",
-            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "traffic": None, "us_per_launch": ms * 1e3, "algorithmic_bytes": alg_bytes, "peak_source": pk["source"],
-            "flops_per_launch": 2 * B * K * N}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mlp", choices=["mlp"])
+    ap.add_argument("--workload", default="mlp", choices=["mlp", "gpt"])
     ap.add_argument("--no-graph", action="store_true", help="time the eager public-API step instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -595,9 +595,10 @@ def _assign_last_wins(full, index, grad):
     order = torch.arange(n, device=flat.device)
     last = torch.full((rows,), -1, dtype=torch.int64, device=flat.device)
     last.scatter_reduce_(0, flat, order, reduce="amax", include_self=True)
-    hit = last >= 0
+    hit = (last >= 0).reshape((rows,) + (1,) * (full.ndim - 1))
     g2 = grad.reshape((n,) + tuple(full.shape[1:]))
-    full[hit] = g2[last[hit]]
+    # gather form (static shapes, no host sync: legal inside CUDA-graph capture)
+    full.copy_(torch.where(hit, g2[last.clamp(min=0)], torch.zeros((), dtype=full.dtype, device=full.device)))
 
 
 def _no_grad_fn(*args, **kwargs):

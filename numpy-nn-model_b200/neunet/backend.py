@@ -80,8 +80,8 @@ class _TorchRandom:
     def binomial(self, n, p, size=None):
         # device-side Bernoulli: the reference's NumPy binomial costs 0.17 s/step on the GPT example
         if n == 1:
-            gen = self._xp.generator()
-            return (torch.rand(tuple(size), device=self._xp.device, generator=gen) < p).to(torch.float32)
+            # torch's default CUDA generator: seeded by torch.manual_seed and safe under graph capture
+            return (torch.rand(tuple(size), device=self._xp.device) < p).to(torch.float32)
         return self._xp.array(np.random.binomial(n, p, size), dtype=np.float32)
 
     def randint(self, low, high=None, size=None):

@@ -217,9 +217,9 @@ def main():
 
 
 def model_goldens():
-    """Whole-model fixtures: the SAME model definitions (tests/models.py) run on the reference."""
+    """Whole-model fixtures: the SAME model definitions (examples/models.py) run on the reference."""
     neunet, nn, optim = import_reference()
-    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(OUT)), "examples"))
     import models as M
     f32 = np.float32
 

@@ -9,7 +9,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "numpy-nn-model_b200")
-for p in (PKG, ROOT):
+EXAMPLES = os.path.join(ROOT, "examples")
+for p in (PKG, ROOT, EXAMPLES):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -1,5 +1,5 @@
 """Whole-model parity against fixtures produced by running the SAME model definitions
-(tests/models.py) on the unmodified reference: GPT (examples/gpt.ipynb architecture), the conv
+(examples/models.py) on the unmodified reference: GPT (examples/gpt.ipynb architecture), the conv
 digits classifier and a two-level DDPM-style UNet. Checks loss, outputs, every parameter gradient
 and the post-Adam parameters -- on "cpu" (host mirror) and, marked gpu, on "cuda" (sm_100a kernels)."""
 import numpy as np
