@@ -112,18 +112,30 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
     }
 }
 
-__global__ void colsum_reduce_kernel(const float* partial, int nparts, long long cols, float* out) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] = sum_p partial[p][c]: 32 columns x 8 partial-lanes per block, fixed-order tree at the end
+// (deterministic), so up to 1024 partial rows reduce in a few microseconds.
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int nparts,
+                                                            long long cols, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * 32 + cx;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(long long)p * cols + c];
-    out[c] = s;
+    if (c < cols)
+        for (int p = py; p < nparts; p += 8) s += partial[(long long)p * cols + c];
+    red[py][cx] = s;
+    __syncthreads();
+    if (py == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += red[y][cx];
+        out[c] = t;
+    }
 }
 
 }  // namespace
 
 size_t stage_colsum_scratch_bytes(int64_t cols) {
-    return (size_t)round_up(cols * 4 * 64, 256);  // <= 64 row chunks per column
+    return (size_t)round_up(cols * 4 * 1024, 256);  // <= 1024 row chunks per column
 }
 
 int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst_hi,
@@ -161,8 +173,8 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     const int sms = num_sms();
     int64_t want_y = std::max<int64_t>(1, (int64_t)sms * 16 / std::max<int64_t>(1, gx * batch));
     want_y = std::min<int64_t>(want_y, 1024);
-    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(want_y, 64 / batch));
-    NNB_REQUIRE(!colsum || batch <= 64, "stage_operand: colsum with batch > 64");
+    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(want_y, 1024 / batch));
+    NNB_REQUIRE(!colsum || batch <= 1024, "stage_operand: colsum with batch > 1024");
     int64_t rpb = std::max<int64_t>(ty, ceil_div(src.rows, want_y));
     rpb = round_up(rpb, ty);
     const int64_t gy = ceil_div(src.rows, rpb);
@@ -181,7 +193,7 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     NNB_CUDA_OK(cudaGetLastError());
     if (colsum) {
         const int nparts = (int)(gy * batch);
-        colsum_reduce_kernel<<<(unsigned)ceil_div(src.cols, 256), 256, 0, stream>>>(
+        colsum_reduce_kernel<<<(unsigned)ceil_div(src.cols, 32), 256, 0, stream>>>(
             colsum_scratch, nparts, src.cols, colsum);
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());

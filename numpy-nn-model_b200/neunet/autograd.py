@@ -585,8 +585,7 @@ class Tensor:
 def _assign_last_wins(full, index, grad):
     """``full[index] = grad`` for one integer index tensor over the first axis, with NumPy's
     deterministic semantics for duplicate indices (the LAST occurrence wins). A plain device
-    index_put with duplicates is non-deterministic; the reference's CPU path (the parity oracle)
-    keeps the last write (autograd.py:909-910)."""
+    index_put with duplicates is non-deterministic; the reference's CPU path keeps the last write (autograd.py:909-910)."""
     torch = _be.torch
     flat = index.reshape(-1)
     n = flat.numel()

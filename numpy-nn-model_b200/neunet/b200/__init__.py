@@ -232,7 +232,8 @@ def _staged_weight(owner, w2d: torch.Tensor, rows: int, cols: int):
 
 
 # ---- nn.Linear -------------------------------------------------------------------------------------
-def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=None, keep_x_staged=False):
+def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=None, keep_x_staged=False,
+                   x_owner=None):
     """O = act(x . w^T + bias); x: (..., K), w: (N, K), bias: (1, N) or None.
     Returns (O, Z, x_staged): Z is the pre-activation when save_z (else None); x_staged holds the
     bf16 planes of x for the backward pass when keep_x_staged (else None)."""
@@ -251,11 +252,25 @@ def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=
     wsb = L.nnb_linear_workspace_bytes(M, K, N, prec, 0)
     ws = _workspace(wsb)
     xst = None
-    if keep_x_staged:
-        xst = torch.empty(L.nnb_weight_staged_bytes(M, K, prec), dtype=torch.uint8, device="cuda")
-        xst._b200_prec = prec
-    _check(L.nnb_linear_forward(_ptr(x2), _ptr(w), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta), prec,
-                                _ptr(wst), _ptr(xst), _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward")
+    # several layers often read the same activation (q/k/v projections of one RMSNorm output): the bf16
+    # planes are cached on the producing Tensor, keyed by storage + torch's version counter
+    xkey = (x2.data_ptr(), x._version, prec, M, K)
+    cached = getattr(x_owner, "_b200_xst", None) if x_owner is not None else None
+    if cached is not None and cached[0] == xkey:
+        xst = cached[1]
+        _check(L.nnb_linear_forward_staged(_ptr(xst), _ptr(wst), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta),
+                                           prec, _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward_staged")
+    else:
+        if keep_x_staged:
+            xst = torch.empty(L.nnb_weight_staged_bytes(M, K, prec), dtype=torch.uint8, device="cuda")
+            xst._b200_prec = prec
+            if x_owner is not None:
+                try:
+                    x_owner._b200_xst = (xkey, xst)
+                except AttributeError:
+                    pass
+        _check(L.nnb_linear_forward(_ptr(x2), _ptr(w), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta), prec,
+                                    _ptr(wst), _ptr(xst), _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward")
     out = out.reshape(lead + (N,))
     if z is not None:
         z = z.reshape(lead + (N,))

@@ -71,7 +71,7 @@ class Linear(Module):
             # the bf16 planes of X made for the forward GEMM are kept for wgrad (dW = dZ^T . X)
             O, Z, xst = b200.linear_forward(X.data, self.weight.data, b.data if b is not None else None,
                                             act=self._act, beta=self._beta, save_z=bool(self._act), owner=self.weight,
-                                            keep_x_staged=self.training_mode())
+                                            keep_x_staged=self.training_mode(), x_owner=X)
         else:
             xst = None
             Z = np.matmul(X.data, self.weight.data.T)
