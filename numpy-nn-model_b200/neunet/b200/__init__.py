@@ -25,7 +25,15 @@ ACT_NONE, ACT_SWISH = 0, 1
 OPT_ADAM_L2, OPT_ADAMW = 0, 1
 
 _PREC_NAMES = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
-_state = {"prec": _PREC_NAMES[os.environ.get("NEUNET_B200_PREC", "bf16x3").lower()], "weights_epoch": 0}
+_state = {"prec": _PREC_NAMES[os.environ.get("NEUNET_B200_PREC", "bf16x3").lower()], "weights_epoch": 0,
+          "capture_epoch": 0}
+
+
+def _cache_scope():
+    """Staged-operand caches are only valid inside the scope that created them: a CUDA-graph capture
+    must re-stage everything it reads (replays do not re-run this Python), so the key carries
+    (capturing?, capture id)."""
+    return (torch.cuda.is_current_stream_capturing(), _state["capture_epoch"])
 
 
 def set_precision(name: str) -> None:
@@ -210,7 +218,7 @@ def _staged_weight(owner, w2d: torch.Tensor, rows: int, cols: int):
     """bf16 planes of a weight matrix, converted once per optimizer step. `owner` is the Parameter
     (any object that can hold an attribute); None disables caching."""
     prec = _state["prec"]
-    key = (w2d.data_ptr(), w2d._version, _state["weights_epoch"], prec, rows, cols)
+    key = (w2d.data_ptr(), w2d._version, _state["weights_epoch"], prec, rows, cols, _cache_scope())
     cached = getattr(owner, "_b200_staged", None) if owner is not None else None
     if cached is not None and cached.key == key:
         return cached.buf
@@ -254,7 +262,7 @@ def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=
     xst = None
     # several layers often read the same activation (q/k/v projections of one RMSNorm output): the bf16
     # planes are cached on the producing Tensor, keyed by storage + torch's version counter
-    xkey = (x2.data_ptr(), x._version, prec, M, K)
+    xkey = (x2.data_ptr(), x._version, prec, M, K, _cache_scope())
     cached = getattr(x_owner, "_b200_xst", None) if x_owner is not None else None
     if cached is not None and cached[0] == xkey:
         xst = cached[1]
@@ -601,9 +609,11 @@ class GraphedStep:
         if optimizer is not None and getattr(optimizer, "_fused", None) is not None:
             optimizer._fused.set_step(optimizer.t)
         self.optimizer = optimizer
+        _state["capture_epoch"] += 1  # invalidates every staged-operand cache made outside this capture
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.outputs = fn(*self.inputs)
+        _state["capture_epoch"] += 1
         if optimizer is not None:
             optimizer.t -= 1  # the capture pass itself launched nothing
         self._dev_t = optimizer.t if optimizer is not None else 0  # value of the device step counter
