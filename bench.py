@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- training samples/s of the neunet dense hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mlp] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gpt|mlp] [--impl ours|reference]
 
-Workload "mlp" = BASELINE.json configs[1]: 2-layer MLP 784 -> 128 -> 10, batch 4096 per GPU, bf16
-tensor-core contractions with fp32 accumulation, Linear fwd/bwd + fused Swish + multi-tensor AdamW,
-CrossEntropy loss, synthetic data, random-init weights (layer init = reference's U(+-1/sqrt(in))).
+Workload "gpt" (default) = BASELINE.json configs[3], the config the headline metric ("training
+samples/sec at 1/2/4/8 B200") is quoted on and that fits one GPU: examples/gpt.ipynb's model verbatim
+(V=15000, d=512, 8 heads, d_ff=2048, 8 layers, dropout 0.1, Adam), T=64, 64 sequences per GPU, bf16
+tensor-core contractions with fp32 accumulation, synthetic tokens, random-init weights. Data parallel
+over N GPUs: batch sharded, gradients all-reduced with NCCL in chunks overlapped with backward.
+Workload "mlp" = configs[1]: 2-layer MLP 784 -> 128 -> 10, batch 4096 per GPU, Linear fwd/bwd + fused
+Swish + multi-tensor AdamW, CrossEntropy loss (layer init = reference's U(+-1/sqrt(in))).
 
-One "step" = zero_grad, forward, loss, backward, optimizer.step on one batch.
+One "step" = zero_grad, forward, loss, backward, (all-reduce,) optimizer.step on one batch.
   value : whole-job samples/s with the batch already resident in HBM; the step is replayed as a CUDA
-          graph captured from the public neunet API (no Python between kernels); each step is timed
-          with CUDA events on the launching stream, L2 is flushed between timed steps, max over ranks.
+          graph captured from the public neunet API (no Python between kernels), timed with CUDA
+          events on the launching stream, max over ranks. gpt: K steps back to back (the per-step
+          working set is far larger than L2); mlp: L2 flushed between the per-step event pairs.
   e2e   : the same metric through the public API with HOST batches: pinned host -> device copy of the
           step's inputs and device -> host read of the loss inside the timed region, every step.
   roofline / cpu_baseline: see DESIGN.md ("Measurement").
@@ -215,18 +220,20 @@ class MlpWorkload:
     def forward_loss(self, x, y):
         return self.loss_fn(self.l2(self.l1(x)), y)
 
+    flush_l2 = True  # the whole working set (~20 MB) fits the 126 MB L2: flush between timed steps
+
     def roofline(self, pk, b200):
         """Dominant kernel = layer-1 forward GEMM (4096 x 784 x 128 + bias + Swish, Z and O written)."""
-        import torch
         c = self.cfg
         B, K, N = c["batch"], c["d_in"], c["d_hid"]
-        ms = _probe_gemm(b200, B, K, N, act=b200.ACT_SWISH)
+        us, nl = b200.probe_linear_gemm(B, K, N, form=0, with_bias=True, swish=True, rounds=5)
         alg = B * K * 2 + N * K * 2 + 2 * B * N * 4
-        ach = alg / (ms * 1e-3) / 1e9
+        ach = alg / (us * 1e-6) / 1e9
         return {"bound": "hbm", "kernel": "gemm_tcgen05_kernel: Linear-1 forward 4096x784x128 + bias + Swish epilogue",
                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
-                "us_per_launch": ms * 1e3, "algorithmic_bytes": alg, "flops_per_launch": 2 * B * K * N,
-                "peak_source": pk["source"] + " hbm_gbs"}
+                "us_per_launch": us, "algorithmic_bytes": alg, "flops_per_launch": 2 * B * K * N,
+                "peak_source": pk["source"] + " hbm_gbs",
+                "how": "graph-paced launches over rotating operand sets > L2, CUDA events (nnb_probe_linear_gemm)"}
 
     def cpu(self):
         r = cpu_mlp_run(self.cfg, steps=150, warmup=3)
@@ -264,38 +271,45 @@ class GptWorkload:
         out, _ = self.model.decoder(ids, self.mask)
         return self.loss_fn(out.reshape(out.shape[0] * out.shape[1], out.shape[2]), tgt)
 
-    def roofline(self, pk, b200):
-        """Dominant kernel class = the FFN GEMMs; probe fc_1 forward: (B*T) x 512 x 2048 (+bias)."""
+    flush_l2 = False  # weights + Adam state (0.65 GB) + activations (> 2 GB) >> 126 MB L2: no flush needed
+
+    def linear_shapes(self):
+        """(K, N, launches per step) of every nn.Linear on the path (gpt cell 2-7)."""
         c = self.cfg
-        M_, K, N = c["batch"] * c["seq"], c["d_model"], c["d_ff"]
-        ms = _probe_gemm(b200, M_, K, N, act=b200.ACT_NONE)
-        fl = 2.0 * M_ * K * N
-        ach = fl / (ms * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel: FFN fc_1 forward {M_}x{K}x{N} + bias",
+        d, ff, V, L = c["d_model"], c["d_ff"], c["vocab"], c["layers"]
+        return [(d, d, 4 * L, "wq/wk/wv/fc"), (d, ff, L, "ffn.fc_1"), (ff, d, L, "ffn.fc_2"), (d, V, 1, "fc_out")]
+
+    def roofline(self, pk, b200):
+        """Dominant kernel = gemm_tcgen05_kernel. One step launches it in 12 Linear shape x form classes
+        (4 layer shapes x fwd/dgrad/wgrad); every class is timed GPU-paced on rotating operand sets > L2 and
+        `achieved` = (sum of algorithmic 2MKN over all Linear GEMM launches of a step) / (sum of their times)."""
+        c = self.cfg
+        M_ = c["batch"] * c["seq"]
+        tot_fl, tot_us, rows = 0.0, 0.0, []
+        for K, N, n, name in self.linear_shapes():
+            for form, fname in enumerate(("fwd", "dgrad", "wgrad")):
+                us, nl = b200.probe_linear_gemm(M_, K, N, form=form, with_bias=(form == 0), rounds=3)
+                fl = 2.0 * M_ * K * N
+                tot_fl += fl * n
+                tot_us += us * n
+                rows.append({"layer": name, "form": fname, "M": M_, "K": K, "N": N, "per_step": n, "us": round(us, 2),
+                             "tflops": round(fl / us * 1e-6, 1), "kernels": nl})
+        ach = tot_fl / tot_us * 1e-6
+        ngemm = sum(r["per_step"] for r in rows)
+        top = max(rows, key=lambda r: r["us"] * r["per_step"])
+        return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel: all nn.Linear fwd/dgrad/wgrad launches of one step "
+                                             f"({ngemm} GEMMs, M={M_})",
                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "us_per_launch": ms * 1e3,
-                "flops_per_launch": fl, "algorithmic_bytes": M_ * K * 2 + N * K * 2 + M_ * N * 4,
-                "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "us_per_launch": tot_us / ngemm,
+                "flops_per_step": tot_fl, "gemm_us_per_step": tot_us,
+                "largest_class": f"{top['layer']} {top['form']} {top['M']}x{top['K']}x{top['N']}: {top['us']} us, {top['tflops']} TFLOP/s",
+                "classes": rows,
+                "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "how": "graph-paced launches over rotating operand sets > L2, CUDA events (nnb_probe_linear_gemm)"}
 
     def cpu(self):
         r = cpu_gpt_run(self.cfg, steps=3, warmup=1, batch=8)
         return r, f"{r['steps']} steps of 8 sequences x T={self.cfg['seq']} (oracle/gpt_numpy.py; cost is linear in batch)"
-
-
-def _probe_gemm(b200, M_, K, N, act):
-    """Median CUDA-event time (ms) of ONE forward GEMM launch on staged operands, L2 flushed before each."""
-    import torch
-    x = torch.randn(M_, K, device="cuda")
-    w = torch.randn(N, K, device="cuda") / K ** 0.5
-    bias = torch.zeros(1, N, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    times = []
-    for it in range(23):
-        flush.zero_()
-        t = b200.time_linear_forward_gemm(x, w, bias, act=act)
-        if it >= 3:
-            times.append(t)
-    return float(np.median(times))
 
 
 def run_ours(args):
@@ -332,30 +346,42 @@ def run_ours(args):
     def train_step(*inputs):
         opt.zero_grad()
         loss = wl.forward_loss(*inputs)
-        loss.backward()
+        loss.backward()  # with overlap on, each ~32 MB gradient chunk is all-reduced as soon as it is final
         if bucket is not None:
-            bucket.all_reduce()  # the one collective: sum of gradients over NVLink (NCCL)
+            bucket.all_reduce()  # the one collective: sum of gradients over NVLink (NCCL); waits for the chunks
         opt.step()
         return loss
 
     # ---- warm-up (eager) then capture the whole step as a CUDA graph ------------------------------
     W = max(args.warmup, 3)
-    for _ in range(W):
+    overlap = bucket is not None and not args.no_overlap
+    for i in range(W):
         train_step(*wl.inputs)
+        if overlap and i == 0:
+            bucket.overlap_backward()  # live set known after one step: hook the chunked, overlapped all-reduce
     torch.cuda.synchronize()
     graphed, graph_err = None, None
     if not args.no_graph:
-        try:
-            graphed = b200.GraphedStep(train_step, wl.inputs, optimizer=opt, warmup=2)
-        except Exception as e:  # report, never hide
-            graph_err = f"{type(e).__name__}: {e}"[:300]
-            graphed = None
+        for attempt in range(2):
             try:
-                torch.cuda.synchronize()
-            except Exception:
-                pass
+                graphed = b200.GraphedStep(train_step, wl.inputs, optimizer=opt, warmup=2)
+                break
+            except Exception as e:  # report, never hide
+                graph_err = f"{type(e).__name__}: {e}"[:300]
+                graphed = None
+                try:
+                    torch.cuda.synchronize()
+                except Exception:
+                    pass
+                if not overlap:
+                    break
+                # retry the capture once with the plain end-of-backward all-reduce
+                overlap = False
+                bucket = GradBucket(params)
+                for p_ in params:
+                    p_._grad_ready = None
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # 2x L2: evicts the working set
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if wl.flush_l2 else None  # 2x L2
 
     def one_step():
         return graphed.replay() if graphed is not None else train_step(*wl.inputs)
@@ -366,7 +392,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(W):
-        flush.zero_()
+        if flush is not None:
+            flush.zero_()
         one_step()
     barrier()
 
@@ -377,7 +404,8 @@ def run_ours(args):
         barrier()
         wall0 = time.perf_counter()
         for i in range(K):
-            flush.zero_()
+            if flush is not None:
+                flush.zero_()
             ev[i][0].record()
             one_step()
             ev[i][1].record()
@@ -388,8 +416,10 @@ def run_ours(args):
         while time.perf_counter() < t_end:
             one_step()
         torch.cuda.synchronize()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    dev_s = sum(step_ms) / 1e3
+    if flush is not None:
+        dev_s = sum(a.elapsed_time(b) for a, b in ev) / 1e3  # the flush kernels sit between the per-step event pairs
+    else:
+        dev_s = ev[0][0].elapsed_time(ev[K - 1][1]) / 1e3    # first start -> last end: K whole steps back to back
     # launches per step: count one eager step (graph replays do not pass through the counter)
     b200.reset_launch_count()
     train_step(*wl.inputs)
@@ -440,7 +470,10 @@ def run_ours(args):
             "warmup": W, "ms_per_step": dev_s / K * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": label, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "flushed (256 MiB write) between timed steps",
+                       "l2": ("flushed (256 MiB write) between timed steps" if flush is not None else
+                              "not flushed: per-step working set (weights + Adam state 0.65 GB, activations > 2 GB) exceeds the 126 MB L2"),
+                       "grad_allreduce": (None if bucket is None else
+                                          ("chunked (32 MB), overlapped with backward" if overlap else "one flat all-reduce after backward")),
                        "step_execution": "cuda-graph replay of the public-API step" if graphed is not None else "eager",
                        "graph_error": graph_err, "precision": b200.get_precision(),
                        "host_wall_ms_per_step": wall / K * 1e3},
@@ -462,10 +495,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mlp", choices=["mlp", "gpt"])
+    ap.add_argument("--workload", default="gpt", choices=["mlp", "gpt"],
+                    help="gpt = BASELINE.json configs[3], the config the 1/2/4/8-GPU samples/s metric is quoted on (default); "
+                         "mlp = configs[1]")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one flat all-reduce after backward instead of overlapped chunks")
     ap.add_argument("--no-graph", action="store_true", help="time the eager public-API step instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

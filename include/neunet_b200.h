@@ -158,6 +158,28 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
                          int64_t cols, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
 
+/* ---- measurement (bench.py roofline) -----------------------------------------------------------------
+ * GPU-paced microseconds of ONE tcgen05 GEMM launch in an nn.Linear form (0 fwd X.W^T [+bias],
+ * 1 dgrad dO.W, 2 wgrad dO^T.X) on staged bf16 operands: `sets` operand/output sets (choose them to
+ * exceed the 126 MB L2 in total) x `rounds`, captured into a CUDA graph and timed by CUDA events on
+ * `stream`. us_per_launch includes the split-K finishing kernel when one is used
+ * (launches_per_gemm = 2). with_bias: bit 0 = add bias, bit 1 = Swish epilogue + Z side output
+ * (form 0 only). Diagnostics only. */
+int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bias, int sets,
+                          int rounds, float* us_per_launch, int* launches_per_gemm,
+                          cudaStream_t stream);
+
+/* ---- Dropout with a device RNG (row N4 of SURVEY.md 8f) ----------------------------------------
+ * neunet/nn/layers/dropout.py:17-46: y = x * mask, mask ~ Bernoulli(1-p) / (1-p); backward is the
+ * same call on the upstream gradient. The mask is not materialised: it is Philox4x32-10 of
+ * (seed, call_id, epoch, element index), so the same (seed, call_id, epoch) regenerates it.
+ * epoch_dev, when non-NULL, is a device-resident uint64 that overrides `epoch` (CUDA-graph replays:
+ * the graph bakes the pointer; nnb_rng_advance increments the value between replays).
+ */
+int nnb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t call_id,
+                uint64_t epoch, const uint64_t* epoch_dev, cudaStream_t stream);
+int nnb_rng_advance(uint64_t* epoch_dev, cudaStream_t stream);
+
 /* ---- fused CrossEntropyLoss (row N3 of SURVEY.md 8f, first half) --------------------------------
  * LogSoftmax(axis=1) + NLLLoss with unit class weights (neunet/nn/losses.py:59-126); native analogue
  * in the reference: cudaCrossEntropyForwardBackward (experimental/losses/cross_entropy_loss/

@@ -173,18 +173,109 @@ __global__ void rmsnorm_bwd_cols_kernel(const float* __restrict__ gY, const floa
     if (pb) pb[(long long)blockIdx.y * cols + c] = sb;
 }
 
-__global__ void colsum2_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
-                                      int nparts, int cols, float* __restrict__ dw,
-                                      float* __restrict__ db) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    float sw = 0.f, sb = 0.f;
-    for (int p = 0; p < nparts; ++p) {
-        sw += pw[(long long)p * cols + c];
-        if (db) sb += pb[(long long)p * cols + c];
+// Fused RMSNorm backward for cols <= 1024, cols % 4 == 0: one pass over gY and X produces dX AND the
+// per-block column partials of dw = sum_rows gY * X/std and db = sum_rows gY (rmsnorm.py:51-59).
+// A warp owns a row at a time (float4 per lane, NJ4 of them), keeps its column partials in registers
+// across its rows, and the 8 warps of the block are combined through shared memory at the end.
+template <int NJ4>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_fused_kernel(
+    const float* __restrict__ gY, const float* __restrict__ X, const float* __restrict__ w,
+    const float* __restrict__ Xstd, float* __restrict__ dX, float* __restrict__ pw,
+    float* __restrict__ pb, long long rows, int cols, int rows_per_block) {
+    __shared__ float red[8][NJ4 * 128 + 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    float4 wv[NJ4], aw[NJ4], ab[NJ4];
+#pragma unroll
+    for (int j = 0; j < NJ4; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        wv[j] = c < cols ? *reinterpret_cast<const float4*>(w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        aw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    dw[c] = sw;
-    if (db) db[c] = sb;
+    for (long long r = r0 + warp; r < r1; r += 8) {
+        float4 x[NJ4], g[NJ4];
+#pragma unroll
+        for (int j = 0; j < NJ4; ++j) {
+            const int c = (lane + 32 * j) * 4;
+            if (c < cols) {
+                x[j] = *reinterpret_cast<const float4*>(X + r * cols + c);
+                g[j] = *reinterpret_cast<const float4*>(gY + r * cols + c);
+            } else {
+                x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                g[j] = x[j];
+            }
+        }
+        const float std = Xstd[r];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ4; ++j) {
+            dot += wv[j].x * g[j].x * x[j].x / std + wv[j].y * g[j].y * x[j].y / std +
+                   wv[j].z * g[j].z * x[j].z / std + wv[j].w * g[j].w * x[j].w / std;
+        }
+        dot = warp_sum(dot);
+        const float cc = dot / (float)cols;
+        const float inv2 = 1.0f / (std * std);
+#pragma unroll
+        for (int j = 0; j < NJ4; ++j) {
+            const int c = (lane + 32 * j) * 4;
+            if (c < cols) {
+                float4 d;
+                d.x = (wv[j].x * g[j].x * std - x[j].x * cc) * inv2;
+                d.y = (wv[j].y * g[j].y * std - x[j].y * cc) * inv2;
+                d.z = (wv[j].z * g[j].z * std - x[j].z * cc) * inv2;
+                d.w = (wv[j].w * g[j].w * std - x[j].w * cc) * inv2;
+                *reinterpret_cast<float4*>(dX + r * cols + c) = d;
+            }
+            aw[j].x += g[j].x * (x[j].x / std); aw[j].y += g[j].y * (x[j].y / std);
+            aw[j].z += g[j].z * (x[j].z / std); aw[j].w += g[j].w * (x[j].w / std);
+            ab[j].x += g[j].x; ab[j].y += g[j].y; ab[j].z += g[j].z; ab[j].w += g[j].w;
+        }
+    }
+    if (pw == nullptr) return;
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? pw : pb;
+        if (dst == nullptr) break;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NJ4; ++j)
+            *reinterpret_cast<float4*>(&red[warp][(lane + 32 * j) * 4]) = pass == 0 ? aw[j] : ab[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < cols; c += 256) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += red[y][c];
+            dst[(long long)blockIdx.x * cols + c] = t;
+        }
+    }
+}
+
+// dw[c] = sum_p pw[p][c] (and db from pb): 32 columns x 32 partial-lanes per block, fixed order
+__global__ void __launch_bounds__(1024) colsum2_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
+                                                              int nparts, int cols, float* __restrict__ dw,
+                                                              float* __restrict__ db) {
+    __shared__ float red[2][32][33];
+    const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float sw = 0.f, sb = 0.f;
+    if (c < cols) {
+#pragma unroll 4
+        for (int p = py; p < nparts; p += 32) {
+            sw += __ldg(pw + (long long)p * cols + c);
+            if (db) sb += __ldg(pb + (long long)p * cols + c);
+        }
+    }
+    red[0][py][cx] = sw;
+    red[1][py][cx] = sb;
+    __syncthreads();
+    if (py == 0 && c < cols) {
+        float tw = 0.f, tb = 0.f;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) { tw += red[0][y][cx]; tb += red[1][y][cx]; }
+        dw[c] = tw;
+        if (db) db[c] = tb;
+    }
 }
 
 int ew_grid(long long n_threads_needed, int threads) {
@@ -276,22 +367,46 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
     (void)X_norm;  // recomputed as X / X_std: cheaper than reading a second [rows, cols] array
     NNB_REQUIRE(gY && X && w && X_std && dX, "nnb_rmsnorm_backward: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_backward: bad shape");
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool fused = cols <= 1024 && (cols % 4) == 0 && al16(gY) && al16(X) && al16(w) && al16(dX);
+    float *pw = nullptr, *pb = nullptr;
+    if (dw) {
+        Bump ws(workspace, workspace_bytes);
+        pw = static_cast<float*>(ws.take((size_t)RMS_MAX_PARTS * cols * 4));
+        pb = db ? static_cast<float*>(ws.take((size_t)RMS_MAX_PARTS * cols * 4)) : nullptr;
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_rmsnorm_backward: workspace too small");
+    }
+    if (fused) {
+        // >= 8 rows per block (one per warp), <= RMS_MAX_PARTS partial rows for the finishing pass
+        long long parts = std::max<long long>(1, std::min<long long>(RMS_MAX_PARTS, ceil_div(rows, 8)));
+        const int rpb = (int)ceil_div(rows, parts);
+        parts = ceil_div(rows, rpb);
+        const int nj4 = (int)ceil_div(cols, 128);
+        if (nj4 <= 1) rmsnorm_bwd_fused_kernel<1><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
+        else if (nj4 <= 2) rmsnorm_bwd_fused_kernel<2><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
+        else if (nj4 <= 4) rmsnorm_bwd_fused_kernel<4><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
+        else rmsnorm_bwd_fused_kernel<8><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
+        if (dw) {
+            colsum2_reduce_kernel<<<(unsigned)ceil_div(cols, 32), 1024, 0, stream>>>(pw, pb, (int)parts, (int)cols, dw, db);
+            count_launch();
+            NNB_CUDA_OK(cudaGetLastError());
+        }
+        return NNB_OK;
+    }
     const long long blocks = ceil_div(rows * 32, 256);
     rmsnorm_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gY, X, w, X_std, dX, rows, (int)cols);
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     if (dw) {
-        Bump ws(workspace, workspace_bytes);
-        float* pw = static_cast<float*>(ws.take((size_t)RMS_MAX_PARTS * cols * 4));
-        float* pb = db ? static_cast<float*>(ws.take((size_t)RMS_MAX_PARTS * cols * 4)) : nullptr;
-        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_rmsnorm_backward: workspace too small");
         const int gx = (int)ceil_div(cols, 128);
         long long parts = std::max<long long>(1, std::min<long long>(RMS_MAX_PARTS, (long long)num_sms() * 4 / gx));
         parts = std::min<long long>(parts, rows);
         const int rpb = (int)ceil_div(rows, parts);
         parts = ceil_div(rows, rpb);
         rmsnorm_bwd_cols_kernel<<<dim3(gx, (unsigned)parts), 128, 0, stream>>>(gY, X, X_std, pw, pb, rows, (int)cols, rpb);
-        colsum2_reduce_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, stream>>>(pw, pb, (int)parts, (int)cols, dw, db);
+        colsum2_reduce_kernel<<<(unsigned)ceil_div(cols, 32), 1024, 0, stream>>>(pw, pb, (int)parts, (int)cols, dw, db);
         count_launch(2);
         NNB_CUDA_OK(cudaGetLastError());
     }

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < a.v.cols) {
         const bool full = c + 3 < a.v.cols;
+#pragma unroll 4
         for (long long r = r0 + ty; r < r1; r += TY) {
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             if (full && a.vec_ok) {
@@ -112,22 +113,24 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
     }
 }
 
-// out[c] = sum_p partial[p][c]: 32 columns x 8 partial-lanes per block, fixed-order tree at the end
-// (deterministic), so up to 1024 partial rows reduce in a few microseconds.
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int nparts,
-                                                            long long cols, float* __restrict__ out) {
-    __shared__ float red[8][33];
+// out[c] = sum_p partial[p][c]: 32 columns x 32 partial-lanes per block, fixed-order tree at the end
+// (deterministic): <= 1024 partial rows are <= 32 independent loads per thread.
+__global__ void __launch_bounds__(1024) colsum_reduce_kernel(const float* __restrict__ partial, int nparts,
+                                                             long long cols, float* __restrict__ out) {
+    __shared__ float red[32][33];
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * 32 + cx;
     float s = 0.f;
-    if (c < cols)
-        for (int p = py; p < nparts; p += 8) s += partial[(long long)p * cols + c];
+    if (c < cols) {
+#pragma unroll 8
+        for (int p = py; p < nparts; p += 32) s += __ldg(partial + (long long)p * cols + c);
+    }
     red[py][cx] = s;
     __syncthreads();
     if (py == 0 && c < cols) {
         float t = 0.f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) t += red[y][cx];
+        for (int y = 0; y < 32; ++y) t += red[y][cx];
         out[c] = t;
     }
 }
@@ -173,7 +176,9 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     const int sms = num_sms();
     int64_t want_y = std::max<int64_t>(1, (int64_t)sms * 16 / std::max<int64_t>(1, gx * batch));
     want_y = std::min<int64_t>(want_y, 1024);
-    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(want_y, 1024 / batch));
+    // with column sums every row chunk adds a partial row that colsum_reduce_kernel must re-read:
+    // ~256 chunks keep all SMs busy while the finishing pass stays a few microseconds
+    if (colsum) want_y = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want_y, 256), 1024 / batch));
     NNB_REQUIRE(!colsum || batch <= 1024, "stage_operand: colsum with batch > 1024");
     int64_t rpb = std::max<int64_t>(ty, ceil_div(src.rows, want_y));
     rpb = round_up(rpb, ty);
@@ -193,7 +198,7 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     NNB_CUDA_OK(cudaGetLastError());
     if (colsum) {
         const int nparts = (int)(gy * batch);
-        colsum_reduce_kernel<<<(unsigned)ceil_div(src.cols, 32), 256, 0, stream>>>(
+        colsum_reduce_kernel<<<(unsigned)ceil_div(src.cols, 32), 1024, 0, stream>>>(
             colsum_scratch, nparts, src.cols, colsum);
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());

@@ -578,8 +578,27 @@ class Tensor:
                     break
             if not advanced:
                 tape.append(node)
+        # leaves with a `_grad_ready` hook (neunet.distributed.GradBucket.overlap_backward): the hook
+        # fires right after the LAST tape node that feeds the leaf has run, i.e. when its gradient is final
+        uses = {}
+        for v in tape:
+            for a in v.args:
+                if isinstance(a, Tensor) and a.args is None and a.requires_grad and getattr(a, "_grad_ready", None) is not None:
+                    ent = uses.get(id(a))
+                    if ent is None:
+                        uses[id(a)] = [a, 1]
+                    else:
+                        ent[1] += 1
         for v in reversed(tape):
             v.grad_fn(*v.args, grad=v.grad)
+            if uses:
+                for a in v.args:
+                    ent = uses.get(id(a)) if isinstance(a, Tensor) else None
+                    if ent is not None:
+                        ent[1] -= 1
+                        if ent[1] == 0:
+                            del uses[id(a)]
+                            a._grad_ready(a)
 
 
 def _assign_last_wins(full, index, grad):

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 import numpy as np
 import torch
@@ -106,6 +106,10 @@ _SIGNATURES = {
     "nnb_rmsnorm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "nnb_rmsnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "nnb_probe_linear_gemm": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, POINTER(c_float),
+                                      POINTER(c_int), c_void_p]),
+    "nnb_dropout": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_uint64, c_uint32, c_uint64, c_void_p, c_void_p]),
+    "nnb_rng_advance": (c_int, [c_void_p, c_void_p]),
     "nnb_cross_entropy_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
     "nnb_cross_entropy_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
@@ -313,31 +317,16 @@ def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, ne
     return dx, dw, db
 
 
-def time_linear_forward_gemm(x, w, bias=None, act=ACT_NONE, beta=1.0):
-    """Milliseconds (CUDA events on the launching stream) of the forward GEMM ALONE: both operands
-    are staged to bf16 first, then one nnb_linear_forward_staged launch is timed. Used by
-    bench.py's roofline probe."""
+def probe_linear_gemm(M, K, N, form=0, with_bias=True, swish=False, rounds=3):
+    """GPU-paced microseconds of one GEMM launch of an nn.Linear form (0 fwd, 1 dgrad, 2 wgrad) in bf16,
+    over operand sets that together exceed the L2 (nnb_probe_linear_gemm). Returns (us, launches)."""
     require_device()
-    L = lib()
-    N, K = w.shape
-    x2 = _f32c(x).reshape(-1, K)
-    M = x2.shape[0]
-    prec = _state["prec"]
-    xs = torch.empty(L.nnb_weight_staged_bytes(M, K, prec), dtype=torch.uint8, device="cuda")
-    wsd = torch.empty(L.nnb_weight_staged_bytes(N, K, prec), dtype=torch.uint8, device="cuda")
-    _check(L.nnb_stage_weight(_ptr(x2), M, K, prec, _ptr(xs), _stream()), "nnb_stage_weight")
-    _check(L.nnb_stage_weight(_ptr(_f32c(w)), N, K, prec, _ptr(wsd), _stream()), "nnb_stage_weight")
-    out = torch.empty((M, N), dtype=torch.float32, device="cuda")
-    z = torch.empty((M, N), dtype=torch.float32, device="cuda") if act else None
-    b = _f32c(bias).reshape(-1) if bias is not None else None
-    ws = _workspace(L.nnb_linear_workspace_bytes(M, K, N, prec, 0))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _check(L.nnb_linear_forward_staged(_ptr(xs), _ptr(wsd), _ptr(b), _ptr(out), _ptr(z), M, K, N, act, float(beta),
-                                       prec, _ptr(ws), ws.numel(), _stream()), "nnb_linear_forward_staged")
-    e1.record()
-    e1.synchronize()
-    return e0.elapsed_time(e1)
+    per_set = 2 * (M * K + N * K + M * N) + 4 * max(M * N, M * K, N * K)  # upper bound, bytes
+    sets = int(min(64, max(2, -(-(300 << 20) // per_set))))
+    us, nl = c_float(0), c_int(0)
+    _check(lib().nnb_probe_linear_gemm(M, K, N, form, int(bool(with_bias)) | (2 if swish else 0), sets, rounds, ctypes.byref(us), ctypes.byref(nl),
+                                       _stream()), "nnb_probe_linear_gemm")
+    return float(us.value), int(nl.value)
 
 
 # ---- Tensor.matmul -----------------------------------------------------------------------------------
@@ -551,6 +540,45 @@ def rmsnorm_backward(grad, x, w, std, need_db=False):
 _REDUCTION = {"none": 0, "mean": 1, "sum": 2}
 
 
+# ---- Dropout (device RNG) ----------------------------------------------------------------------------
+_rng = {"seed": 0x5EED5EED, "epoch": 0, "dev": None, "capture_calls": 0, "graph_used": False}
+
+
+def manual_seed(seed: int) -> None:
+    """Seed of the device dropout RNG (Philox key). Masks are a function of (seed, call, epoch, index)."""
+    _rng["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _rng["epoch"] = 0
+
+
+def _rng_epoch_dev():
+    if _rng["dev"] is None:
+        _rng["dev"] = torch.zeros(1, dtype=torch.int64, device="cuda")
+    return _rng["dev"]
+
+
+def dropout_ticket():
+    """Identity of one dropout mask: (seed, call_id, host epoch, device-epoch tensor or None).
+    Eager calls take a fresh host epoch each; calls recorded into a CUDA graph take a per-capture call
+    index and read the device-resident epoch, which GraphedStep.replay() advances before every replay."""
+    if torch.cuda.is_current_stream_capturing():
+        _rng["capture_calls"] += 1
+        _rng["graph_used"] = True
+        return (_rng["seed"], _rng["capture_calls"], 0, _rng_epoch_dev())
+    _rng["epoch"] += 1
+    return (_rng["seed"], 0, (1 << 62) + _rng["epoch"], None)
+
+
+def dropout_apply(x, p, ticket):
+    """y = x * mask(ticket) / (1 - p): forward on activations, backward on the upstream gradient."""
+    require_device()
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    seed, call_id, epoch, dev = ticket
+    _check(lib().nnb_dropout(_ptr(x), _ptr(y), x.numel(), float(p), seed, call_id, epoch, _ptr(dev), _stream()),
+           "nnb_dropout")
+    return y
+
+
 def cross_entropy_forward(logits, targets, ignore_index=-100, reduction="mean"):
     """Returns (loss, saved) -- loss is a 0-d tensor (mean/sum) or [rows]; saved feeds the backward."""
     require_device()
@@ -611,8 +639,10 @@ class GraphedStep:
         self.optimizer = optimizer
         _state["capture_epoch"] += 1  # invalidates every staged-operand cache made outside this capture
         self.graph = torch.cuda.CUDAGraph()
+        _rng["graph_used"] = False
         with torch.cuda.graph(self.graph):
             self.outputs = fn(*self.inputs)
+        self._uses_rng = _rng["graph_used"]  # dropout inside: bump the device epoch before every replay
         _state["capture_epoch"] += 1
         if optimizer is not None:
             optimizer.t -= 1  # the capture pass itself launched nothing
@@ -629,6 +659,8 @@ class GraphedStep:
         opt = self.optimizer
         if opt is not None and opt.t != self._dev_t and getattr(opt, "_fused", None) is not None:
             opt._fused.set_step(opt.t)  # eager steps were interleaved: re-sync the device counter
+        if self._uses_rng:
+            _check(lib().nnb_rng_advance(_ptr(_rng_epoch_dev()), _stream()), "nnb_rng_advance")
         self.graph.replay()
         if opt is not None:
             opt.t += 1

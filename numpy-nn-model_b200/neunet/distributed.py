@@ -8,6 +8,12 @@ pass: it is folded into the multi-tensor Adam(W) kernel (``optimizer.grad_scale`
 
 Parameters whose ``.grad`` is None (e.g. the GPT example's never-used ``cross_attn``) are skipped
 exactly as ``optim.py:21-22`` skips them, so they cost no bandwidth.
+
+Overlap: ``GradBucket.overlap_backward()`` splits the flat bucket into ~32 MB chunks in REVERSE
+parameter order and registers ``_grad_ready`` hooks (``Tensor.backward`` fires one when the last tape
+node that feeds a leaf has run). A chunk's all-reduce is issued asynchronously the moment its last
+gradient is final, so NCCL runs on its own stream underneath the remaining wgrad/dgrad kernels;
+``all_reduce()`` then only waits and handles whatever was not launched (first step, dead parameters).
 """
 from __future__ import annotations
 
@@ -34,21 +40,26 @@ def rank():
 
 class GradBucket:
     """Flat fp32 bucket holding every parameter's gradient; ``all_reduce()`` packs the current
-    ``param.grad`` arrays into it, runs one NCCL (or gloo, on CPU) all-reduce and points each
+    ``param.grad`` arrays into it, runs the NCCL (or gloo, on CPU) sum all-reduce and points each
     ``param.grad`` at its slice of the reduced bucket."""
 
-    def __init__(self, params):
+    def __init__(self, params, chunk_bytes=32 << 20):
         self.params = list(params)
         self.sizes = [int(np.prod(p.shape)) for p in self.params]
         self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
         self.device = self.params[0].device if self.params else "cpu"
+        self.chunk_bytes = int(chunk_bytes)
         total = int(self.offsets[-1])
         if self.device == "cuda":
             import torch
             self.flat = torch.zeros(total, dtype=torch.float32, device="cuda")
         else:
             self.flat = np.zeros(total, dtype=np.float32)
-        self._live = None
+        self._chunks = None      # [(first_param, last_param_exclusive)] in launch (reverse) order
+        self._chunk_of = {}      # param index -> chunk index
+        self._pending = []       # per chunk: gradients still missing this step
+        self._launched = []      # per chunk: async work handle (or True) once issued this step
+        self._index = {id(p): i for i, p in enumerate(self.params)}
 
     def _slice(self, i):
         return self.flat[int(self.offsets[i]): int(self.offsets[i + 1])]
@@ -67,39 +78,103 @@ class GradBucket:
                 dist.broadcast(t, src)
                 p.data[...] = t.numpy()
 
-    def all_reduce(self):
-        """Sum gradients over all ranks. Live set = parameters with a gradient on THIS rank; it must
-        be the same on every rank (it is, for replicated models)."""
-        live = [i for i, p in enumerate(self.params) if p.grad is not None]
+    # ---- packing + collective over a run of parameters [a, b) --------------------------------------
+    def _pack(self, a, b):
+        live = [i for i in range(a, b) if self.params[i].grad is not None]
         if not live:
-            return
+            return live
         if self.device == "cuda":
             import torch
             srcs = [self.params[i].grad.reshape(-1) for i in live]
             dsts = [self._slice(i) for i in live]
             torch._foreach_copy_(dsts, srcs)
-            # contiguous run of live slices -> one collective over [lo, hi)
-            lo, hi = int(self.offsets[live[0]]), int(self.offsets[live[-1] + 1])
-            if len(live) != live[-1] - live[0] + 1:  # holes (grad None): zero them so the sum is unaffected
-                for i in range(live[0], live[-1] + 1):
-                    if self.params[i].grad is None:
-                        self._slice(i).zero_()
-            if world_size() > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM)
-            for i in live:
-                self.params[i].grad = self._slice(i).reshape(tuple(self.params[i].shape))
         else:
             for i in live:
                 self._slice(i)[...] = np.asarray(self.params[i].grad, dtype=np.float32).reshape(-1)
-            lo, hi = int(self.offsets[live[0]]), int(self.offsets[live[-1] + 1])
-            for i in range(live[0], live[-1] + 1):
-                if self.params[i].grad is None:
+        for i in range(live[0], live[-1] + 1):  # holes (grad None) inside the run: zero so the sum is unaffected
+            if self.params[i].grad is None:
+                if self.device == "cuda":
+                    self._slice(i).zero_()
+                else:
                     self._slice(i)[...] = 0
-            if world_size() > 1:
-                import torch
-                import torch.distributed as dist
-                t = torch.from_numpy(self.flat[lo:hi])
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            for i in live:
-                self.params[i].grad = self._slice(i).reshape(tuple(self.params[i].shape))
+        return live
+
+    def _reduce(self, live, async_op=False):
+        """One sum all-reduce over the contiguous run covering `live`; returns the work handle."""
+        if not live or world_size() == 1:
+            return None
+        import torch.distributed as dist
+        lo, hi = int(self.offsets[live[0]]), int(self.offsets[live[-1] + 1])
+        if self.device == "cuda":
+            return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=async_op)
+        import torch
+        return dist.all_reduce(torch.from_numpy(self.flat[lo:hi]), op=dist.ReduceOp.SUM, async_op=async_op)
+
+    def _adopt(self, live):
+        for i in live:
+            self.params[i].grad = self._slice(i).reshape(tuple(self.params[i].shape))
+
+    # ---- overlap with backward --------------------------------------------------------------------
+    def overlap_backward(self, live_only=True):
+        """Register ready-hooks so chunks are reduced while backward is still running. Call after one
+        ordinary step: with `live_only` the chunks are built from the parameters that received a
+        gradient in that step (dead parameters would otherwise keep a chunk from ever completing)."""
+        idx = [i for i, p in enumerate(self.params) if (p.grad is not None or not live_only)]
+        self._chunks, self._chunk_of = [], {}
+        run, run_bytes = [], 0
+        for i in reversed(idx):  # backward produces gradients roughly in reverse parameter order
+            run.append(i)
+            run_bytes += self.sizes[i] * 4
+            if run_bytes >= self.chunk_bytes:
+                self._chunks.append(sorted(run))
+                run, run_bytes = [], 0
+        if run:
+            self._chunks.append(sorted(run))
+        for c, members in enumerate(self._chunks):
+            for i in members:
+                self._chunk_of[i] = c
+        for i, p in enumerate(self.params):
+            p._grad_ready = self._on_ready if i in self._chunk_of else None
+        self._reset_step()
+
+    def _reset_step(self):
+        if self._chunks is not None:
+            self._pending = [len(m) for m in self._chunks]
+            self._launched = [None] * len(self._chunks)
+
+    def _on_ready(self, param):
+        i = self._index.get(id(param))
+        c = self._chunk_of.get(i)
+        if c is None or self._launched[c] is not None:
+            return
+        self._pending[c] -= 1
+        if self._pending[c] == 0:
+            members = self._chunks[c]
+            live = self._pack(members[0], members[-1] + 1)
+            self._launched[c] = (live, self._reduce(live, async_op=True))
+
+    def all_reduce(self):
+        """Sum gradients over all ranks. Live set = parameters with a gradient on THIS rank; it must
+        be the same on every rank (it is, for replicated models)."""
+        if self._chunks is None:
+            live = self._pack(0, len(self.params))
+            self._reduce(live)
+            self._adopt(live)
+            return
+        done = set()
+        for c, st in enumerate(self._launched):
+            if st is None:  # chunk never completed during backward: do it now, in chunk order on every rank
+                members = self._chunks[c]
+                live = self._pack(members[0], members[-1] + 1)
+                st = (live, self._reduce(live, async_op=True))
+            live, work = st
+            if work is not None:
+                work.wait()
+            self._adopt(live)
+            done.update(live)
+        rest = [i for i, p in enumerate(self.params) if p.grad is not None and i not in done and i not in self._chunk_of]
+        if rest:  # parameters that were dead when the chunks were built but have a gradient now
+            live = self._pack(rest[0], rest[-1] + 1)
+            self._reduce(live)
+            self._adopt(live)
+        self._reset_step()

@@ -41,7 +41,20 @@ class _StaticTensor(Tensor):
 
 
 def _dropout_grad(X: Tensor, mask, grad):
+    if isinstance(mask, _DeviceMask):
+        from ... import b200
+        X.apply_grad(b200.dropout_apply(grad, mask.p, mask.ticket))
+        return
     X.apply_grad(grad * mask)
+
+
+class _DeviceMask:
+    """Stands in for the saved mask array of dropout.py:31 on "cuda": the mask is regenerated from
+    its Philox ticket in backward (neunet/b200: dropout_ticket), never stored."""
+    __slots__ = ("p", "ticket")
+
+    def __init__(self, p, ticket):
+        self.p, self.ticket = p, ticket
 
 
 class Dropout(Module):
@@ -53,6 +66,11 @@ class Dropout(Module):
     def forward(self, X: Tensor) -> Tensor:
         if not isinstance(X, Tensor):
             raise TypeError("Input must be a tensor")
+        if self.training and X.device == "cuda" and 0 <= self.p < 1:
+            from ... import b200
+            mask = _DeviceMask(self.p, b200.dropout_ticket())
+            return _StaticTensor(b200.dropout_apply(X.data, self.p, mask.ticket), (X, mask), "dropout", X.device,
+                                 _dropout_grad)
         if self.training:
             mask = X.xp.random.binomial(1, 1 - self.p, size=tuple(X.data.shape))
             mask = (mask.astype(np.float32) if isinstance(mask, np.ndarray) else mask) * self.scale

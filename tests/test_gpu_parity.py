@@ -456,3 +456,50 @@ def test_graphed_step_tracks_eager_training():
     graph_losses.append(g(xs[5], ys[5]).item())
     np.testing.assert_allclose(graph_losses, eager_losses[2:], rtol=1e-4)
     assert relerr(l1.weight.data, eager_w) < 1e-4
+
+
+# ---- Dropout (device RNG; neunet/nn/layers/dropout.py:17-46) ---------------------------------------
+def test_dropout_device_mask_statistics_and_backward_consistency():
+    """The reference draws mask ~ Bernoulli(1-p)/(1-p) from xp.random (a different generator on every
+    back-end), so parity is on the distribution and on the contract: y = x*mask, dx = grad*mask with
+    the SAME mask, kept elements scaled by exactly 1/(1-p), eval mode is the identity."""
+    b200.manual_seed(123)
+    p = 0.1
+    x = np.random.RandomState(0).randn(4096, 512).astype(np.float32) + 3.0  # no zeros in x
+    layer = nn.Dropout(p)
+    xt = dev(x, True)
+    y = layer(xt)
+    g = np.random.RandomState(1).randn(*x.shape).astype(np.float32) + 5.0
+    y.backward(neunet.tensor(g, device="cuda").data)
+    yh, dxh = host(y.data), host(xt.grad)
+    keep = yh != 0
+    assert abs(keep.mean() - (1 - p)) < 3e-3                       # 2M draws: sigma ~ 2e-4
+    np.testing.assert_array_equal(keep, dxh != 0)                  # same mask both ways
+    scale = np.float32(1.0 / (1.0 - p))
+    np.testing.assert_array_equal(yh[keep], (x * scale)[keep])     # bit-exact scaling of kept elements
+    np.testing.assert_array_equal(dxh[keep], (g * scale)[keep])
+    # rows and columns are not correlated (a counter bug would show as stripes)
+    assert abs(keep.mean(axis=0) - (1 - p)).max() < 0.03 and abs(keep.mean(axis=1) - (1 - p)).max() < 0.08
+    # a second call draws a different mask; re-seeding reproduces the first
+    y2 = host(layer(xt).data)
+    assert ((y2 != 0) != keep).mean() > 0.1
+    b200.manual_seed(123)
+    np.testing.assert_array_equal(host(layer(dev(x)).data), yh)
+    layer.eval()
+    np.testing.assert_array_equal(host(layer(dev(x)).data), x)
+
+
+def test_dropout_ragged_size_and_graph_replays_draw_fresh_masks():
+    x = np.ones(1003, dtype=np.float32)   # not a multiple of 4: scalar tail
+    layer = nn.Dropout(0.5)
+    xt = dev(x)
+    y = host(layer(xt).data)
+    assert set(np.unique(y)) <= {0.0, 2.0} and 0.4 < (y != 0).mean() < 0.6
+
+    def step(t):
+        return layer(t)
+    g = b200.GraphedStep(step, [xt], warmup=1)
+    a = host(g.replay().data).copy()
+    b = host(g.replay().data).copy()
+    assert 0.3 < (a != b).mean() < 0.7      # independent masks per replay
+    assert 0.4 < (a != 0).mean() < 0.6
