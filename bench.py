@@ -460,7 +460,11 @@ def run_ours(args):
     h2d = sum(h.numel() * h.element_size() for h in wl.host[0])
     d2h = 4
 
-    roof = wl.roofline(pk, b200)
+    try:
+        roof = wl.roofline(pk, b200)
+    except Exception as e:  # a failed probe must not lose the step measurements above
+        roof = {"bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                "error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         cpu, cpu_sample = wl.cpu()
@@ -485,10 +489,18 @@ def run_ours(args):
                              "sample": cpu_sample + f", NumPy/OpenBLAS, {cores} cores visible"},
             "final_loss": last_loss,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Tear-down: no collective after the timing all-reduces. Destroying the NCCL communicator while CUDA
+        # graphs that captured its kernels are alive can block forever (seen on the 2-GPU box: both ranks hung
+        # in destroy_process_group after printing), so drop the graph, drain the device and leave without it.
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -101,17 +101,24 @@ int nnb_stage_weight(const float* W, int64_t rows, int64_t cols, int prec, void*
  *   forward : C  = alpha * A . B
  *   backward: dA = alpha * G . B^T   (autograd.py:209)     dB = alpha * A^T . G   (autograd.py:211)
  * dA or dB may be NULL. Un-broadcasting a gradient stays in Tensor._reverse_broadcast.
+ * A_staged_out / B_staged_out (forward): NULL, or 256-byte aligned buffers of
+ * nnb_matmul_staged_bytes(b0, b1, M, K, prec) / (b0, b1, K, N, prec) bytes that receive the bf16 planes
+ * of the operands; handed back as A_staged / B_staged to nnb_matmul_backward (same strides, same
+ * prec) they save re-converting A and B there.
  */
+size_t nnb_matmul_staged_bytes(int64_t b0, int64_t b1, int64_t rows, int64_t cols, int prec);
 size_t nnb_matmul_workspace_bytes(int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N,
                                   int prec, int backward);
 int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* B,
                        const int64_t b_strides[4], float* C, int64_t b0, int64_t b1, int64_t M,
-                       int64_t K, int64_t N, float alpha, int prec, void* workspace,
-                       size_t workspace_bytes, cudaStream_t stream);
+                       int64_t K, int64_t N, float alpha, int prec, void* A_staged_out,
+                       void* B_staged_out, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
 int nnb_matmul_backward(const float* A, const int64_t a_strides[4], const float* B,
                         const int64_t b_strides[4], const float* G, float* dA, float* dB,
                         int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N, float alpha,
-                        int prec, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                        int prec, const void* A_staged, const void* B_staged, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- nn.Conv2d ------------------------------------------------------------------------------
  * NCHW cross-correlation exactly as neunet/nn/layers/conv2d.py:297-355 (forward) and 16-117
@@ -162,7 +169,7 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
  * GPU-paced microseconds of ONE tcgen05 GEMM launch in an nn.Linear form (0 fwd X.W^T [+bias],
  * 1 dgrad dO.W, 2 wgrad dO^T.X) on staged bf16 operands: `sets` operand/output sets (choose them to
  * exceed the 126 MB L2 in total) x `rounds`, captured into a CUDA graph and timed by CUDA events on
- * `stream`. us_per_launch includes the split-K finishing kernel when one is used
+ * a private stream created for the measurement (ordered after the work already queued on `stream`). us_per_launch includes the split-K finishing kernel when one is used
  * (launches_per_gemm = 2). with_bias: bit 0 = add bias, bit 1 = Swish epilogue + Z side output
  * (form 0 only). Diagnostics only. */
 int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bias, int sets,
@@ -222,6 +229,13 @@ int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double
  * kept in device memory, so replaying a captured step keeps the bias corrections moving;
  * nnb_adamw_set_step() seeds that counter (number of steps already taken). */
 int nnb_adamw_set_step(nnb_adamw* opt, int64_t step, cudaStream_t stream);
+/* Fused weight staging: for every tensor i with staged[i] != NULL the step kernel also writes the bf16
+ * planes of the UPDATED weight, viewed as [size_i / cols[i], cols[i]], into staged[i] (a buffer of
+ * nnb_weight_staged_bytes(rows, cols, prec) bytes, the layout nnb_stage_weight() produces), so the next
+ * nnb_linear_forward / backward can take it as W_staged without a conversion pass. staged = NULL turns
+ * the feature off. Not callable during stream capture (it uploads tables synchronously). */
+int nnb_adamw_set_staging(nnb_adamw* opt, void* const* staged, const int64_t* cols, int prec,
+                          cudaStream_t stream);
 int nnb_adamw_destroy(nnb_adamw* opt);
 
 #ifdef __cplusplus

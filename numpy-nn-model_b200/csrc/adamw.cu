@@ -23,6 +23,10 @@ struct nnb_adamw {
     int* d_blk_chunk = nullptr;
     std::vector<const float*> h_g;  // pageable on purpose: the driver stages such async copies at call
                                     // time, so the next eager step may overwrite it immediately
+    void** d_stage = nullptr;       // per tensor: bf16 staging destination (hi plane) or null
+    long long* d_stage_cols = nullptr;  // per tensor: columns of the 2-D weight view
+    long long* d_stage_lo = nullptr;    // per tensor: element offset of the lo plane (0 = BF16 mode)
+    bool staging = false;
     long long* d_t = nullptr;     // device-resident step counter (CUDA-graph replays advance it)
     std::vector<const float**> snapshots;  // pinned pointer tables owned by captured graphs
 };
@@ -53,12 +57,40 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
     p -= s.lr * m_hat / (sqrtf(v_hat) + s.eps);         // optim.py:33 / 69
 }
 
+// bf16 (hi [+ lo]) copy of an updated weight element range into the staged plane the next forward GEMM
+// reads through TMA (common.cuh: Staged, ld = round_up(cols, 8)), so weights are never re-converted.
+__device__ __forceinline__ void emit_staged(__nv_bfloat16* hi, long long lo_off, long long cols, long long i,
+                                            const float* x, int n) {
+    const long long ld = (cols + 7) & ~7ll;
+    const long long row = i / cols, col = i - row * cols;
+    if (n == 4 && (cols & 3) == 0) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2bfloat16_rn(x[j]);
+            l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+        }
+        const long long o = row * ld + col;
+        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+        if (lo_off) *reinterpret_cast<uint2*>(hi + lo_off + o) = *reinterpret_cast<const uint2*>(l);
+        return;
+    }
+    long long r = row, c = col;
+    for (int j = 0; j < n; ++j) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x[j]);
+        hi[r * ld + c] = h;
+        if (lo_off) hi[lo_off + r * ld + c] = __float2bfloat16_rn(x[j] - __bfloat162float(h));
+        if (++c == cols) { c = 0; ++r; }
+    }
+}
+
 __global__ void __launch_bounds__(ADAM_THREADS)
 adamw_multi_kernel(float* const* __restrict__ P, const float* const* __restrict__ G,
                    float* const* __restrict__ Mm, float* const* __restrict__ V,
                    const long long* __restrict__ sizes, const int* __restrict__ blk_tensor,
                    const int* __restrict__ blk_chunk, AdamScalars s,
-                   const long long* __restrict__ d_t) {
+                   const long long* __restrict__ d_t, void* const* __restrict__ stage,
+                   const long long* __restrict__ stage_cols, const long long* __restrict__ stage_lo) {
     if (d_t != nullptr) {
         // graph mode: the step count lives on the device, so a replayed graph keeps advancing the
         // bias corrections 1 - beta^t (formed in double, rounded once, like the host path)
@@ -79,6 +111,8 @@ adamw_multi_kernel(float* const* __restrict__ P, const float* const* __restrict_
     float* m = Mm[t];
     float* v = V[t];
     const long long n = sizes[t];
+    __nv_bfloat16* st_hi = stage ? static_cast<__nv_bfloat16*>(stage[t]) : nullptr;
+    const long long st_cols = st_hi ? stage_cols[t] : 1, st_lo = st_hi ? stage_lo[t] : 0;
     const long long base = (long long)blk_chunk[blockIdx.x] * ADAM_CHUNK;
     const long long end = min(base + ADAM_CHUNK, n);
     const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
@@ -99,13 +133,22 @@ adamw_multi_kernel(float* const* __restrict__ P, const float* const* __restrict_
                 *reinterpret_cast<float4*>(p + i) = pp;
                 *reinterpret_cast<float4*>(m + i) = mm;
                 *reinterpret_cast<float4*>(v + i) = vv;
+                if (st_hi) {
+                    const float x[4] = {pp.x, pp.y, pp.z, pp.w};
+                    emit_staged(st_hi, st_lo, st_cols, i, x, 4);
+                }
             } else {
-                for (long long j = i; j < end; ++j) adam_update(p[j], g[j], m[j], v[j], s);
+                for (long long j = i; j < end; ++j) {
+                    adam_update(p[j], g[j], m[j], v[j], s);
+                    if (st_hi) emit_staged(st_hi, st_lo, st_cols, j, p + j, 1);
+                }
             }
         }
     } else {
-        for (long long j = base + threadIdx.x; j < end; j += ADAM_THREADS)
+        for (long long j = base + threadIdx.x; j < end; j += ADAM_THREADS) {
             adam_update(p[j], g[j], m[j], v[j], s);
+            if (st_hi) emit_staged(st_hi, st_lo, st_cols, j, p + j, 1);
+        }
     }
 }
 
@@ -142,6 +185,10 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     NNB_CUDA_OK(cudaMalloc(&o->d_m, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_v, n * sizeof(float*)));
     NNB_CUDA_OK(cudaMalloc(&o->d_sizes, n * sizeof(long long)));
+    NNB_CUDA_OK(cudaMalloc(&o->d_stage, n * sizeof(void*)));
+    NNB_CUDA_OK(cudaMalloc(&o->d_stage_cols, n * sizeof(long long)));
+    NNB_CUDA_OK(cudaMalloc(&o->d_stage_lo, n * sizeof(long long)));
+    NNB_CUDA_OK(cudaMemsetAsync(o->d_stage, 0, n * sizeof(void*), stream));
     NNB_CUDA_OK(cudaMalloc(&o->d_t, sizeof(long long)));
     NNB_CUDA_OK(cudaMemsetAsync(o->d_t, 0, sizeof(long long), stream));
     NNB_CUDA_OK(cudaMalloc(&o->d_blk_tensor, bt.size() * sizeof(int)));
@@ -214,9 +261,45 @@ int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double
     adamw_multi_kernel<<<opt->nblocks, ADAM_THREADS, 0, stream>>>(opt->d_p, opt->d_g, opt->d_m, opt->d_v,
                                                                   opt->d_sizes, opt->d_blk_tensor,
                                                                   opt->d_blk_chunk, s,
-                                                                  step == 0 ? opt->d_t : nullptr);
+                                                                  step == 0 ? opt->d_t : nullptr,
+                                                                  opt->staging ? opt->d_stage : nullptr,
+                                                                  opt->d_stage_cols, opt->d_stage_lo);
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_adamw_set_staging(nnb_adamw* opt, void* const* staged, const int64_t* cols, int prec,
+                          cudaStream_t stream) {
+    NNB_REQUIRE(opt, "nnb_adamw_set_staging: null handle");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_adamw_set_staging: bad prec");
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NNB_CUDA_OK(cudaStreamIsCapturing(stream, &cap));
+    NNB_REQUIRE(cap == cudaStreamCaptureStatusNone, "nnb_adamw_set_staging: not allowed during stream capture");
+    if (staged == nullptr) {
+        opt->staging = false;
+        return NNB_OK;
+    }
+    NNB_REQUIRE(cols, "nnb_adamw_set_staging: null cols");
+    std::vector<long long> sizes(opt->n), hc(opt->n), hl(opt->n);
+    NNB_CUDA_OK(cudaMemcpyAsync(sizes.data(), opt->d_sizes, opt->n * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    NNB_CUDA_OK(cudaStreamSynchronize(stream));
+    bool any = false;
+    for (int i = 0; i < opt->n; ++i) {
+        hc[i] = 1;
+        hl[i] = 0;
+        if (staged[i] == nullptr) continue;
+        NNB_REQUIRE(cols[i] > 0 && sizes[i] % cols[i] == 0, "nnb_adamw_set_staging: tensor %d: cols must divide its size", i);
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(staged[i]) & 255) == 0, "nnb_adamw_set_staging: tensor %d: buffer not 256-byte aligned", i);
+        hc[i] = cols[i];
+        if (prec == NNB_PREC_BF16X3) hl[i] = (long long)(staged_plane_bytes(1, sizes[i] / cols[i], cols[i]) / 2);
+        any = true;
+    }
+    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_stage, staged, opt->n * sizeof(void*), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_stage_cols, hc.data(), opt->n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaMemcpyAsync(opt->d_stage_lo, hl.data(), opt->n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    NNB_CUDA_OK(cudaStreamSynchronize(stream));
+    opt->staging = any;
     return NNB_OK;
 }
 
@@ -232,6 +315,7 @@ int nnb_adamw_destroy(nnb_adamw* opt) {
     if (!opt) return NNB_OK;
     cudaFree(opt->d_p); cudaFree((void*)opt->d_g); cudaFree(opt->d_m); cudaFree(opt->d_v);
     cudaFree(opt->d_sizes); cudaFree(opt->d_blk_tensor); cudaFree(opt->d_blk_chunk);
+    cudaFree(opt->d_stage); cudaFree(opt->d_stage_cols); cudaFree(opt->d_stage_lo);
     for (auto* sn : opt->snapshots) cudaFreeHost((void*)sn);
     cudaFree(opt->d_t);
     delete opt;

@@ -30,10 +30,26 @@ ce_rows_kernel(const float* __restrict__ logits, const int* __restrict__ targets
     if (row >= rows) return;
     const float* x = logits + row * C;
     float m = -FLT_MAX, s = 0.f;
-    for (int i = lane; i < C; i += stride) {
-        const float v = x[i];
-        if (v > m) { s *= expf(m - v); m = v; }
-        s += expf(v - m);
+    if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && C >= 4) {
+        // 16-byte loads; the running max moves rarely, so one rescale per float4 instead of per element
+        const int c4 = C >> 2;
+        for (int i = lane; i < c4; i += stride) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+            const float vm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            if (vm > m) { s *= expf(m - vm); m = vm; }
+            s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+        }
+        for (int i = (c4 << 2) + lane; i < C; i += stride) {
+            const float v = x[i];
+            if (v > m) { s *= expf(m - v); m = v; }
+            s += expf(v - m);
+        }
+    } else {
+        for (int i = lane; i < C; i += stride) {
+            const float v = x[i];
+            if (v > m) { s *= expf(m - v); m = v; }
+            s += expf(v - m);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -87,24 +103,43 @@ ce_finish_kernel(const float* __restrict__ row_loss, const int* __restrict__ tar
     }
 }
 
+// grid = (column chunks, rows): the per-row scalars (target, lse, upstream) are read once per block and
+// the row is streamed with 16-byte accesses (4 B read + 4 B written per logit)
 __global__ void __launch_bounds__(256)
 ce_backward_kernel(const float* __restrict__ logits, const int* __restrict__ targets,
                    const float* __restrict__ lse, const float* __restrict__ inv_denom,
                    const float* __restrict__ upstream, int upstream_per_row, long long rows, int C,
-                   int ignore_index, float* __restrict__ dlogits) {
-    const long long total = rows * C;
-    const float inv = inv_denom ? *inv_denom : 1.0f;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / C;
-        const int c = (int)(idx - r * C);
-        const int t = targets[r];
-        float g = 0.f;
-        if (t != ignore_index) {
-            const float up = upstream_per_row ? upstream[r] : upstream[0];
-            g = (expf(logits[idx] - lse[r]) - (c == t ? 1.f : 0.f)) * inv * up;
+                   int ignore_index, float* __restrict__ dlogits, int vec) {
+    const long long r = blockIdx.y;
+    const int t = targets[r];
+    const float* x = logits + r * C;
+    float* d = dlogits + r * C;
+    const int c0 = blockIdx.x * (256 * 4 * 4);
+    const int c1 = min(c0 + 256 * 4 * 4, C);
+    if (t == ignore_index) {
+        for (int c = c0 + threadIdx.x; c < c1; c += 256) d[c] = 0.f;
+        return;
+    }
+    const float l = lse[r];
+    const float sc = (inv_denom ? *inv_denom : 1.0f) * (upstream_per_row ? upstream[r] : upstream[0]);
+    if (vec) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int c = c0 + (it * 256 + threadIdx.x) * 4;
+            if (c + 3 < c1) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
+                float4 g;
+                g.x = (expf(v.x - l) - (c == t ? 1.f : 0.f)) * sc;
+                g.y = (expf(v.y - l) - (c + 1 == t ? 1.f : 0.f)) * sc;
+                g.z = (expf(v.z - l) - (c + 2 == t ? 1.f : 0.f)) * sc;
+                g.w = (expf(v.w - l) - (c + 3 == t ? 1.f : 0.f)) * sc;
+                *reinterpret_cast<float4*>(d + c) = g;
+            } else {
+                for (int j = c; j < c1; ++j) d[j] = (expf(x[j] - l) - (j == t ? 1.f : 0.f)) * sc;
+            }
         }
-        dlogits[idx] = g;
+    } else {
+        for (int c = c0 + threadIdx.x; c < c1; c += 256) d[c] = (expf(x[c] - l) - (c == t ? 1.f : 0.f)) * sc;
     }
 }
 
@@ -146,11 +181,16 @@ int nnb_cross_entropy_backward(const float* logits, const int32_t* targets, cons
                                cudaStream_t stream) {
     NNB_REQUIRE(logits && targets && lse && upstream && dlogits, "nnb_cross_entropy_backward: null pointer");
     NNB_REQUIRE(rows > 0 && C > 0 && C < (1ll << 31), "nnb_cross_entropy_backward: bad shape");
-    const long long total = rows * C;
-    const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 16));
-    ce_backward_kernel<<<blocks, 256, 0, stream>>>(logits, targets, lse, inv_denom, upstream, upstream_per_row, rows,
-                                                   (int)C, (int)ignore_index, dlogits);
-    count_launch();
+    const int vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0;
+    // blockIdx.y is limited to 65535: fold larger row counts through several launches
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, rows - r0);
+        dim3 grid((unsigned)ceil_div(C, 256 * 16), (unsigned)nr);
+        ce_backward_kernel<<<grid, 256, 0, stream>>>(logits + r0 * C, targets + r0, lse + r0, inv_denom,
+                                                     upstream_per_row ? upstream + r0 : upstream, upstream_per_row, nr,
+                                                     (int)C, (int)ignore_index, dlogits + r0 * C, vec);
+        count_launch();
+    }
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
 }

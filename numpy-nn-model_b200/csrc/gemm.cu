@@ -303,6 +303,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
             const int n0 = n_blk * BN;
             const int acc = local_iter & 1;
             const uint32_t acc_phase = (local_iter >> 1) & 1;
+            // per-column bias: lane l holds bias[col0 + l] of the NEXT chunk (one coalesced 128 B load,
+            // issued a whole chunk ahead -- the first one before the accumulator wait) and the 32 values
+            // are broadcast with shuffles, so no global-load latency sits between tcgen05.ld and the store
+            const bool col_bias = p.bias != nullptr && !p.bias_per_row;
+            float bias_next = 0.f;
+            if (col_bias && n0 + lane < p.N) bias_next = __ldg(p.bias + n0 + lane);
             ptx::mbar_wait(&tmem_full[acc], acc_phase, 4);
             ptx::tc_fence_after();
             const int row_base = m0 + q * 32;
@@ -311,6 +317,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
                 const int col0 = n0 + c * 32;
+                const float bias_cur = bias_next;
+                if (col_bias && c + 1 < NCHUNK && col0 + 32 + lane < p.N) bias_next = __ldg(p.bias + col0 + 32 + lane);
+                else bias_next = 0.f;
                 if (col0 >= p.N || !rows_live) {
                     if (c == NCHUNK - 1) {
                         ptx::tc_fence_before();
@@ -341,17 +350,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                             const float rb = row < p.M ? p.bias[row] : 0.f;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) x[j] += rb;
-                        } else if (p.bias_vec && col0 + 32 <= p.N) {
-                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 t = __ldg(b4 + j);
-                                x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
-                            }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
+                            for (int j = 0; j < 32; ++j) x[j] += __shfl_sync(0xffffffffu, bias_cur, j);  // 0 past N
                         }
                     }
                     const bool has_z = p.Z != nullptr;
@@ -410,8 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                         coff = col;
                     }
                     coff += (long long)ob * p.batch_stride_d;
-                    float cb = 0.f;
-                    if (p.bias != nullptr && !p.bias_per_row && col_ok) cb = p.bias[col];
+                    const float cb = bias_cur;  // bias[col0 + lane] (0 past N or without a column bias)
 #pragma unroll 4
                     for (int rr = 0; rr < 32; ++rr) {
                         const int row = row_base + rr;

@@ -20,8 +20,12 @@ struct Op {
 // Returns the operand with mn_major set accordingly.
 //   reduction_is_cols = true : logical matrix is [out_dim, reduction]
 //   reduction_is_cols = false: logical matrix is [reduction, out_dim]
+// `keep`: optional caller-owned buffer of nnb_matmul_staged_bytes(); the planes are written there
+// instead of the workspace (forward, so backward can reuse them) or, with `have` set, are taken from
+// it as already converted (backward) and nothing is launched.
 int stage_view(Bump& ws, const float* ptr, const int64_t st[4], int64_t b0, int64_t b1, int64_t R,
-               int64_t C, bool reduction_is_cols, int prec, cudaStream_t stream, GemmOperand* out) {
+               int64_t C, bool reduction_is_cols, int prec, cudaStream_t stream, GemmOperand* out,
+               void* keep = nullptr, bool have = false) {
     View4 v;
     v.ptr = ptr;
     const bool bcast = (st[0] == 0 || b0 == 1) && (st[1] == 0 || b1 == 1);
@@ -37,13 +41,25 @@ int stage_view(Bump& ws, const float* ptr, const int64_t st[4], int64_t b0, int6
         transposed = true;
     }
     const int64_t batch = v.b0 * v.b1;
-    auto* hi = static_cast<__nv_bfloat16*>(ws.take(staged_plane_bytes(batch, v.rows, v.cols)));
-    __nv_bfloat16* lo = nullptr;
-    if (prec == NNB_PREC_BF16X3)
-        lo = static_cast<__nv_bfloat16*>(ws.take(staged_plane_bytes(batch, v.rows, v.cols)));
-    if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "matmul: workspace too small (need >= %zu bytes)", ws.off);
-    int rc = stage_operand(v, false, prec, hi, lo, STAGE_COPY, nullptr, 0.f, nullptr, nullptr, stream, &out->st);
-    if (rc) return rc;
+    const size_t pb = staged_plane_bytes(batch, v.rows, v.cols);
+    __nv_bfloat16 *hi, *lo = nullptr;
+    if (keep != nullptr) {
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(keep) & 255) == 0, "matmul: staged buffer must be 256-byte aligned");
+        hi = static_cast<__nv_bfloat16*>(keep);
+        if (prec == NNB_PREC_BF16X3) lo = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(keep) + pb);
+    } else {
+        hi = static_cast<__nv_bfloat16*>(ws.take(pb));
+        if (prec == NNB_PREC_BF16X3) lo = static_cast<__nv_bfloat16*>(ws.take(pb));
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "matmul: workspace too small (need >= %zu bytes)", ws.off);
+    }
+    if (keep != nullptr && have) {
+        Staged& s = out->st;
+        s.hi = hi; s.lo = lo; s.rows = v.rows; s.cols = v.cols; s.ld = staged_ld(v.cols);
+        s.batch = batch; s.batch_stride = v.rows * s.ld;
+    } else {
+        int rc = stage_operand(v, false, prec, hi, lo, STAGE_COPY, nullptr, 0.f, nullptr, nullptr, stream, &out->st);
+        if (rc) return rc;
+    }
     // staged rows = R (cols = C) unless transposed. K-major <=> staged cols are the reduction.
     const bool staged_cols_are_reduction = transposed ? !reduction_is_cols : reduction_is_cols;
     out->mn_major = !staged_cols_are_reduction;
@@ -79,19 +95,26 @@ size_t nnb_matmul_workspace_bytes(int64_t b0, int64_t b1, int64_t M, int64_t K, 
     return bytes;
 }
 
+size_t nnb_matmul_staged_bytes(int64_t b0, int64_t b1, int64_t rows, int64_t cols, int prec) {
+    if (b0 <= 0 || b1 <= 0 || rows <= 0 || cols <= 0) return 0;
+    const int64_t b = b0 * b1;
+    return (size_t)planes(prec) * std::max(staged_plane_bytes(b, rows, cols), staged_plane_bytes(b, cols, rows));
+}
+
 int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* B,
                        const int64_t b_strides[4], float* C, int64_t b0, int64_t b1, int64_t M,
-                       int64_t K, int64_t N, float alpha, int prec, void* workspace,
-                       size_t workspace_bytes, cudaStream_t stream) {
+                       int64_t K, int64_t N, float alpha, int prec, void* A_staged_out,
+                       void* B_staged_out, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
     NNB_REQUIRE(A && B && C && a_strides && b_strides, "nnb_matmul_forward: null pointer");
     NNB_REQUIRE(b0 > 0 && b1 > 0 && M > 0 && K > 0 && N > 0, "nnb_matmul_forward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_matmul_forward: bad prec");
     Bump ws(workspace, workspace_bytes);
     GemmProblem g;
     g.M = M; g.N = N; g.K = K; g.batch = b0 * b1;
-    int rc = stage_view(ws, A, a_strides, b0, b1, M, K, /*reduction_is_cols=*/true, prec, stream, &g.A);
+    int rc = stage_view(ws, A, a_strides, b0, b1, M, K, /*reduction_is_cols=*/true, prec, stream, &g.A, A_staged_out);
     if (rc) return rc;
-    rc = stage_view(ws, B, b_strides, b0, b1, K, N, /*reduction_is_cols=*/false, prec, stream, &g.B);
+    rc = stage_view(ws, B, b_strides, b0, b1, K, N, /*reduction_is_cols=*/false, prec, stream, &g.B, B_staged_out);
     if (rc) return rc;
     g.D = C; g.ldd = N; g.batch_stride_d = M * N;
     g.epi.alpha = alpha;
@@ -103,7 +126,8 @@ int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* 
 int nnb_matmul_backward(const float* A, const int64_t a_strides[4], const float* B,
                         const int64_t b_strides[4], const float* G, float* dA, float* dB,
                         int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N, float alpha,
-                        int prec, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                        int prec, const void* A_staged, const void* B_staged, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream) {
     NNB_REQUIRE(A && B && G && a_strides && b_strides, "nnb_matmul_backward: null pointer");
     NNB_REQUIRE(b0 > 0 && b1 > 0 && M > 0 && K > 0 && N > 0, "nnb_matmul_backward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_matmul_backward: bad prec");
@@ -119,11 +143,13 @@ int nnb_matmul_backward(const float* A, const int64_t a_strides[4], const float*
     g_red_rows.mn_major = true;
     GemmOperand a_op, b_op;
     if (dA) {  // dA[M,K] = alpha * G[M,N] . B[K,N]^T   (autograd.py:209)
-        rc = stage_view(ws, B, b_strides, b0, b1, K, N, /*reduction_is_cols=*/true, prec, stream, &b_op);
+        rc = stage_view(ws, B, b_strides, b0, b1, K, N, /*reduction_is_cols=*/true, prec, stream, &b_op,
+                        const_cast<void*>(B_staged), B_staged != nullptr);
         if (rc) return rc;
     }
     if (dB) {  // dB[K,N] = alpha * A[M,K]^T . G[M,N]   (autograd.py:211)
-        rc = stage_view(ws, A, a_strides, b0, b1, M, K, /*reduction_is_cols=*/false, prec, stream, &a_op);
+        rc = stage_view(ws, A, a_strides, b0, b1, M, K, /*reduction_is_cols=*/false, prec, stream, &a_op,
+                        const_cast<void*>(A_staged), A_staged != nullptr);
         if (rc) return rc;
     }
     const size_t sk_bytes = ws.remaining();

@@ -49,6 +49,14 @@ extern "C" int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, 
     cudaStreamCaptureStatus cs;
     NNB_CUDA_OK(cudaStreamIsCapturing(stream, &cs));
     NNB_REQUIRE(cs == cudaStreamCaptureStatusNone, "nnb_probe_linear_gemm: stream is capturing");
+    // the legacy default stream cannot be captured: run on a private stream, ordered after the caller's work
+    NNB_CUDA_OK(cudaStreamSynchronize(stream));
+    struct OwnStream {
+        cudaStream_t s = nullptr;
+        ~OwnStream() { if (s) cudaStreamDestroy(s); }
+    } own;
+    NNB_CUDA_OK(cudaStreamCreateWithFlags(&own.s, cudaStreamNonBlocking));
+    stream = own.s;
     Bufs bufs;
     // fwd: A = X[M,K], B = W[N,K] -> D[M,N];  dgrad: A = G[M,N], B = W[N,K] (MN-major) -> D[M,K];
     // wgrad: A = G[M,N] (MN-major), B = X[M,K] (MN-major) -> D[N,K]   (linear.py:19-22, 54)

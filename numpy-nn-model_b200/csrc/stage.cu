@@ -39,8 +39,8 @@ struct StageArgs {
 // idles. blockIdx.y owns a chunk of rows, blockIdx.z = batch. Column partial sums (bias gradient)
 // are reduced over TY in shared memory and written once per block.
 template <bool X3, int OP>
-__global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
-    const int TX = a.tx, TY = 128 / a.tx;
+__global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
+    const int TX = a.tx, TY = (int)blockDim.x / a.tx;
     const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x / TX;
     const long long c = ((long long)blockIdx.x * TX + tx) * 4;
     const int bz = blockIdx.z;
@@ -52,7 +52,6 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < a.v.cols) {
         const bool full = c + 3 < a.v.cols;
-#pragma unroll 4
         for (long long r = r0 + ty; r < r1; r += TY) {
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             if (full && a.vec_ok) {
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(128) stage_rows_kernel(const StageArgs a) {
         }
     }
     if (a.partial != nullptr) {
-        __shared__ float red[128 * 4];
+        __shared__ float red[512 * 4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) red[(ty * TX + tx) * 4 + j] = cs[j];
         __syncthreads();
@@ -167,7 +166,9 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     a.vec_ok = src.s_c == 1 && (src.s_r % 4) == 0 && (src.s_b0 % 4) == 0 && (src.s_b1 % 4) == 0 &&
                al16(src.ptr) && (aux == nullptr || al16(aux));
 
-    const int threads = 128;
+    // with column sums: 512-thread blocks, so ~256 row chunks (= partial rows to re-read) still put
+    // >= 128 K threads in flight; plain conversion keeps small blocks and up to 1024 chunks
+    const int threads = colsum ? 512 : 128;
     int tx = 128;
     while (tx > 1 && (tx / 2) * 4 >= src.cols) tx >>= 1;  // smallest power of two covering the columns
     a.tx = tx;

@@ -192,7 +192,14 @@ class Tensor:
         t = self.ensure_tensor(t)
         rg = self.requires_grad or t.requires_grad
         xp = self.xp
-        out = Tensor._wrap(xp.matmul(self.data, t.data), (self, t) if rg else None, "matmul", rg, self.device)
+        staged = None
+        if rg and self.device == "cuda" and self.data.ndim >= 2 and t.data.ndim >= 2:
+            from . import b200
+            # keep the bf16 planes of both operands: backward (dA = G.B^T, dB = A^T.G) reads the same planes
+            data, staged = b200.matmul(self.data, t.data, keep_staged=True)
+        else:
+            data = xp.matmul(self.data, t.data)
+        out = Tensor._wrap(data, (self, t) if rg else None, "matmul", rg, self.device)
         if not rg:
             return out
 
@@ -215,7 +222,7 @@ class Tensor:
                     g2 = g2.unsqueeze(-2)
                 if bd.ndim == 1:
                     g2 = g2.unsqueeze(-1)
-                da, db = b200.matmul_backward(a2, b2, g2, a.requires_grad, b.requires_grad)
+                da, db = b200.matmul_backward(a2, b2, g2, a.requires_grad, b.requires_grad, staged=staged)
                 if da is not None:
                     a.apply_grad(da.squeeze(-2) if ad.ndim == 1 else da)
                 if db is not None:

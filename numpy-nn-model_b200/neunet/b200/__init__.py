@@ -85,12 +85,13 @@ _SIGNATURES = {
     "nnb_weight_staged_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "nnb_stage_weight": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "nnb_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
+    "nnb_matmul_staged_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "nnb_matmul_forward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_int64,
-                                   c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_size_t,
-                                   c_void_p]),
+                                   c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
     "nnb_matmul_backward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int,
-                                    c_void_p, c_size_t, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nnb_conv2d_out_shape": (c_int, [POINTER(nnb_conv2d_desc), POINTER(c_int64), POINTER(c_int64)]),
     "nnb_conv2d_workspace_bytes": (c_size_t, [POINTER(nnb_conv2d_desc), c_int, c_int]),
     "nnb_conv2d_forward": (c_int, [POINTER(nnb_conv2d_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_int,
@@ -120,6 +121,7 @@ _SIGNATURES = {
     "nnb_adamw_step": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_int64, c_int,
                                c_float, c_void_p]),
     "nnb_adamw_set_step": (c_int, [c_void_p, c_int64, c_void_p]),
+    "nnb_adamw_set_staging": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p]),
     "nnb_adamw_destroy": (c_int, [c_void_p]),
 }
 
@@ -209,7 +211,12 @@ def _workspace(nbytes: int):
 
 # ---- weight staging cache ------------------------------------------------------------------------
 class _StagedWeight:
-    __slots__ = ("buf", "key")
+    """bf16 planes of one weight. `persistent` entries are owned by an optimizer whose step kernel rewrites
+    them with every update (nnb_adamw_set_staging): they stay valid across CUDA-graph captures/replays."""
+    __slots__ = ("buf", "key", "persistent")
+
+    def __init__(self):
+        self.persistent = False
 
 
 def weights_changed() -> None:
@@ -222,10 +229,20 @@ def _staged_weight(owner, w2d: torch.Tensor, rows: int, cols: int):
     """bf16 planes of a weight matrix, converted once per optimizer step. `owner` is the Parameter
     (any object that can hold an attribute); None disables caching."""
     prec = _state["prec"]
-    key = (w2d.data_ptr(), w2d._version, _state["weights_epoch"], prec, rows, cols, _cache_scope())
     cached = getattr(owner, "_b200_staged", None) if owner is not None else None
-    if cached is not None and cached.key == key:
+    if owner is not None:
+        try:
+            owner._b200_wants_staging = True  # optimizers emit the planes of such weights from their step kernel
+        except AttributeError:
+            pass
+    if cached is not None and cached.persistent and cached.key == (w2d.data_ptr(), w2d._version, _state["weights_epoch"],
+                                                                     prec, rows, cols):
         return cached.buf
+    key = (w2d.data_ptr(), w2d._version, _state["weights_epoch"], prec, rows, cols, _cache_scope())
+    if cached is not None and not cached.persistent and cached.key == key:
+        return cached.buf
+    if cached is not None and cached.persistent:
+        cached = None  # never scribble over an optimizer-owned buffer with another precision / shape
     L = lib()
     nbytes = L.nnb_weight_staged_bytes(rows, cols, prec)
     if cached is not None and cached.buf.numel() >= nbytes:
@@ -372,8 +389,10 @@ def _matmul_norm(a, b):
     return a4, b4, (a4.shape[0], a4.shape[1], M, K, N), out_shape, tuple(batch)
 
 
-def matmul(a, b, alpha=1.0):
-    """``xp.matmul`` for device arrays (neunet/autograd.py:199), any NumPy-legal rank combination."""
+def matmul(a, b, alpha=1.0, keep_staged=False):
+    """``xp.matmul`` for device arrays (neunet/autograd.py:199), any NumPy-legal rank combination.
+    With keep_staged the bf16 planes of both operands are kept and returned as a third value
+    ``(a_staged, b_staged, prec)`` for ``matmul_backward(..., staged=...)``."""
     require_device()
     L = lib()
     a = a if a.dtype == torch.float32 else a.to(torch.float32)
@@ -384,12 +403,19 @@ def matmul(a, b, alpha=1.0):
     out = torch.empty((b0, b1, M, N), dtype=torch.float32, device="cuda")
     prec = _state["prec"]
     ws = _workspace(L.nnb_matmul_workspace_bytes(b0, b1, M, K, N, prec, 0))
+    ast = bst = None
+    if keep_staged:
+        ast = torch.empty(L.nnb_matmul_staged_bytes(b0, b1, M, K, prec), dtype=torch.uint8, device="cuda")
+        bst = torch.empty(L.nnb_matmul_staged_bytes(b0, b1, K, N, prec), dtype=torch.uint8, device="cuda")
     _check(L.nnb_matmul_forward(_ptr(a4), _strides4(a4), _ptr(b4), _strides4(b4), _ptr(out), b0, b1, M, K, N,
-                                float(alpha), prec, _ptr(ws), ws.numel(), _stream()), "nnb_matmul_forward")
+                                float(alpha), prec, _ptr(ast), _ptr(bst), _ptr(ws), ws.numel(), _stream()),
+           "nnb_matmul_forward")
+    if keep_staged:
+        return out.reshape(out_shape), (ast, bst, prec, tuple(_strides4(a4)), tuple(_strides4(b4)))
     return out.reshape(out_shape)
 
 
-def matmul_backward(a, b, grad, need_da=True, need_db=True, alpha=1.0):
+def matmul_backward(a, b, grad, need_da=True, need_db=True, alpha=1.0, staged=None):
     """(dA, dB) for matrix x matrix operands, shaped like the BROADCAST operands (the caller's
     apply_grad un-broadcasts, neunet/autograd.py:85-93, 948-962)."""
     require_device()
@@ -400,9 +426,12 @@ def matmul_backward(a, b, grad, need_da=True, need_db=True, alpha=1.0):
     db = torch.empty((b0, b1, K, N), dtype=torch.float32, device="cuda") if need_db else None
     prec = _state["prec"]
     ws = _workspace(L.nnb_matmul_workspace_bytes(b0, b1, M, K, N, prec, 1))
+    ast = bst = None
+    if staged is not None and staged[2] == prec and staged[3] == tuple(_strides4(a4)) and staged[4] == tuple(_strides4(b4)):
+        ast, bst = staged[0], staged[1]  # planes converted by the forward call: same views, same precision
     _check(L.nnb_matmul_backward(_ptr(a4), _strides4(a4), _ptr(b4), _strides4(b4), _ptr(g4), _ptr(da), _ptr(db),
-                                 b0, b1, M, K, N, float(alpha), prec, _ptr(ws), ws.numel(), _stream()),
-           "nnb_matmul_backward")
+                                 b0, b1, M, K, N, float(alpha), prec, _ptr(ast), _ptr(bst), _ptr(ws), ws.numel(),
+                                 _stream()), "nnb_matmul_backward")
     if da is not None:
         da = da.reshape(batch + (M, K))
     if db is not None:
@@ -552,8 +581,18 @@ def manual_seed(seed: int) -> None:
 
 def _rng_epoch_dev():
     if _rng["dev"] is None:
+        if torch.cuda.is_current_stream_capturing():
+            # allocated (and zero-filled) inside a capture it would belong to the graph and be reset by every replay
+            raise RuntimeError("dropout inside a CUDA-graph capture needs the RNG epoch buffer created beforehand "
+                               "(use neunet.b200.GraphedStep, or call neunet.b200.rng_prepare_capture() first)")
         _rng["dev"] = torch.zeros(1, dtype=torch.int64, device="cuda")
     return _rng["dev"]
+
+
+def rng_prepare_capture():
+    """Create the device-resident RNG epoch before a CUDA-graph capture that contains dropout."""
+    require_device()
+    return _rng_epoch_dev()
 
 
 def dropout_ticket():
@@ -639,6 +678,7 @@ class GraphedStep:
         self.optimizer = optimizer
         _state["capture_epoch"] += 1  # invalidates every staged-operand cache made outside this capture
         self.graph = torch.cuda.CUDAGraph()
+        rng_prepare_capture()
         _rng["graph_used"] = False
         with torch.cuda.graph(self.graph):
             self.outputs = fn(*self.inputs)
@@ -704,6 +744,48 @@ class FusedAdam:
         _check(L.nnb_adamw_step(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                 int(t), mode, float(grad_scale), _stream()), "nnb_adamw_step")
         weights_changed()
+
+    def sync_staging(self, owners):
+        """Fused weight staging: for every parameter that a Linear layer has asked bf16 planes for
+        (``_b200_wants_staging``), the step kernel also emits those planes, and the parameter's staging
+        cache entry is stamped valid for the new weights. Called by the optimizer around each step."""
+        prec = _state["prec"]
+        want = tuple(bool(getattr(o, "_b200_wants_staging", False)) and o.data.ndim == 2 for o in owners)
+        if torch.cuda.is_current_stream_capturing():
+            if getattr(self, "_stage_key", None) != (want, prec):
+                return  # tables cannot be re-uploaded inside a capture; the layers keep converting on their own
+        elif getattr(self, "_stage_key", None) != (want, prec):
+            bufs, cols = [], []
+            for o, w in zip(owners, want):
+                if w:
+                    r, c = o.data.shape
+                    bufs.append(torch.empty(lib().nnb_weight_staged_bytes(r, c, prec), dtype=torch.uint8, device="cuda"))
+                    cols.append(c)
+                else:
+                    bufs.append(None)
+                    cols.append(1)
+            arr = (c_void_p * self.n)(*[(b.data_ptr() if b is not None else None) for b in bufs])
+            carr = (c_int64 * self.n)(*cols)
+            _check(lib().nnb_adamw_set_staging(self._h, arr if any(want) else None, carr, prec, _stream()),
+                   "nnb_adamw_set_staging")
+            self._stage_bufs, self._stage_key = bufs, (want, prec)
+        self._stage_live = True
+
+    def stamp_staging(self, owners, grads):
+        """After a step: mark the emitted planes as the staged form of the CURRENT weights."""
+        if not getattr(self, "_stage_live", False):
+            return
+        want, prec = self._stage_key
+        for o, w, b, g in zip(owners, want, self._stage_bufs, grads):
+            if not w or b is None:
+                continue
+            prev = getattr(o, "_b200_staged", None)
+            if g is None and not (prev is not None and prev.persistent and prev.buf is b):
+                continue  # parameter skipped by the kernel and never emitted: nothing valid to stamp
+            sw = _StagedWeight()
+            sw.buf, sw.persistent = b, True
+            sw.key = (o.data.data_ptr(), o.data._version, _state["weights_epoch"], prec) + tuple(o.data.shape)
+            o._b200_staged = sw
 
     def set_step(self, t):
         """Seed the device-resident step counter (steps already taken) before capturing a graph."""

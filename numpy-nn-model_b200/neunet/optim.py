@@ -48,7 +48,9 @@ class _AdamBase:
                 if not g.is_contiguous() or g.dtype != p.data.dtype:
                     g = g.contiguous().to(p.data.dtype)
             grads.append(g)
+        self._fused.sync_staging(self.params)  # the kernel also writes the bf16 planes Linear layers read
         self._fused.step(grads, self.lr, self.betas, self.eps, self.weight_decay, self.t, self._mode, self.grad_scale)
+        self._fused.stamp_staging(self.params, grads)
 
     def step(self):
         self.t += 1
