@@ -49,6 +49,16 @@ for _p in (os.path.join(ROOT, "examples"),):
         sys.path.insert(0, _p)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch measured once with ncu (profiles/r1_gemm_classes_dram.json); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_classes_dram.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -229,8 +239,11 @@ class MlpWorkload:
         us, nl = b200.probe_linear_gemm(B, K, N, form=0, with_bias=True, swish=True, rounds=5)
         alg = B * K * 2 + N * K * 2 + 2 * B * N * 4
         ach = alg / (us * 1e-6) / 1e9
+        tr = (ncu_traffic() or {}).get("mlp_layer1_fwd")
         return {"bound": "hbm", "kernel": "gemm_tcgen05_kernel: Linear-1 forward 4096x784x128 + bias + Swish epilogue",
-                "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": (tr["dram_read"] + tr["dram_write"]) if tr else None,
+                "traffic_source": tr["source"] if tr else None,
                 "us_per_launch": us, "algorithmic_bytes": alg, "flops_per_launch": 2 * B * K * N,
                 "peak_source": pk["source"] + " hbm_gbs",
                 "how": "graph-paced launches over rotating operand sets > L2, CUDA events (nnb_probe_linear_gemm)"}
@@ -300,7 +313,11 @@ class GptWorkload:
         return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel: all nn.Linear fwd/dgrad/wgrad launches of one step "
                                              f"({ngemm} GEMMs, M={M_})",
                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "us_per_launch": tot_us / ngemm,
+                "frac": ach / pk["bf16_tflops_sustained"],
+                "traffic": (ncu_traffic() or {}).get("traffic_per_launch_weighted"),
+                "traffic_note": "DRAM read+write bytes per launch, weighted over the same GEMM classes (profiles/r1_gemm_classes_dram.md; "
+                                "algorithmic operand+output bytes per launch: %.0f)" % ((ncu_traffic() or {}).get("algorithmic_bytes_per_launch_weighted", float("nan"))),
+                "us_per_launch": tot_us / ngemm,
                 "flops_per_step": tot_fl, "gemm_us_per_step": tot_us,
                 "largest_class": f"{top['layer']} {top['form']} {top['M']}x{top['K']}x{top['N']}: {top['us']} us, {top['tflops']} TFLOP/s",
                 "classes": rows,

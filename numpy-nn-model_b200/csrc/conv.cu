@@ -123,6 +123,124 @@ __global__ void stage_nchw_to_c_bhw_kernel(const float* __restrict__ g, int B, i
     }
 }
 
+// ---------------------------------------------------------------- channels-last fast path (C % 8 == 0)
+// The generic gather above pays ~15 integer divisions per ELEMENT and reads NCHW with a 9-way scatter.
+// When both channel counts are multiples of 8 the activations are first converted ONCE to bf16
+// channels-last planes ([B*H*W][C], tiled transpose), and `col` is built in (k, l, c) order, so every
+// (output position, tap) is one contiguous run of C bf16 copied with 16-byte accesses. The weights are
+// staged in the same (k, l, c) order; wgrad's [Cout][(k,l,c)] result is permuted back to the reference's
+// [Cout][Cin][kh][kw] by a small kernel.
+
+// src fp32 [B][C][HW] -> dst bf16 [B][HW][C]   (32 x 32 tiles through shared memory)
+template <bool X3>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW,
+                                                           __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const float* s = src + (long long)b * C * HW;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, hw = hw0 + tx;
+        tile[r][tx] = (c < C && hw < HW) ? s[(long long)c * HW + hw] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int hw = hw0 + r, c = c0 + tx;
+        if (hw < HW && c < C) {
+            const float v = tile[tx][r];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const long long o = ((long long)b * HW + hw) * C + c;
+            hi[o] = h;
+            if (X3) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
+// col[(b,p,q)][(k,l,c)] = nhwc[b][yy][xx][c] (same tap geometry as GatherArgs); one thread = 8 channels
+struct GatherNhwcArgs {
+    const __nv_bfloat16* hi_src;
+    const __nv_bfloat16* lo_src;
+    int C, Hs, Ws, P, Q, kh, kw;
+    int sp0, sp1, off0, off1, dk0, dk1, up0, up1;
+    long long M;
+    long long ld;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(256) gather_nhwc_kernel(const GatherNhwcArgs a) {
+    const int c8 = a.C >> 3;
+    const int taps = a.kh * a.kw;
+    const long long per_row = (long long)taps * c8;
+    const long long total = a.M * per_row;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long m = idx / per_row;
+        const int rem = (int)(idx - m * per_row);
+        const int t = rem / c8;
+        const int j = rem - t * c8;
+        const int kk = t / a.kw, lw = t - kk * a.kw;
+        const int q = (int)(m % a.Q);
+        const long long t2 = m / a.Q;
+        const int p = (int)(t2 % a.P);
+        const int b = (int)(t2 / a.P);
+        const int ny = p * a.sp0 - a.off0 + kk * a.dk0;
+        const int nx = q * a.sp1 - a.off1 + lw * a.dk1;
+        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+        if (ny >= 0 && nx >= 0 && (ny % a.up0) == 0 && (nx % a.up1) == 0) {
+            const int yy = ny / a.up0, xx = nx / a.up1;
+            if (yy < a.Hs && xx < a.Ws) {
+                const long long so = (((long long)b * a.Hs + yy) * a.Ws + xx) * a.C + j * 8;
+                vh = *reinterpret_cast<const uint4*>(a.hi_src + so);
+                if (X3) vl = *reinterpret_cast<const uint4*>(a.lo_src + so);
+            }
+        }
+        const long long o = m * a.ld + (long long)t * a.C + j * 8;
+        *reinterpret_cast<uint4*>(a.hi + o) = vh;
+        if (X3) *reinterpret_cast<uint4*>(a.lo + o) = vl;
+    }
+}
+
+// Wk[o][(k,l,c)] = W[o][c][k][l]; with `flip` (dgrad): Wr[i][(k',l',o)] = W[o][i][kh-1-k'][kw-1-l']
+template <bool X3>
+__global__ void stage_weight_klc_kernel(const float* __restrict__ W, int Cout, int Cin, int khw, int flip,
+                                        long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long long total = (long long)Cout * Cin * khw;
+    const int R = flip ? Cin : Cout, Cc = flip ? Cout : Cin;  // staged rows / channel (fastest) dimension
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % Cc);
+        const long long t = idx / Cc;
+        const int tap = (int)(t % khw);
+        const int r = (int)(t / khw);
+        (void)R;
+        const float v = flip ? W[((long long)c * Cin + r) * khw + (khw - 1 - tap)]
+                             : W[((long long)r * Cin + c) * khw + tap];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const long long dst = (long long)r * ld + (long long)tap * Cc + c;
+        hi[dst] = h;
+        if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// dW[o][c][tap] = T[o][(tap, c)]
+__global__ void permute_dw_kernel(const float* __restrict__ T, int Cout, int Cin, int khw, float* __restrict__ dW) {
+    const long long total = (long long)Cout * Cin * khw;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % khw);
+        const long long t = idx / khw;
+        const int c = (int)(t % Cin);
+        const int o = (int)(t / Cin);
+        dW[idx] = T[((long long)o * khw + tap) * Cin + c];
+    }
+}
+
 // db[o] = sum_{b,h,w} dO[b,o,h,w]   (conv2d.py:94) -- one block per channel, fixed-order tree reduce
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ g, int B, int C,
                                                           int HW, float* __restrict__ out) {
@@ -290,6 +408,45 @@ Staged as_staged(const Planes& p, int64_t rows, int64_t cols) {
     return s;
 }
 
+bool use_nhwc(const Geo& g) { return !use_direct(g) && (g.Cin % 8) == 0 && (g.Cout % 8) == 0; }
+
+Planes take_nhwc(Bump& ws, int64_t positions, int64_t C, int prec) {
+    Planes p;
+    const size_t b = (size_t)round_up(positions * C * 2, 256);
+    p.hi = static_cast<__nv_bfloat16*>(ws.take(b));
+    p.lo = prec == NNB_PREC_BF16X3 ? static_cast<__nv_bfloat16*>(ws.take(b)) : nullptr;
+    return p;
+}
+
+int run_to_nhwc(const float* src, int B, int C, int HW, const Planes& dst, bool x3, cudaStream_t stream) {
+    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+    NNB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv2d: too many channels / images for the layout pass");
+    if (x3) nchw_to_nhwc_kernel<true><<<grid, 256, 0, stream>>>(src, C, HW, dst.hi, dst.lo);
+    else nchw_to_nhwc_kernel<false><<<grid, 256, 0, stream>>>(src, C, HW, dst.hi, dst.lo);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int run_gather_nhwc(const GatherNhwcArgs& a, bool x3, cudaStream_t stream) {
+    const long long total = a.M * a.kh * a.kw * (a.C / 8);
+    if (x3) gather_nhwc_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(a);
+    else gather_nhwc_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(a);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int run_stage_weight_klc(const float* W, const Geo& g, bool flip, const Planes& dst, int64_t ld, bool x3,
+                         cudaStream_t stream) {
+    const long long total = (long long)g.Cout * g.Cin * g.kh * g.kw;
+    if (x3) stage_weight_klc_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(W, g.Cout, g.Cin, g.kh * g.kw, flip ? 1 : 0, ld, dst.hi, dst.lo);
+    else stage_weight_klc_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(W, g.Cout, g.Cin, g.kh * g.kw, flip ? 1 : 0, ld, dst.hi, dst.lo);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
 }  // namespace
 }  // namespace nnb
 
@@ -314,6 +471,13 @@ size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backwa
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo, Kc = (int64_t)g.Cin * g.kh * g.kw;
     const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
     size_t b = 8192;
+    if (use_nhwc(g)) {  // channels-last planes of X and dO, fp32 [Cout][(k,l,c)] wgrad result
+        b += p * (size_t)round_up((int64_t)g.B * g.H * g.W * g.Cin * 2, 256);
+        if (backward) {
+            b += p * (size_t)round_up(M * g.Cout * 2, 256);
+            b += (size_t)round_up((int64_t)g.Cout * Kc * 4, 256);
+        }
+    }
     b += p * staged_plane_bytes(1, M, Kc);  // col(X)
     if (!backward) {
         b += p * staged_plane_bytes(1, g.Cout, Kc);  // W
@@ -348,14 +512,28 @@ int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt
     Planes col = take_planes(ws, M, Kc, prec);
     Planes wp = take_planes(ws, g.Cout, Kc, prec);
     if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_forward: workspace too small (need >= %zu)", ws.off);
-    GatherArgs a{X, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
-                 M, (int)Kc, staged_ld(Kc), col.hi, col.lo};
-    rc = run_gather(a, x3, stream);
-    if (rc) return rc;
     Staged wst;
-    rc = stage_operand(view2d(Wt, g.Cout, Kc, Kc), false, prec, wp.hi, wp.lo, STAGE_COPY, nullptr, 0.f,
-                       nullptr, nullptr, stream, &wst);
-    if (rc) return rc;
+    if (use_nhwc(g)) {
+        Planes xh = take_nhwc(ws, (int64_t)g.B * g.H * g.W, g.Cin, prec);
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_forward: workspace too small (need >= %zu)", ws.off);
+        rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
+        if (rc) return rc;
+        GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+                         M, staged_ld(Kc), col.hi, col.lo};
+        rc = run_gather_nhwc(a, x3, stream);
+        if (rc) return rc;
+        rc = run_stage_weight_klc(Wt, g, false, wp, staged_ld(Kc), x3, stream);
+        if (rc) return rc;
+        wst = as_staged(wp, g.Cout, Kc);
+    } else {
+        GatherArgs a{X, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+                     M, (int)Kc, staged_ld(Kc), col.hi, col.lo};
+        rc = run_gather(a, x3, stream);
+        if (rc) return rc;
+        rc = stage_operand(view2d(Wt, g.Cout, Kc, Kc), false, prec, wp.hi, wp.lo, STAGE_COPY, nullptr, 0.f,
+                           nullptr, nullptr, stream, &wst);
+        if (rc) return rc;
+    }
     GemmProblem p;
     p.M = g.Cout; p.N = M; p.K = Kc;
     p.A.st = wst;
@@ -405,6 +583,58 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
         wr = take_planes(ws, g.Cin, Kg, prec);
     }
     if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
+    if (use_nhwc(g)) {
+        // channels-last path: X and dO become bf16 [positions][C] planes once; dO's planes are wgrad's
+        // A operand as they are (MN-major: rows = reduction) and the gather source of dgrad
+        Planes xh = take_nhwc(ws, (int64_t)g.B * g.H * g.W, g.Cin, prec);
+        Planes gh = take_nhwc(ws, M, g.Cout, prec);
+        float* dwt = static_cast<float*>(ws.take((size_t)round_up((int64_t)g.Cout * Kc * 4, 256)));
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
+        const size_t skb = ws.remaining();
+        float* skp = static_cast<float*>(ws.take(skb));
+        rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
+        if (rc) return rc;
+        rc = run_to_nhwc(dO, g.B, g.Cout, (int)HWo, gh, x3, stream);
+        if (rc) return rc;
+        GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+                         M, staged_ld(Kc), col.hi, col.lo};
+        rc = run_gather_nhwc(a, x3, stream);
+        if (rc) return rc;
+        {   // wgrad: T[o][(k,l,c)] = sum_m gh[m][o] * col[m][(k,l,c)], then T -> dW[o][c][k][l]
+            GemmProblem p;
+            p.M = g.Cout; p.N = Kc; p.K = M;
+            p.A.st = as_staged(gh, M, g.Cout); p.A.mn_major = true;
+            p.B.st = as_staged(col, M, Kc); p.B.mn_major = true;
+            p.D = dwt; p.ldd = Kc;
+            p.splitk_ws = skp; p.splitk_ws_bytes = skb;
+            rc = gemm(p, stream);
+            if (rc) return rc;
+            const long long total = (long long)g.Cout * Kc;
+            permute_dw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(dwt, g.Cout, g.Cin, g.kh * g.kw, dW);
+            count_launch();
+            NNB_CUDA_OK(cudaGetLastError());
+        }
+        if (dX) {
+            GatherNhwcArgs ga{gh.hi, gh.lo, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
+                              g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1, g.s0, g.s1,
+                              Mx, staged_ld(Kg), colg.hi, colg.lo};
+            rc = run_gather_nhwc(ga, x3, stream);
+            if (rc) return rc;
+            rc = run_stage_weight_klc(Wt, g, true, wr, staged_ld(Kg), x3, stream);
+            if (rc) return rc;
+            const int64_t HW = (int64_t)g.H * g.W;
+            GemmProblem p;
+            p.M = g.Cin; p.N = Mx; p.K = Kg;
+            p.A.st = as_staged(wr, g.Cin, Kg);
+            p.B.st = as_staged(colg, Mx, Kg);
+            p.D = dX; p.ldd = HW;
+            p.col_group = HW; p.group_stride = (int64_t)g.Cin * HW;
+            p.splitk_ws = skp; p.splitk_ws_bytes = skb;
+            rc = gemm(p, stream);
+            if (rc) return rc;
+        }
+        return NNB_OK;
+    }
     const size_t sk_bytes = ws.remaining();
     float* sk = static_cast<float*>(ws.take(sk_bytes));
 

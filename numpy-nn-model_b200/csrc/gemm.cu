@@ -382,8 +382,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (ptx::elect_one()) {
-                        ptx::tma_store_3d(&maps.d, tile_d, col0, row_base, ob);
-                        if (has_z) ptx::tma_store_3d(&maps.z, tile_z, col0, row_base, ob);
+                        if (p.col_group > 0) {  // grouped columns: (column in group, row, group)
+                            const int grp = col0 / p.col_group;
+                            ptx::tma_store_3d(&maps.d, tile_d, col0 - grp * p.col_group, row_base, grp);
+                        } else {
+                            ptx::tma_store_3d(&maps.d, tile_d, col0, row_base, ob);
+                            if (has_z) ptx::tma_store_3d(&maps.z, tile_z, col0, row_base, ob);
+                        }
                         ptx::tma_store_commit();
                     }
                     store_parity ^= 1;
@@ -599,7 +604,9 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     // TMA-store epilogue ~160 cycles per 32-column chunk, HBM ~3400 B/cycle chip-wide)
     const int64_t total_iters_all = ceil_div(g.K, BK) * red_batches;
     const int nseg_h = x3 ? 3 : 1;
-    const bool tma_ok_h = g.col_group == 0 && (g.ldd % 4) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0;
+    const bool tma_ok_h = (g.col_group == 0 || ((g.col_group % 32) == 0 && (g.N % g.col_group) == 0 && g.epi.Z == nullptr &&
+                                                (g.group_stride % 4) == 0)) &&
+                          (g.ldd % 4) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0;
     int bn = 0, cg = 1;
     int64_t splits = 1;
     {
@@ -745,12 +752,20 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
         bool tma = splits == 1 && g.col_group == 0 && g.epi.D16 == nullptr && ok16(g.D) &&
                    (g.ldd % 4) == 0 && (out_batches == 1 || (bsd % 4) == 0) &&
                    (g.epi.Z == nullptr || ok16(g.epi.Z));
+        // column-group outputs (conv: D[o][(b, hw)] -> NCHW) go through TMA too when a 32-column chunk never
+        // straddles two groups: the group index becomes the third tensor-map coordinate
+        const bool tma_grouped = splits == 1 && g.col_group > 0 && (g.col_group % 32) == 0 &&
+                                 (g.N % g.col_group) == 0 && out_batches == 1 && g.epi.D16 == nullptr &&
+                                 g.epi.Z == nullptr && ok16(g.D) && (g.ldd % 4) == 0 && (g.group_stride % 4) == 0;
         if (tma) {
             int rc2 = encode_out_map(&maps.d, g.D, g.N, g.M, g.ldd, out_batches, bsd);
             if (!rc2 && g.epi.Z) rc2 = encode_out_map(&maps.z, g.epi.Z, g.N, g.M, g.ldd, out_batches, bsd);
             if (rc2) return rc2;
+        } else if (tma_grouped) {
+            int rc2 = encode_out_map(&maps.d, g.D, g.col_group, g.M, g.ldd, g.N / g.col_group, g.group_stride);
+            if (rc2) return rc2;
         }
-        ka.tma_store = tma ? 1 : 0;
+        ka.tma_store = (tma || tma_grouped) ? 1 : 0;
     }
 
     const int64_t work = tiles * splits;

@@ -50,7 +50,33 @@ __global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
     const long long r0 = (long long)blockIdx.y * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, (long long)a.v.rows);
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
-    if (c < a.v.cols) {
+    if (OP == STAGE_COPY && c + 3 < a.v.cols && a.vec_ok) {
+        // hot path (contiguous rows, plain conversion): four rows per trip with all loads issued before
+        // the first store, so each thread keeps 64 B in flight instead of 16 B
+        for (long long r = r0 + ty; r < r1; r += 4 * TY) {
+            float4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + (long long)u * TY;
+                t[u] = rr < r1 ? __ldg(reinterpret_cast<const float4*>(src + rr * a.v.s_r + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + (long long)u * TY;
+                if (rr >= r1) break;
+                const float x[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    split_bf16(x[j], h[j], l[j]);
+                    cs[j] += x[j];
+                }
+                const long long o = (long long)bz * a.plane_stride + rr * a.ld + c;
+                *reinterpret_cast<uint2*>(a.hi + o) = *reinterpret_cast<const uint2*>(h);
+                if (X3) *reinterpret_cast<uint2*>(a.lo + o) = *reinterpret_cast<const uint2*>(l);
+            }
+        }
+    } else if (c < a.v.cols) {
         const bool full = c + 3 < a.v.cols;
         for (long long r = r0 + ty; r < r1; r += TY) {
             float x[4] = {0.f, 0.f, 0.f, 0.f};

@@ -334,12 +334,13 @@ def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, ne
     return dx, dw, db
 
 
-def probe_linear_gemm(M, K, N, form=0, with_bias=True, swish=False, rounds=3):
+def probe_linear_gemm(M, K, N, form=0, with_bias=True, swish=False, rounds=3, sets=None):
     """GPU-paced microseconds of one GEMM launch of an nn.Linear form (0 fwd, 1 dgrad, 2 wgrad) in bf16,
     over operand sets that together exceed the L2 (nnb_probe_linear_gemm). Returns (us, launches)."""
     require_device()
     per_set = 2 * (M * K + N * K + M * N) + 4 * max(M * N, M * K, N * K)  # upper bound, bytes
-    sets = int(min(64, max(2, -(-(300 << 20) // per_set))))
+    if sets is None:
+        sets = int(min(64, max(2, -(-(300 << 20) // per_set))))
     us, nl = c_float(0), c_int(0)
     _check(lib().nnb_probe_linear_gemm(M, K, N, form, int(bool(with_bias)) | (2 if swish else 0), sets, rounds, ctypes.byref(us), ctypes.byref(nl),
                                        _stream()), "nnb_probe_linear_gemm")
