@@ -119,6 +119,18 @@ def cpu_gpt_run(cfg, steps, warmup, batch=8, seed=0):
     return dict(samples_per_s=batch * steps / dt, ms_per_step=dt / steps * 1e3, batch=batch, steps=steps)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms must use the host cores they can get
+    (the reference's NumPy path is multi-threaded through OpenBLAS), so lift the BLAS pool limit at run time."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -142,6 +154,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg, label = workload_label(args)
+    use_all_host_threads()
     steps = max(args.steps, 1)
     if args.workload == "gpt":
         steps = min(steps, 5)
@@ -484,6 +497,7 @@ def run_ours(args):
                 "error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
+        use_all_host_threads()
         cpu, cpu_sample = wl.cpu()
         blas, cores = host_threads()
         line = {

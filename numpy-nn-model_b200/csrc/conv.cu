@@ -241,15 +241,19 @@ __global__ void permute_dw_kernel(const float* __restrict__ T, int Cout, int Cin
     }
 }
 
-// db[o] = sum_{b,h,w} dO[b,o,h,w]   (conv2d.py:94) -- one block per channel, fixed-order tree reduce
+// db[o] = sum_{b,h,w} dO[b,o,h,w]   (conv2d.py:94): grid = (channels, chunks of the batch); partial sums are
+// added in a fixed order by direct_wgrad_finish_kernel (deterministic)
+constexpr int CHANNEL_SUM_CHUNKS = 64;
+
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ g, int B, int C,
-                                                          int HW, float* __restrict__ out) {
+                                                          int HW, float* __restrict__ partial) {
     const int c = blockIdx.x;
+    const int bper = (B + gridDim.y - 1) / gridDim.y;
+    const int b0 = blockIdx.y * bper, b1 = min(b0 + bper, B);
     float s = 0.f;
-    const long long n = (long long)B * HW;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        const long long b = i / HW, hw = i - b * HW;
-        s += g[(b * C + c) * HW + hw];
+    for (int b = b0; b < b1; ++b) {
+        const float* p = g + ((long long)b * C + c) * HW;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) s += p[i];
     }
     __shared__ float red[256];
     red[threadIdx.x] = s;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
         if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[c] = red[0];
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * C + c] = red[0];
 }
 
 // ---------------------------------------------------------------- direct fp32 kernels (tiny channel counts)
@@ -323,10 +327,13 @@ direct_dgrad_kernel(const Geo g, const float* __restrict__ dO, const float* __re
     }
 }
 
-// one block per weight element (o, i, k, l): reduce over (b, ho, wo)
+// grid = (weight elements (o, i, k, l), chunks of the (b, ho, wo) reduction): every block writes one partial
+// sum, direct_wgrad_finish_kernel adds the chunks in a fixed order (deterministic, no atomics)
+constexpr int DIRECT_WGRAD_CHUNKS = 64;
+
 __global__ void __launch_bounds__(256)
 direct_wgrad_kernel(const Geo g, const float* __restrict__ X, const float* __restrict__ dO,
-                    float* __restrict__ dW) {
+                    float* __restrict__ partial) {
     int idx = blockIdx.x;
     const int l = idx % g.kw; idx /= g.kw;
     const int k = idx % g.kh; idx /= g.kh;
@@ -334,8 +341,10 @@ direct_wgrad_kernel(const Geo g, const float* __restrict__ X, const float* __res
     const int o = idx / g.Cin;
     const int HWo = g.Ho * g.Wo;
     const long long n = (long long)g.B * HWo;
+    const long long per = (n + gridDim.y - 1) / gridDim.y;
+    const long long e0 = (long long)blockIdx.y * per, e1 = min(e0 + per, n);
     float s = 0.f;
-    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int b = (int)(e / HWo);
         const int r = (int)(e - (long long)b * HWo);
         const int ho = r / g.Wo, wo = r - ho * g.Wo;
@@ -352,7 +361,16 @@ direct_wgrad_kernel(const Geo g, const float* __restrict__ X, const float* __res
         if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
         __syncthreads();
     }
-    if (threadIdx.x == 0) dW[blockIdx.x] = red[0];
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void direct_wgrad_finish_kernel(const float* __restrict__ partial, int nw, int chunks,
+                                           float* __restrict__ dW) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nw) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[(long long)c * nw + w];
+    dW[w] = s;
 }
 
 int grid_for(long long n, int threads) {
@@ -466,11 +484,12 @@ int nnb_conv2d_out_shape(const nnb_conv2d_desc* d, int64_t* Ho, int64_t* Wo) {
 size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backward) {
     Geo g{};
     if (make_geo(d, &g)) return 0;
-    if (use_direct(g)) return 256;
+    const size_t dbp = (size_t)round_up((int64_t)CHANNEL_SUM_CHUNKS * g.Cout * 4, 256) + 256;  // db partial sums
+    if (use_direct(g)) return 512 + dbp + (size_t)DIRECT_WGRAD_CHUNKS * g.Cout * g.Cin * g.kh * g.kw * 4;
     const size_t p = planes(prec);
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo, Kc = (int64_t)g.Cin * g.kh * g.kw;
     const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
-    size_t b = 8192;
+    size_t b = 8192 + dbp;
     if (use_nhwc(g)) {  // channels-last planes of X and dO, fp32 [Cout][(k,l,c)] wgrad result
         b += p * (size_t)round_up((int64_t)g.B * g.H * g.W * g.Cin * 2, 256);
         if (backward) {
@@ -555,14 +574,25 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
     int rc = make_geo(d, &g);
     if (rc) return rc;
     const int64_t HWo = (int64_t)g.Ho * g.Wo;
+    Bump ws(workspace, workspace_bytes);
     if (db) {
-        channel_sum_kernel<<<g.Cout, 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, db);
-        count_launch();
+        const int chunks = std::min(CHANNEL_SUM_CHUNKS, g.B);
+        float* part = static_cast<float*>(ws.take((size_t)CHANNEL_SUM_CHUNKS * g.Cout * 4));
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
+        channel_sum_kernel<<<dim3((unsigned)g.Cout, (unsigned)chunks), 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, part);
+        direct_wgrad_finish_kernel<<<(unsigned)ceil_div(g.Cout, 256), 256, 0, stream>>>(part, g.Cout, chunks, db);
+        count_launch(2);
         NNB_CUDA_OK(cudaGetLastError());
     }
     if (use_direct(g)) {
-        direct_wgrad_kernel<<<g.Cout * g.Cin * g.kh * g.kw, 256, 0, stream>>>(g, X, dO, dW);
-        count_launch();
+        const int nw = g.Cout * g.Cin * g.kh * g.kw;
+        const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DIRECT_WGRAD_CHUNKS, (g.B * HWo + 4095) / 4096));
+        Bump& dws = ws;
+        float* partial = static_cast<float*>(dws.take((size_t)chunks * nw * 4));
+        if (!dws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", dws.off);
+        direct_wgrad_kernel<<<dim3((unsigned)nw, (unsigned)chunks), 256, 0, stream>>>(g, X, dO, partial);
+        direct_wgrad_finish_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, stream>>>(partial, nw, chunks, dW);
+        count_launch(2);
         if (dX) {
             const long long total = (long long)g.B * g.Cin * g.H * g.W;
             direct_dgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(g, dO, Wt, dX);
@@ -574,7 +604,6 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
     const bool x3 = prec == NNB_PREC_BF16X3;
     const int64_t M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
     const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
-    Bump ws(workspace, workspace_bytes);
     Planes col = take_planes(ws, M, Kc, prec);
     Planes gp = take_planes(ws, g.Cout, M, prec);
     Planes colg{nullptr, nullptr}, wr{nullptr, nullptr};
