@@ -107,6 +107,13 @@ int nnb_stage_weight(const float* W, int64_t rows, int64_t cols, int prec, void*
  * prec) they save re-converting A and B there.
  */
 size_t nnb_matmul_staged_bytes(int64_t b0, int64_t b1, int64_t rows, int64_t cols, int prec);
+/* Opt-in fp32 CUDA-core path for small batched products (>= 16 batch elements with M, K, N <= 128, e.g. the
+ * 64 x 64 x 64 attention products of examples/gpt.ipynb): exact fp32, one launch, no staging, no workspace;
+ * prec and the staged-plane arguments are ignored there. Off by default (the tcgen05 path measured faster
+ * inside the GPT step); nnb_matmul_set_small_path(1) turns it on process-wide and returns the previous
+ * setting. nnb_matmul_uses_tensor_cores() tells which path a call with these sizes takes (1 = tcgen05). */
+int nnb_matmul_set_small_path(int on);
+int nnb_matmul_uses_tensor_cores(int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N);
 size_t nnb_matmul_workspace_bytes(int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N,
                                   int prec, int backward);
 int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* B,

@@ -613,6 +613,8 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
         static const int env_cg = [] { const char* e = getenv("NNB_GEMM_CG"); return e ? atoi(e) : 0; }();
         static const int verbose = [] { const char* e = getenv("NNB_GEMM_VERBOSE"); return e ? atoi(e) : 0; }();
         static const int env_bn = [] { const char* e = getenv("NNB_GEMM_BN"); return e ? atoi(e) : 0; }();
+        static const int env_splits = [] { const char* e = getenv("NNB_GEMM_SPLITS"); return e ? atoi(e) : 0; }();
+        const int force_splits = g.force_splits ? g.force_splits : env_splits;
         int force_cg = g.force_cg ? g.force_cg : env_cg;
         int force_bn = g.force_bn ? g.force_bn : env_bn;
         if (force_cg == 2 && g.M <= BM) force_cg = 1;  // a single row-block cannot use a CTA pair
@@ -632,7 +634,7 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
                 const int64_t t = ceil_div(g.M, BM * cgi) * ceil_div(g.N, c) * out_batches;
                 for (int si = 0; si < 12; ++si) {
                     const int64_t sp = scand[si];
-                    if (g.force_splits && sp != g.force_splits) continue;
+                    if (force_splits && sp != force_splits) continue;
                     if (sp > 1 && (sp > total_iters_all || total_iters_all / sp < 2)) continue;
                     if (sp > 1) {
                         const size_t need = (size_t)sp * out_batches * g.M * g.N * 4;
@@ -647,7 +649,7 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
                     double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0 + (cgi == 2 ? 800.0 : 0.0);
                     if (sp > 1) {
                         const double out_bytes = (double)g.M * g.N * out_batches * 4.0;
-                        cyc += (2.0 * sp + 1.0) * out_bytes / 3400.0 + 4000.0;
+                        cyc += (2.0 * sp + 1.0) * out_bytes / 3400.0 + 7000.0;  // partial traffic + the dependent finishing launch (measured: profiles/r1_linear_ladder.md, wgrad sweep)
                     }
                     if (cyc < best) { best = cyc; bn = c; splits = sp; cg = cgi; }
                 }

@@ -3,6 +3,8 @@
 // (examples/gpt.ipynb cell 2 l.25-36). A view whose last dim is not contiguous but whose
 // second-to-last is gets staged in its memory order and handed to the GEMM with the other operand
 // major, so no transposing copy is ever made.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "workspace.cuh"
 
@@ -66,6 +68,100 @@ int stage_view(Bump& ws, const float* ptr, const int64_t st[4], int64_t b0, int6
     return NNB_OK;
 }
 
+// ---- small batched products on the CUDA cores (fp32 FMA) --------------------------------------------
+// OPT-IN alternative for GPT attention at the notebook's sizes (512 independent 64 x 64 x 64 products per
+// call, gpt cell 2 l.25-36), where a 128-row tensor tile is half padding and every operand needs its own
+// bf16 staging launch: one CTA computes one 64 x 64 output tile of one batch element straight from the
+// strided fp32 views (either operand may be a transposed view), so a call is ONE launch and the result is
+// fp32-exact. C[b] = alpha * A[b] . B[b], A: [M,K] strides (ar, ac), B: [K,N] strides (br, bc).
+struct SmallBmm {
+    const float* A; const float* B; float* C;
+    long long a_s0, a_s1, a_r, a_c, b_s0, b_s1, b_r, b_c;
+    int b1, M, K, N;
+    float alpha;
+};
+
+__global__ void __launch_bounds__(128) small_bmm_kernel(const SmallBmm p) {
+    // 128 threads, 4 x 8 outputs each: per k step 3 LDS.128 feed 32 FMAs, so the FMA pipe (not the
+    // shared-memory port) is the limit
+    constexpr int TM = 64, TN = 64, TK = 32;
+    __shared__ __align__(16) float As[TK][TM + 4];
+    __shared__ __align__(16) float Bs[TK][TN + 4];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;  // tx: 8 column groups of 8, ty: 16 row groups of 4
+    const int bz = blockIdx.z, i0 = bz / p.b1, i1 = bz - i0 * p.b1;
+    const float* A = p.A + i0 * p.a_s0 + i1 * p.a_s1;
+    const float* B = p.B + i0 * p.b_s0 + i1 * p.b_s1;
+    float* C = p.C + (long long)bz * p.M * p.N;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const bool a_k_fast = p.a_c == 1 || p.a_r != 1;   // consecutive threads walk the contiguous dimension
+    const bool b_n_fast = p.b_c == 1 || p.b_r != 1;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < p.K; k0 += TK) {
+#pragma unroll 4
+        for (int i = 0; i < (TM * TK) / 128; ++i) {
+            const int e = tid + i * 128;
+            const int r = a_k_fast ? e / TK : e % TM, kk = a_k_fast ? e % TK : e / TM;
+            As[kk][r] = (m0 + r < p.M && k0 + kk < p.K) ? A[(long long)(m0 + r) * p.a_r + (long long)(k0 + kk) * p.a_c] : 0.f;
+            const int c = b_n_fast ? e % TN : e / TK, kb = b_n_fast ? e / TN : e % TK;
+            Bs[kb][c] = (n0 + c < p.N && k0 + kb < p.K) ? B[(long long)(k0 + kb) * p.b_r + (long long)(n0 + c) * p.b_c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < TK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + ty * 4 + i;
+        if (r >= p.M) continue;
+        float* crow = C + (long long)r * p.N;
+        const int c0 = n0 + tx * 8;
+        if (c0 + 7 < p.N && ((reinterpret_cast<uintptr_t>(crow + c0) & 15) == 0)) {
+            *reinterpret_cast<float4*>(crow + c0) = make_float4(p.alpha * acc[i][0], p.alpha * acc[i][1], p.alpha * acc[i][2], p.alpha * acc[i][3]);
+            *reinterpret_cast<float4*>(crow + c0 + 4) = make_float4(p.alpha * acc[i][4], p.alpha * acc[i][5], p.alpha * acc[i][6], p.alpha * acc[i][7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < p.N) crow[c0 + j] = p.alpha * acc[i][j];
+        }
+    }
+}
+
+// Off by default: measured inside the GPT-small step the tcgen05 path (2 staging launches + a half-padded
+// 128-row tile) still wins, 5.92 vs 6.36 ms per step. nnb_matmul_set_small_path(1) or
+// NNB_MATMUL_SIMT=1 selects the fp32 kernel (exact fp32 products, one launch per call).
+int g_small_path = [] { const char* e = getenv("NNB_MATMUL_SIMT"); return e ? atoi(e) : 0; }();
+
+bool small_bmm_ok(int64_t batch, int64_t M, int64_t K, int64_t N) {
+    return g_small_path && batch >= 16 && M <= 128 && N <= 128 && K <= 128;
+}
+
+// strides {s0, s1, row, col} of the logical [b0,b1,R,C] operand
+int small_bmm(const float* A, const int64_t as[4], const float* B, const int64_t bs[4], float* C, int64_t b0,
+              int64_t b1, int64_t M, int64_t K, int64_t N, float alpha, cudaStream_t stream) {
+    NNB_REQUIRE(b0 * b1 <= 65535, "matmul: more than 65535 batch elements on the small-product path");
+    SmallBmm p{A, B, C, as[0], as[1], as[2], as[3], bs[0], bs[1], bs[2], bs[3], (int)b1, (int)M, (int)K, (int)N, alpha};
+    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64), (unsigned)(b0 * b1));
+    small_bmm_kernel<<<grid, 128, 0, stream>>>(p);
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
 const int64_t* contig_strides(int64_t b1, int64_t R, int64_t C, int64_t out[4]) {
     out[3] = 1; out[2] = C; out[1] = R * C; out[0] = b1 * R * C;
     return out;
@@ -95,6 +191,16 @@ size_t nnb_matmul_workspace_bytes(int64_t b0, int64_t b1, int64_t M, int64_t K, 
     return bytes;
 }
 
+int nnb_matmul_set_small_path(int on) {
+    const int prev = g_small_path;
+    g_small_path = on ? 1 : 0;
+    return prev;
+}
+
+int nnb_matmul_uses_tensor_cores(int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N) {
+    return (small_bmm_ok(b0 * b1, M, K, N) && b0 * b1 <= 65535) ? 0 : 1;
+}
+
 size_t nnb_matmul_staged_bytes(int64_t b0, int64_t b1, int64_t rows, int64_t cols, int prec) {
     if (b0 <= 0 || b1 <= 0 || rows <= 0 || cols <= 0) return 0;
     const int64_t b = b0 * b1;
@@ -109,6 +215,8 @@ int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* 
     NNB_REQUIRE(A && B && C && a_strides && b_strides, "nnb_matmul_forward: null pointer");
     NNB_REQUIRE(b0 > 0 && b1 > 0 && M > 0 && K > 0 && N > 0, "nnb_matmul_forward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_matmul_forward: bad prec");
+    if (small_bmm_ok(b0 * b1, M, K, N) && b0 * b1 <= 65535)
+        return small_bmm(A, a_strides, B, b_strides, C, b0, b1, M, K, N, alpha, stream);
     Bump ws(workspace, workspace_bytes);
     GemmProblem g;
     g.M = M; g.N = N; g.K = K; g.batch = b0 * b1;
@@ -131,10 +239,23 @@ int nnb_matmul_backward(const float* A, const int64_t a_strides[4], const float*
     NNB_REQUIRE(A && B && G && a_strides && b_strides, "nnb_matmul_backward: null pointer");
     NNB_REQUIRE(b0 > 0 && b1 > 0 && M > 0 && K > 0 && N > 0, "nnb_matmul_backward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_matmul_backward: bad prec");
-    Bump ws(workspace, workspace_bytes);
     const int64_t batch = b0 * b1;
     int64_t gst[4];
     contig_strides(b1, M, N, gst);
+    if (small_bmm_ok(batch, M, K, N) && batch <= 65535) {
+        if (dA) {  // dA[M,K] = alpha * G[M,N] . (B[K,N])^T: B^T is the same memory with row/col strides swapped
+            const int64_t bt[4] = {b_strides[0], b_strides[1], b_strides[3], b_strides[2]};
+            int rc = small_bmm(G, gst, B, bt, dA, b0, b1, M, N, K, alpha, stream);
+            if (rc) return rc;
+        }
+        if (dB) {  // dB[K,N] = alpha * (A[M,K])^T . G[M,N]
+            const int64_t at[4] = {a_strides[0], a_strides[1], a_strides[3], a_strides[2]};
+            int rc = small_bmm(A, at, G, gst, dB, b0, b1, K, M, N, alpha, stream);
+            if (rc) return rc;
+        }
+        return NNB_OK;
+    }
+    Bump ws(workspace, workspace_bytes);
     GemmOperand g_red_cols, g_red_rows;
     // G is used as [M, N(reduction)] for dA and as [M(reduction), N] for dB: same staged planes.
     int rc = stage_view(ws, G, gst, b0, b1, M, N, true, prec, stream, &g_red_cols);

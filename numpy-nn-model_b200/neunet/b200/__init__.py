@@ -86,6 +86,8 @@ _SIGNATURES = {
     "nnb_stage_weight": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "nnb_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     "nnb_matmul_staged_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
+    "nnb_matmul_uses_tensor_cores": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64]),
+    "nnb_matmul_set_small_path": (c_int, [c_int]),
     "nnb_matmul_forward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, c_int64,
                                    c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_size_t, c_void_p]),
@@ -405,6 +407,11 @@ def matmul(a, b, alpha=1.0, keep_staged=False):
     prec = _state["prec"]
     ws = _workspace(L.nnb_matmul_workspace_bytes(b0, b1, M, K, N, prec, 0))
     ast = bst = None
+    if keep_staged and not L.nnb_matmul_uses_tensor_cores(b0, b1, M, K, N):
+        keep_staged = False  # fp32 CUDA-core path for small batched products: nothing is staged
+        out_only = True
+    else:
+        out_only = False
     if keep_staged:
         ast = torch.empty(L.nnb_matmul_staged_bytes(b0, b1, M, K, prec), dtype=torch.uint8, device="cuda")
         bst = torch.empty(L.nnb_matmul_staged_bytes(b0, b1, K, N, prec), dtype=torch.uint8, device="cuda")
@@ -413,6 +420,8 @@ def matmul(a, b, alpha=1.0, keep_staged=False):
            "nnb_matmul_forward")
     if keep_staged:
         return out.reshape(out_shape), (ast, bst, prec, tuple(_strides4(a4)), tuple(_strides4(b4)))
+    if out_only:
+        return out.reshape(out_shape), None
     return out.reshape(out_shape)
 
 

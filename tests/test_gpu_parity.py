@@ -546,3 +546,42 @@ def test_matmul_backward_reuses_forward_planes_bit_exactly():
     assert torch.equal(q.grad, da)
     # k's gradient flows back through the transpose: compare in the transposed frame
     assert torch.equal(k.grad, db.permute(0, 1, 3, 2))
+
+
+@pytest.mark.parametrize("batch,M,K,N", [((20,), 70, 33, 100), ((4, 8), 64, 64, 64), ((3, 6), 17, 128, 5)])
+def test_matmul_small_batched_products_fp32_path(batch, M, K, N):
+    """Opt-in fp32 CUDA-core kernel for >= 16 batch elements with M, K, N <= 128, straight from the strided
+    views (nnb_matmul_set_small_path): results equal NumPy fp32 to round-off, forward and backward, for plain,
+    transposed and broadcast operands."""
+    prev = b200.lib().nnb_matmul_set_small_path(1)   # opt-in path (off by default)
+    try:
+        _small_products_case(batch, M, K, N)
+    finally:
+        b200.lib().nnb_matmul_set_small_path(prev)
+    assert b200.lib().nnb_matmul_uses_tensor_cores(int(np.prod(batch)), 1, M, K, N) == (0 if prev else 1)
+
+
+def _small_products_case(batch, M, K, N):
+    assert b200.lib().nnb_matmul_uses_tensor_cores(int(np.prod(batch)), 1, M, K, N) == 0
+    rng = np.random.RandomState(11)
+    a = rng.randn(*batch, M, K).astype(np.float32)
+    bt = rng.randn(*batch, N, K).astype(np.float32)            # used as a transposed view, like k in attention
+    g = rng.randn(*batch, M, N).astype(np.float32)
+    A, BT = dev(a, True), dev(bt, True)
+    nd = len(batch)
+    perm = tuple(range(nd)) + (nd + 1, nd)
+    out = neunet.matmul(A, BT.transpose(*perm))
+    ref = np.matmul(a, np.swapaxes(bt, -1, -2))
+    assert relerr(out.data, ref) < 2e-6
+    out.backward(torch.from_numpy(g).cuda())
+    assert relerr(A.grad, np.matmul(g, bt)) < 2e-6
+    assert relerr(BT.grad, np.swapaxes(np.matmul(np.swapaxes(a, -1, -2), g), -1, -2)) < 2e-6
+    # broadcast right operand: one [K, N] matrix shared by every batch element
+    w = rng.randn(K, N).astype(np.float32)
+    Wt = dev(w, True)
+    A2 = dev(a, True)
+    o2 = neunet.matmul(A2, Wt)
+    assert relerr(o2.data, np.matmul(a, w)) < 2e-6
+    o2.backward(torch.from_numpy(g).cuda())
+    assert relerr(A2.grad, np.matmul(g, w.T)) < 2e-6
+    assert relerr(Wt.grad, np.einsum("bmk,bmn->kn", a.reshape(-1, M, K), g.reshape(-1, M, N))) < 1e-5
