@@ -56,6 +56,9 @@ int nnb_version(void);
 /* Fails with NNB_ERR_UNSUPPORTED unless the current device is compute capability 10.x. */
 int nnb_device_check(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernels this library has launched since the last reset (bench.py's `gpu_launches`). */
+/* Programmatic dependent launch for the library's hot-path kernels (on by default, NNB_PDL=0 in the
+ * environment turns it off): returns the previous setting. Results are identical either way. */
+int nnb_set_pdl(int on);
 uint64_t nnb_launch_count(void);
 void nnb_launch_count_reset(void);
 

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256)
 ce_rows_kernel(const float* __restrict__ logits, const int* __restrict__ targets, long long rows, int C,
                int ignore_index, float* __restrict__ row_loss, float* __restrict__ lse_out) {
     constexpr bool WARP = THREADS == 32;
+    pdl_trigger();
+    pdl_wait();
     const long long row = WARP ? ((long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) : blockIdx.x;
     const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;
     const int stride = WARP ? 32 : THREADS;
@@ -84,6 +86,8 @@ ce_finish_kernel(const float* __restrict__ row_loss, const int* __restrict__ tar
                  int ignore_index, int reduction, float* __restrict__ loss_out, float* __restrict__ inv_denom) {
     __shared__ float ssum[1024];
     __shared__ float scnt[1024];
+    pdl_trigger();
+    pdl_wait();
     float s = 0.f, c = 0.f;
     for (long long i = threadIdx.x; i < rows; i += 1024) {
         s += row_loss[i];
@@ -110,6 +114,8 @@ ce_backward_kernel(const float* __restrict__ logits, const int* __restrict__ tar
                    const float* __restrict__ lse, const float* __restrict__ inv_denom,
                    const float* __restrict__ upstream, int upstream_per_row, long long rows, int C,
                    int ignore_index, float* __restrict__ dlogits, int vec) {
+    pdl_trigger();
+    pdl_wait();
     const long long r = blockIdx.y;
     const int t = targets[r];
     const float* x = logits + r * C;
@@ -159,16 +165,17 @@ int nnb_cross_entropy_forward(const float* logits, const int32_t* targets, int64
     NNB_REQUIRE(reduction == 0 || (loss_out && inv_denom), "nnb_cross_entropy_forward: reduction needs loss_out/inv_denom");
     if (C <= 2048) {
         const int wpb = 8;
-        ce_rows_kernel<32><<<(unsigned)ceil_div(rows, wpb), 32 * wpb, 0, stream>>>(logits, targets, rows, (int)C,
-                                                                                     (int)ignore_index, row_loss, lse);
+        NNB_CUDA_OK(launch_pdl(ce_rows_kernel<32>, dim3((unsigned)ceil_div(rows, wpb)), dim3(32 * wpb), 0, stream, logits,
+                               (const int*)targets, (long long)rows, (int)C, (int)ignore_index, row_loss, lse));
     } else {
-        ce_rows_kernel<256><<<(unsigned)rows, 256, 0, stream>>>(logits, targets, rows, (int)C, (int)ignore_index,
-                                                                row_loss, lse);
+        NNB_CUDA_OK(launch_pdl(ce_rows_kernel<256>, dim3((unsigned)rows), dim3(256), 0, stream, logits, (const int*)targets,
+                               (long long)rows, (int)C, (int)ignore_index, row_loss, lse));
     }
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     if (reduction != 0) {
-        ce_finish_kernel<<<1, 1024, 0, stream>>>(row_loss, targets, rows, (int)ignore_index, reduction, loss_out, inv_denom);
+        NNB_CUDA_OK(launch_pdl(ce_finish_kernel, dim3(1), dim3(1024), 0, stream, (const float*)row_loss, (const int*)targets,
+                               (long long)rows, (int)ignore_index, reduction, loss_out, inv_denom));
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());
     }
@@ -186,9 +193,9 @@ int nnb_cross_entropy_backward(const float* logits, const int32_t* targets, cons
     for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
         const int64_t nr = std::min<int64_t>(65535, rows - r0);
         dim3 grid((unsigned)ceil_div(C, 256 * 16), (unsigned)nr);
-        ce_backward_kernel<<<grid, 256, 0, stream>>>(logits + r0 * C, targets + r0, lse + r0, inv_denom,
-                                                     upstream_per_row ? upstream + r0 : upstream, upstream_per_row, nr,
-                                                     (int)C, (int)ignore_index, dlogits + r0 * C, vec);
+        NNB_CUDA_OK(launch_pdl(ce_backward_kernel, grid, dim3(256), 0, stream, logits + r0 * C, (const int*)(targets + r0),
+                               lse + r0, inv_denom, upstream_per_row ? upstream + r0 : upstream, upstream_per_row,
+                               (long long)nr, (int)C, (int)ignore_index, dlogits + r0 * C, vec));
         count_launch();
     }
     NNB_CUDA_OK(cudaGetLastError());

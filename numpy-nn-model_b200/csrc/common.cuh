@@ -35,6 +35,36 @@ void count_launch(int n = 1);
 
 int num_sms();
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// A training step is a chain of several hundred short dependent kernels; with the
+// programmatic-stream-serialization launch attribute the next kernel's CTAs are scheduled while the current
+// kernel drains (it calls pdl_trigger() at its start), run their prologue, and block in pdl_wait() until the
+// predecessor has completed and flushed. Kernels launched this way must not touch global memory before
+// pdl_wait(). nnb_set_pdl(0) / NNB_PDL=0 turns the attribute off (the device calls are then no-ops).
+bool pdl_enabled();
+int set_pdl(int on);
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
                                                       long long n, uint32_t thresh, float scale,
                                                       uint64_t seed, uint32_t call_id, uint64_t epoch_host,
                                                       const unsigned long long* __restrict__ epoch_dev, int vec) {
+    pdl_trigger();
+    pdl_wait();
     const uint64_t epoch = epoch_dev ? (uint64_t)*epoch_dev : epoch_host;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const long long nvec = (n + 3) >> 2;
@@ -78,8 +80,8 @@ int nnb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uin
     const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     const long long nvec = (n + 3) / 4;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(nvec, 256), (long long)num_sms() * 16));
-    dropout_kernel<<<blocks, 256, 0, stream>>>(x, y, (long long)n, thresh, scale, seed, call_id, epoch,
-                                               reinterpret_cast<const unsigned long long*>(epoch_dev), vec);
+    NNB_CUDA_OK(launch_pdl(dropout_kernel, dim3(blocks), dim3(256), 0, stream, x, y, (long long)n, thresh, scale, seed,
+                           call_id, epoch, reinterpret_cast<const unsigned long long*>(epoch_dev), vec));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;

@@ -35,6 +35,8 @@ __device__ __forceinline__ float warp_max(float v) {
 template <bool BWD>
 __global__ void swish_kernel(const float* __restrict__ x, const float* __restrict__ g,
                              float* __restrict__ y, long long n, float beta, int vec) {
+    pdl_trigger();
+    pdl_wait();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     if (vec) {
@@ -65,6 +67,8 @@ __global__ void swish_kernel(const float* __restrict__ x, const float* __restric
 template <bool BWD>
 __global__ void softmax_rows_kernel(const float* __restrict__ a, const float* __restrict__ g,
                                     float* __restrict__ out, long long rows, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -118,6 +122,8 @@ __global__ void rmsnorm_fwd_kernel(const float* __restrict__ X, const float* __r
                                    const float* __restrict__ b, float* __restrict__ Y,
                                    float* __restrict__ Xstd, float* __restrict__ Xnorm,
                                    long long rows, int cols, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -183,6 +189,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_fused_kernel(
     const float* __restrict__ Xstd, float* __restrict__ dX, float* __restrict__ pw,
     float* __restrict__ pb, long long rows, int cols, int rows_per_block) {
     __shared__ float red[8][NJ4 * 128 + 4];
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(r0 + rows_per_block, rows);
@@ -256,6 +264,8 @@ __global__ void __launch_bounds__(1024) colsum2_reduce_kernel(const float* __res
                                                               int nparts, int cols, float* __restrict__ dw,
                                                               float* __restrict__ db) {
     __shared__ float red[2][32][33];
+    pdl_trigger();
+    pdl_wait();
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     float sw = 0.f, sb = 0.f;
@@ -295,7 +305,8 @@ extern "C" {
 int nnb_swish_forward(const float* x, float* y, int64_t n, float beta, cudaStream_t stream) {
     NNB_REQUIRE(x && y && n > 0, "nnb_swish_forward: bad arguments");
     const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-    swish_kernel<false><<<ew_grid(vec ? (n + 3) / 4 : n, 256), 256, 0, stream>>>(x, nullptr, y, n, beta, vec);
+    NNB_CUDA_OK(launch_pdl(swish_kernel<false>, dim3(ew_grid(vec ? (n + 3) / 4 : n, 256)), dim3(256), 0, stream, x,
+                           (const float*)nullptr, y, (long long)n, beta, vec));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
@@ -306,7 +317,8 @@ int nnb_swish_backward(const float* x, const float* grad, float* dx, int64_t n, 
     NNB_REQUIRE(x && grad && dx && n > 0, "nnb_swish_backward: bad arguments");
     const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad) |
                       reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
-    swish_kernel<true><<<ew_grid(vec ? (n + 3) / 4 : n, 256), 256, 0, stream>>>(x, grad, dx, n, beta, vec);
+    NNB_CUDA_OK(launch_pdl(swish_kernel<true>, dim3(ew_grid(vec ? (n + 3) / 4 : n, 256)), dim3(256), 0, stream, x, grad, dx,
+                           (long long)n, beta, vec));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
@@ -318,7 +330,8 @@ int nnb_softmax_forward(const float* x, float* y, int64_t outer, int64_t n, int6
     NNB_REQUIRE(outer > 0 && n > 0 && inner > 0 && n < (1ll << 31), "nnb_softmax_forward: bad shape");
     if (inner == 1) {
         const long long blocks = ceil_div(outer * 32, 256);
-        softmax_rows_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, nullptr, y, outer, (int)n);
+        NNB_CUDA_OK(launch_pdl(softmax_rows_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, stream, x,
+                               (const float*)nullptr, y, (long long)outer, (int)n));
     } else {
         const long long blocks = ceil_div(outer * inner, 256);
         softmax_strided_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, nullptr, y, outer, (int)n, inner);
@@ -334,7 +347,8 @@ int nnb_softmax_backward(const float* y, const float* grad, float* dx, int64_t o
     NNB_REQUIRE(outer > 0 && n > 0 && inner > 0 && n < (1ll << 31), "nnb_softmax_backward: bad shape");
     if (inner == 1) {
         const long long blocks = ceil_div(outer * 32, 256);
-        softmax_rows_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(y, grad, dx, outer, (int)n);
+        NNB_CUDA_OK(launch_pdl(softmax_rows_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, stream, y, grad, dx,
+                               (long long)outer, (int)n));
     } else {
         const long long blocks = ceil_div(outer * inner, 256);
         softmax_strided_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(y, grad, dx, outer, (int)n, inner);
@@ -349,7 +363,8 @@ int nnb_rmsnorm_forward(const float* X, const float* w, const float* b, float* Y
     NNB_REQUIRE(X && w && Y, "nnb_rmsnorm_forward: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_forward: bad shape");
     const long long blocks = ceil_div(rows * 32, 256);
-    rmsnorm_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, w, b, Y, X_std, X_norm, rows, (int)cols, eps);
+    NNB_CUDA_OK(launch_pdl(rmsnorm_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, X, w, b, Y, X_std, X_norm,
+                           (long long)rows, (int)cols, eps));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
@@ -382,14 +397,18 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
         const int rpb = (int)ceil_div(rows, parts);
         parts = ceil_div(rows, rpb);
         const int nj4 = (int)ceil_div(cols, 128);
-        if (nj4 <= 1) rmsnorm_bwd_fused_kernel<1><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
-        else if (nj4 <= 2) rmsnorm_bwd_fused_kernel<2><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
-        else if (nj4 <= 4) rmsnorm_bwd_fused_kernel<4><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
-        else rmsnorm_bwd_fused_kernel<8><<<(unsigned)parts, 256, 0, stream>>>(gY, X, w, X_std, dX, pw, pb, rows, (int)cols, rpb);
+        const dim3 fg((unsigned)parts), fb(256);
+        const long long rows_ll = rows;
+        const int cols_i = (int)cols;
+        if (nj4 <= 1) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<1>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
+        else if (nj4 <= 2) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<2>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
+        else if (nj4 <= 4) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<4>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
+        else NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<8>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());
         if (dw) {
-            colsum2_reduce_kernel<<<(unsigned)ceil_div(cols, 32), 1024, 0, stream>>>(pw, pb, (int)parts, (int)cols, dw, db);
+            NNB_CUDA_OK(launch_pdl(colsum2_reduce_kernel, dim3((unsigned)ceil_div(cols, 32)), dim3(1024), 0, stream,
+                                   (const float*)pw, (const float*)pb, (int)parts, (int)cols, dw, db));
             count_launch();
             NNB_CUDA_OK(cudaGetLastError());
         }
@@ -406,7 +425,8 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
         const int rpb = (int)ceil_div(rows, parts);
         parts = ceil_div(rows, rpb);
         rmsnorm_bwd_cols_kernel<<<dim3(gx, (unsigned)parts), 128, 0, stream>>>(gY, X, X_std, pw, pb, rows, (int)cols, rpb);
-        colsum2_reduce_kernel<<<(unsigned)ceil_div(cols, 32), 1024, 0, stream>>>(pw, pb, (int)parts, (int)cols, dw, db);
+        NNB_CUDA_OK(launch_pdl(colsum2_reduce_kernel, dim3((unsigned)ceil_div(cols, 32)), dim3(1024), 0, stream,
+                               (const float*)pw, (const float*)pb, (int)parts, (int)cols, dw, db));
         count_launch(2);
         NNB_CUDA_OK(cudaGetLastError());
     }

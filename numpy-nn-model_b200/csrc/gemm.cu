@@ -169,6 +169,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
     if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above (tensor-map prefetch, barrier init, TMEM allocation) overlapped the previous
+    // kernel's tail; operands, bias and outputs may only be touched once it has completed
+    pdl_trigger();
+    pdl_wait();
 
     const int tiles_per_batch = p.num_m * p.num_n;
     const int tiles = tiles_per_batch * p.out_batches;
@@ -451,6 +455,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
 
 // Sum split-K partials and apply the epilogue.
 __global__ void splitk_reduce_kernel(const KArgs p) {
+    pdl_trigger();
+    pdl_wait();
     const long long per = (long long)p.M * p.N;
     const long long total = per * p.out_batches;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -552,13 +558,22 @@ int launch(const GemmMaps& maps, const KArgs& ka, int grid, cudaStream_t stream)
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CG;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (CG == 2) ? 1 : 0;
+    cfg.numAttrs = na;
     NNB_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, maps, ka));
     count_launch();
     return NNB_OK;
@@ -788,7 +803,7 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     if (splits > 1) {
         const int64_t total = g.M * g.N * out_batches;
         const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sms * 8);
-        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ka);
+        NNB_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, ka));
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());
     }

@@ -1,6 +1,7 @@
 // Library-wide plumbing: error string, launch counter, device queries.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -24,6 +25,10 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+static std::atomic<int> g_pdl{[] { const char* e = getenv("NNB_PDL"); return e ? atoi(e) : 1; }()};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+int set_pdl(int on) { return g_pdl.exchange(on ? 1 : 0); }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -63,6 +68,8 @@ int nnb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
                          min);
     return NNB_OK;
 }
+
+int nnb_set_pdl(int on) { return nnb::set_pdl(on); }
 
 uint64_t nnb_launch_count(void) { return nnb::g_launches.load(); }
 void nnb_launch_count_reset(void) { nnb::g_launches.store(0); }

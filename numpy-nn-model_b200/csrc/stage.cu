@@ -40,6 +40,8 @@ struct StageArgs {
 // are reduced over TY in shared memory and written once per block.
 template <bool X3, int OP>
 __global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
+    pdl_trigger();
+    pdl_wait();  // launched with the PDL attribute: nothing above touches global memory
     const int TX = a.tx, TY = (int)blockDim.x / a.tx;
     const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x / TX;
     const long long c = ((long long)blockIdx.x * TX + tx) * 4;
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
 __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const float* __restrict__ partial, int nparts,
                                                              long long cols, float* __restrict__ out) {
     __shared__ float red[32][33];
+    pdl_trigger();
+    pdl_wait();
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * 32 + cx;
     float s = 0.f;
@@ -215,18 +219,18 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     if (colsum) a.partial = colsum_scratch;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
     if (x3) {
-        if (op == STAGE_SWISH_BWD) stage_rows_kernel<true, STAGE_SWISH_BWD><<<grid, threads, 0, stream>>>(a);
-        else stage_rows_kernel<true, STAGE_COPY><<<grid, threads, 0, stream>>>(a);
+        if (op == STAGE_SWISH_BWD) NNB_CUDA_OK(launch_pdl(stage_rows_kernel<true, STAGE_SWISH_BWD>, grid, dim3(threads), 0, stream, a));
+        else NNB_CUDA_OK(launch_pdl(stage_rows_kernel<true, STAGE_COPY>, grid, dim3(threads), 0, stream, a));
     } else {
-        if (op == STAGE_SWISH_BWD) stage_rows_kernel<false, STAGE_SWISH_BWD><<<grid, threads, 0, stream>>>(a);
-        else stage_rows_kernel<false, STAGE_COPY><<<grid, threads, 0, stream>>>(a);
+        if (op == STAGE_SWISH_BWD) NNB_CUDA_OK(launch_pdl(stage_rows_kernel<false, STAGE_SWISH_BWD>, grid, dim3(threads), 0, stream, a));
+        else NNB_CUDA_OK(launch_pdl(stage_rows_kernel<false, STAGE_COPY>, grid, dim3(threads), 0, stream, a));
     }
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     if (colsum) {
         const int nparts = (int)(gy * batch);
-        colsum_reduce_kernel<<<(unsigned)ceil_div(src.cols, 32), 1024, 0, stream>>>(
-            colsum_scratch, nparts, src.cols, colsum);
+        NNB_CUDA_OK(launch_pdl(colsum_reduce_kernel, dim3((unsigned)ceil_div(src.cols, 32)), dim3(1024), 0, stream,
+                               (const float*)colsum_scratch, nparts, (long long)src.cols, colsum));
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());
     }

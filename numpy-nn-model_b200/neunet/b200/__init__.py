@@ -72,6 +72,7 @@ _SIGNATURES = {
     "nnb_last_error": (c_char_p, []),
     "nnb_version": (c_int, []),
     "nnb_device_check": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "nnb_set_pdl": (c_int, [c_int]),
     "nnb_launch_count": (c_uint64, []),
     "nnb_launch_count_reset": (None, []),
     "nnb_linear_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
@@ -687,16 +688,35 @@ class GraphedStep:
             optimizer._fused.set_step(optimizer.t)
         self.optimizer = optimizer
         _state["capture_epoch"] += 1  # invalidates every staged-operand cache made outside this capture
-        self.graph = torch.cuda.CUDAGraph()
         rng_prepare_capture()
-        _rng["graph_used"] = False
-        with torch.cuda.graph(self.graph):
-            self.outputs = fn(*self.inputs)
-        self._uses_rng = _rng["graph_used"]  # dropout inside: bump the device epoch before every replay
+        t_before = optimizer.t if optimizer is not None else 0
+        try:
+            self._capture(fn)
+        except Exception:
+            if optimizer is not None:
+                optimizer.t = t_before
+            # programmatic-dependent-launch edges are the one capture ingredient older drivers may refuse:
+            # retry once with plain stream serialization before giving up
+            prev = lib().nnb_set_pdl(0)
+            if not prev:
+                raise
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            _state["capture_epoch"] += 1
+            self._capture(fn)
         _state["capture_epoch"] += 1
         if optimizer is not None:
             optimizer.t -= 1  # the capture pass itself launched nothing
         self._dev_t = optimizer.t if optimizer is not None else 0  # value of the device step counter
+
+    def _capture(self, fn):
+        self.graph = torch.cuda.CUDAGraph()
+        _rng["graph_used"] = False
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.inputs)
+        self._uses_rng = _rng["graph_used"]  # dropout inside: bump the device epoch before every replay
 
     def load(self, *arrays, non_blocking=True):
         """Copy new values (pinned torch tensors / device tensors / NumPy arrays) into the static inputs."""

@@ -585,3 +585,46 @@ def _small_products_case(batch, M, K, N):
     o2.backward(torch.from_numpy(g).cuda())
     assert relerr(A2.grad, np.matmul(g, w.T)) < 2e-6
     assert relerr(Wt.grad, np.einsum("bmk,bmn->kn", a.reshape(-1, M, K), g.reshape(-1, M, N))) < 1e-5
+
+
+# ---- Conv2d channels-last fast path (Cin, Cout multiples of 8) at ragged geometry and at DDPM size ----------
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,s,pad4,d", [
+    (2, 16, 13, 10, 32, (2, 3), (1, 2), (1, 0, 2, 1), (1, 1)),   # rectangular kernel/stride, asymmetric padding
+    (3, 24, 12, 9, 40, (3, 3), (2, 1), (0, 2, 1, 1), (2, 1)),    # mixed stride + dilation, ragged Ho*Wo
+    (2, 64, 8, 8, 64, (4, 4), (2, 2), (1, 1, 1, 1), (1, 1)),     # DDPM down-sample, Ho*Wo = 16 (scalar NCHW epilogue)
+])
+def test_conv2d_fast_path_ragged_geometry_vs_oracle(B, Cin, H, W, Cout, k, s, pad4, d):
+    rng = np.random.RandomState(Cin + Cout)
+    x = rng.uniform(-1, 1, (B, Cin, H, W)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (Cout, Cin) + k) / np.sqrt(Cin * k[0] * k[1])).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, Cout).astype(np.float32)
+    ref = R.conv2d_forward(x, w, b, s, pad4, d)
+    g = rng.uniform(-1, 1, ref.shape).astype(np.float32)
+    dx, dw, db = R.conv2d_backward(x, w, b, g, s, pad4, d)
+    xd, wd, gd = [torch.from_numpy(a).cuda() for a in (x, w, g)]
+    out = b200.conv2d_forward(xd, wd, torch.from_numpy(b).cuda(), s, pad4, d)
+    gdx, gdw, gdb = b200.conv2d_backward(xd, wd, gd, s, pad4, d)
+    assert relerr(out, ref) < X3
+    assert relerr(gdx, dx) < X3 and relerr(gdw, dw) < X3 and relerr(gdb, db) < 1e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", X3), ("bf16", BF)])
+def test_conv2d_ddpm_size_vs_torch_fp32(prec, tol):
+    """A full-size DDPM layer (256 -> 256 3x3 @16x16 and the 4x4 s2 p1 down-sample, B = 16) against torch's
+    own fp32 convolution (TF32 off) as an independent second oracle (torch reproduces the
+    reference's conv semantics to round-off); the NumPy oracle needs minutes at this size."""
+    b200.set_precision(prec)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for k, s, p in ((3, 1, 1), (4, 2, 1)):
+        x = (torch.rand(16, 256, 16, 16, device="cuda", generator=gen) * 2 - 1).requires_grad_(True)
+        w = ((torch.rand(256, 256, k, k, device="cuda", generator=gen) * 2 - 1) / (256 * k * k) ** 0.5).requires_grad_(True)
+        bias = (torch.rand(256, device="cuda", generator=gen) - 0.5).requires_grad_(True)
+        ref = torch.nn.functional.conv2d(x, w, bias, stride=s, padding=p)
+        g = torch.rand(ref.shape, device="cuda", generator=gen) * 2 - 1
+        ref.backward(g)
+        out = b200.conv2d_forward(x.detach(), w.detach(), bias.detach(), (s, s), (p, p, p, p), (1, 1))
+        dx, dw, db = b200.conv2d_backward(x.detach(), w.detach(), g, (s, s), (p, p, p, p), (1, 1))
+        assert relerr(out, ref.detach()) < tol
+        assert relerr(dx, x.grad) < tol and relerr(dw, w.grad) < tol and relerr(db, bias.grad) < 1e-4
