@@ -661,7 +661,7 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
                     // shared-memory traffic per k-block: TMA fill + UMMA operand reads of the local tiles
                     const double fill = iters * 2.0 * (16384.0 + (c / cgi) * 128.0) / 128.0;
                     const double epi = (c / 32) * ((tma_ok_h && sp == 1) ? 160.0 : 1300.0) + 300.0;
-                    double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0 + (cgi == 2 ? 800.0 : 0.0);
+                    double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0 + (cgi == 2 ? 2000.0 : 0.0);
                     if (sp > 1) {
                         const double out_bytes = (double)g.M * g.N * out_batches * 4.0;
                         cyc += (2.0 * sp + 1.0) * out_bytes / 3400.0 + 7000.0;  // partial traffic + the dependent finishing launch (measured: profiles/r1_linear_ladder.md, wgrad sweep)

@@ -165,3 +165,39 @@ def test_conv_classifier_gpu(_gpu):
 @pytest.mark.gpu
 def test_unet_gpu(_gpu):
     _unet("cuda", 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-4), ("bf16", 2e-2)])
+def test_gpt_small_full_size_step_vs_oracle(_gpu, prec, tol):
+    """BASELINE configs[3] at FULL model size (V=15000, d=512, 8 heads, d_ff=2048, 8 layers, T=64; 4 sequences
+    = the notebook's batch) on the device against the oracle's hand-written forward/backward of the same
+    architecture (oracle/gpt_numpy.py, pinned to the reference by tests/golden/model_gpt.npz): loss, logits and
+    every parameter gradient. eval mode (dropout is RNG-dependent). bf16x3 must meet the fp32-faithful bar;
+    plain bf16 (the bench's throughput mode) is reported against a looser, stated bound."""
+    from neunet import b200
+    from oracle import gpt_numpy as G
+    b200.set_precision(prec)
+    V, d, h, ff, L, T, B = 15000, 512, 8, 2048, 8, 64, 4
+    np.random.seed(0)
+    model = M.build_gpt(neunet, nn, vocab=V, d_model=d, n_heads=h, d_ff=ff, n_layers=L, pad_idx=0, device="cuda")
+    model.eval()
+    ps = [_host(p.data).copy() for p in model.parameters()]
+    batch = np.random.RandomState(1).randint(3, V, (B, T + 1))
+    loss_ref, logits_ref, grads_ref = G.step_grads(ps, batch, h)
+    opt = Adam(model.parameters(), lr=1.5e-4, betas=(0.9, 0.98), eps=1e-9)
+    opt.zero_grad()
+    loss, logits = M.gpt_train_step(neunet, nn, model, opt, batch)
+    np.testing.assert_allclose(float(loss.item()), float(loss_ref), rtol=max(tol, 1e-5))
+    assert _rel(logits.data, logits_ref) < tol
+    gmax = max(np.abs(g).max() for g in grads_ref if g is not None)
+    checked = 0
+    for p, g in zip(model.parameters(), grads_ref):
+        if g is None:
+            assert p.grad is None
+            continue
+        if np.abs(g).max() < 1e-6 * gmax:
+            continue
+        assert _rel(p.grad, g) < tol * 5, f"grad of a {tuple(p.shape)} parameter"
+        checked += 1
+    assert checked >= 100
