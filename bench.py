@@ -39,6 +39,8 @@ for p in (os.path.join(ROOT, "numpy-nn-model_b200"), ROOT):
 
 import numpy as np  # noqa: E402
 
+# N > 1: persistent GEMM grids leave this many SMs' worth of room for NCCL (0 = use every SM); see DESIGN.md section 6
+DEFAULT_DP_GEMM_SMS = 0
 MLP = dict(name="mlp_784_128_10", d_in=784, d_hid=128, d_out=10, batch=4096, lr=1e-3)
 # examples/gpt.ipynb cells 8, 11: V=15000, d=512, 8 heads, d_ff=2048, 8 layers, Adam(1.5e-4, (0.9, 0.98), 1e-9);
 # synthetic tokens in [3, V) (ids 0/1/2 are pad/sos/eos), T=64, 64 sequences per GPU
@@ -362,6 +364,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     b200.require_device()
     b200.set_precision("bf16")
+    gemm_sms = args.gemm_sms if args.gemm_sms >= 0 else DEFAULT_DP_GEMM_SMS
+    if world > 1 and gemm_sms > 0:
+        b200.lib().nnb_set_sm_budget(int(gemm_sms))
     torch.manual_seed(1234 + rank)
     pk = peaks()
     _, label = workload_label(args)
@@ -410,6 +415,7 @@ def run_ours(args):
                 bucket = GradBucket(params)
                 for p_ in params:
                     p_._grad_ready = None
+                    p_._grad_buffer = None
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if wl.flush_l2 else None  # 2x L2
 
@@ -507,6 +513,7 @@ def run_ours(args):
             "config": {"workload": label, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": ("flushed (256 MiB write) between timed steps" if flush is not None else
                               "not flushed: per-step working set (weights + Adam state 0.65 GB, activations > 2 GB) exceeds the 126 MB L2"),
+                       "gemm_sms": (gemm_sms if (world > 1 and gemm_sms > 0) else "all"),
                        "grad_allreduce": (None if bucket is None else
                                           ("chunked (32 MB), overlapped with backward" if overlap else "one flat all-reduce after backward")),
                        "step_execution": "cuda-graph replay of the public-API step" if graphed is not None else "eager",
@@ -544,6 +551,8 @@ def main():
     ap.add_argument("--workload", default="gpt", choices=["mlp", "gpt"],
                     help="gpt = BASELINE.json configs[3], the config the 1/2/4/8-GPU samples/s metric is quoted on (default); "
                          "mlp = configs[1]")
+    ap.add_argument("--gemm-sms", type=int, default=-1,
+                    help="N>1: SMs the persistent GEMM grids are sized for (rest is left to NCCL's CTAs); 0 = all, -1 = default")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one flat all-reduce after backward instead of overlapped chunks")
     ap.add_argument("--no-graph", action="store_true", help="time the eager public-API step instead of a CUDA-graph replay")
     args = ap.parse_args()

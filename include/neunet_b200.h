@@ -59,6 +59,9 @@ int nnb_device_check(int* sm_count, int* cc_major, int* cc_minor);
 /* Programmatic dependent launch for the library's hot-path kernels (on by default, NNB_PDL=0 in the
  * environment turns it off): returns the previous setting. Results are identical either way. */
 int nnb_set_pdl(int on);
+/* Size persistent grids (GEMM) for at most `sms` SMs (0 = all): leaves room for NCCL's CTAs during
+ * data-parallel training. Returns the previous budget. NNB_SM_BUDGET in the environment sets the default. */
+int nnb_set_sm_budget(int sms);
 uint64_t nnb_launch_count(void);
 void nnb_launch_count_reset(void);
 

@@ -33,7 +33,8 @@ int fail(int code, const char* fmt, ...);
 // Kernel-launch accounting (bench.py reports `gpu_launches`).
 void count_launch(int n = 1);
 
-int num_sms();
+int num_sms();            // SMs the library sizes its grids for (device count, or the budget below)
+int set_sm_budget(int n);  // 0 = all SMs
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------
 // A training step is a chain of several hundred short dependent kernels; with the

@@ -1,4 +1,5 @@
 // Library-wide plumbing: error string, launch counter, device queries.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
@@ -32,7 +33,12 @@ int set_pdl(int on) { return g_pdl.exchange(on ? 1 : 0); }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-int num_sms() {
+// SM budget for persistent grids: data-parallel training wants a few SMs left for NCCL's CTAs, which cannot
+// share an SM with a GEMM CTA (230 KB of dynamic shared memory) and would otherwise only run between GEMMs.
+static std::atomic<int> g_sm_budget{[] { const char* e = getenv("NNB_SM_BUDGET"); return e ? atoi(e) : 0; }()};
+int set_sm_budget(int n) { return g_sm_budget.exchange(n > 0 ? n : 0); }
+
+static int device_sms() {
     static int sms[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -43,6 +49,11 @@ int num_sms() {
         sms[dev] = v;
     }
     return sms[dev];
+}
+
+int num_sms() {
+    const int all = device_sms(), b = g_sm_budget.load(std::memory_order_relaxed);
+    return (b > 0 && b < all) ? std::max(b, 2) : all;
 }
 
 }  // namespace nnb
@@ -70,6 +81,7 @@ int nnb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int nnb_set_pdl(int on) { return nnb::set_pdl(on); }
+int nnb_set_sm_budget(int sms) { return nnb::set_sm_budget(sms); }
 
 uint64_t nnb_launch_count(void) { return nnb::g_launches.load(); }
 void nnb_launch_count_reset(void) { nnb::g_launches.store(0); }

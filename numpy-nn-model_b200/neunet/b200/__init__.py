@@ -73,6 +73,7 @@ _SIGNATURES = {
     "nnb_version": (c_int, []),
     "nnb_device_check": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "nnb_set_pdl": (c_int, [c_int]),
+    "nnb_set_sm_budget": (c_int, [c_int]),
     "nnb_launch_count": (c_uint64, []),
     "nnb_launch_count_reset": (None, []),
     "nnb_linear_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
@@ -309,9 +310,16 @@ def linear_forward(x, w, bias=None, act=ACT_NONE, beta=1.0, save_z=False, owner=
     return out, z, xst
 
 
+def _usable_out(buf, shape):
+    return (buf is not None and isinstance(buf, torch.Tensor) and buf.is_cuda and buf.dtype == torch.float32
+            and buf.is_contiguous() and tuple(buf.shape) == tuple(shape))
+
+
 def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, need_db=True, owner=None,
-                    x_staged=None):
-    """Returns (dX like x, dW (N,K), db (1,N)) -- dX / db None when not requested."""
+                    x_staged=None, dw_out=None, db_out=None):
+    """Returns (dX like x, dW (N,K), db (1,N)) -- dX / db None when not requested. dw_out / db_out: optional
+    caller-owned destinations (e.g. slices of the data-parallel gradient bucket) the GEMM / column sums write
+    into directly instead of fresh tensors."""
     require_device()
     L = lib()
     N, K = w.shape
@@ -320,8 +328,10 @@ def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, ne
     g2 = _f32c(grad).reshape(-1, N)
     w = _f32c(w)
     dx = torch.empty((M, K), dtype=torch.float32, device="cuda") if need_dx else None
-    dw = torch.empty((N, K), dtype=torch.float32, device="cuda")
-    db = torch.empty((1, N), dtype=torch.float32, device="cuda") if need_db else None
+    dw = dw_out if _usable_out(dw_out, (N, K)) else torch.empty((N, K), dtype=torch.float32, device="cuda")
+    db = None
+    if need_db:
+        db = db_out if _usable_out(db_out, (1, N)) else torch.empty((1, N), dtype=torch.float32, device="cuda")
     z2 = _f32c(z).reshape(-1, N) if z is not None else None
     prec = _state["prec"]
     wst = _staged_weight(owner, w, N, K) if need_dx else None

@@ -85,9 +85,12 @@ class GradBucket:
             return live
         if self.device == "cuda":
             import torch
-            srcs = [self.params[i].grad.reshape(-1) for i in live]
-            dsts = [self._slice(i) for i in live]
-            torch._foreach_copy_(dsts, srcs)
+            # gradients a layer already wrote into its bucket slice (Parameter._grad_buffer) need no copy
+            todo = [i for i in live if self.params[i].grad.data_ptr() != self._slice(i).data_ptr()]
+            if todo:
+                srcs = [self.params[i].grad.reshape(-1) for i in todo]
+                dsts = [self._slice(i) for i in todo]
+                torch._foreach_copy_(dsts, srcs)
         else:
             for i in live:
                 self._slice(i)[...] = np.asarray(self.params[i].grad, dtype=np.float32).reshape(-1)
@@ -135,6 +138,9 @@ class GradBucket:
                 self._chunk_of[i] = c
         for i, p in enumerate(self.params):
             p._grad_ready = self._on_ready if i in self._chunk_of else None
+            # layers that can take an output destination write their gradient straight into the bucket
+            p._grad_buffer = (self._slice(i).reshape(tuple(p.shape))
+                              if (i in self._chunk_of and self.device == "cuda") else None)
         self._reset_step()
 
     def _reset_step(self):

@@ -28,9 +28,13 @@ class _LinearTensor(Tensor):
 def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, x_staged, grad):
     if X.device == "cuda":
         from ... import b200
+        # data-parallel training: the first (normally only) gradient contribution of a parameter is written
+        # straight into its slice of the all-reduce bucket (neunet.distributed.GradBucket.overlap_backward)
+        dw_out = getattr(weight, "_grad_buffer", None) if weight.grad is None else None
+        db_out = getattr(bias, "_grad_buffer", None) if (bias is not None and bias.grad is None) else None
         dx, dw, db = b200.linear_backward(X.data, weight.data, grad, z=Z, act=act, beta=beta,
                                           need_dx=X.requires_grad, need_db=bias is not None, owner=weight,
-                                          x_staged=x_staged)
+                                          x_staged=x_staged, dw_out=dw_out, db_out=db_out)
         if dx is not None:
             X.apply_grad(dx)
         weight.apply_grad(dw)
