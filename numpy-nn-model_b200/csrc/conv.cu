@@ -211,14 +211,13 @@ template <bool X3>
 __global__ void stage_weight_klc_kernel(const float* __restrict__ W, int Cout, int Cin, int khw, int flip,
                                         long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo) {
     const long long total = (long long)Cout * Cin * khw;
-    const int R = flip ? Cin : Cout, Cc = flip ? Cout : Cin;  // staged rows / channel (fastest) dimension
+    const int Cc = flip ? Cout : Cin;  // channel (fastest) dimension of the staged rows
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % Cc);
         const long long t = idx / Cc;
         const int tap = (int)(t % khw);
         const int r = (int)(t / khw);
-        (void)R;
         const float v = flip ? W[((long long)c * Cin + r) * khw + (khw - 1 - tap)]
                              : W[((long long)r * Cin + c) * khw + tap];
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
