@@ -161,7 +161,7 @@ def run_reference(args):
     if args.workload == "gpt":
         steps = min(steps, 5)
         r = cpu_gpt_run(cfg, steps=steps, warmup=1, batch=8)
-        sample = f"{steps} steps of 8 sequences x T={cfg['seq']} (oracle/gpt_numpy.py; cost is linear in batch)"
+        sample = f"{steps} steps of 8 sequences x T={cfg['seq']} (oracle/gpt_numpy.py, dropout off -- the CPU arm does slightly LESS work than the GPU arm; cost is linear in batch)"
     else:
         r = cpu_mlp_run(cfg, steps=steps, warmup=max(args.warmup, 1))
         sample = f"{steps} steps of batch {cfg['batch']} (oracle/restated.py)"
@@ -341,7 +341,7 @@ class GptWorkload:
 
     def cpu(self):
         r = cpu_gpt_run(self.cfg, steps=3, warmup=1, batch=8)
-        return r, f"{r['steps']} steps of 8 sequences x T={self.cfg['seq']} (oracle/gpt_numpy.py; cost is linear in batch)"
+        return r, f"{r['steps']} steps of 8 sequences x T={self.cfg['seq']} (oracle/gpt_numpy.py, dropout off -- the CPU arm does slightly LESS work than the GPU arm; cost is linear in batch)"
 
 
 def run_ours(args):
