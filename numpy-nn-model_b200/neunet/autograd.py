@@ -508,8 +508,16 @@ class Tensor:
             if a.requires_grad:
                 # assignment, not accumulation: duplicate indices keep the last write (autograd.py:909-910)
                 full = xp.zeros_like(a.data)
-                if a.device == "cuda" and _be.is_device_array(index) and index.dtype == _be.torch.int64:
-                    _assign_last_wins(full, index, grad)
+                rows = None
+                if a.device == "cuda":
+                    # an integer index tensor over the first axis, bare or followed only by new axes
+                    # (ddpm cell 4: coef[timesteps, None, None, None]): a device index_put with duplicate
+                    # indices is non-deterministic, the reference keeps the LAST write
+                    first = index[0] if (isinstance(index, tuple) and index and all(i is None for i in index[1:])) else index
+                    if _be.is_device_array(first) and first.dtype == _be.torch.int64:
+                        rows = first
+                if rows is not None:
+                    _assign_last_wins(full, rows, grad)
                 else:
                     full[index] = grad
                 a.apply_grad(full)

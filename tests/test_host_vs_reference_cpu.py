@@ -22,17 +22,21 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "neunet")), 
 CASES = r'''
 import numpy as np
 
-def run_cases(neunet, nn):
-    T = neunet.tensor
+def run_cases(neunet, nn, device="cpu"):
+    def T(data, **kw):
+        return neunet.tensor(data, device=device, **kw)
+
+    def host(a):
+        return a if isinstance(a, np.ndarray) else a.detach().cpu().numpy()
     rng = np.random.RandomState(7)
     out = {}
 
     def rec(name, result, *leaves, grad=None):
         g = rng.standard_normal(result.shape).astype(np.float32) if grad is None else grad
         result.backward(g)
-        out[name + ".out"] = np.asarray(result.data, dtype=np.float32)
+        out[name + ".out"] = np.asarray(host(result.data), dtype=np.float32)
         for i, l in enumerate(leaves):
-            out[f"{name}.g{i}"] = np.asarray(l.grad, dtype=np.float32)
+            out[f"{name}.g{i}"] = np.asarray(host(l.grad), dtype=np.float32)
 
     def leaf(*shape, lo=None):
         a = rng.standard_normal(shape).astype(np.float32)
@@ -84,33 +88,33 @@ def run_cases(neunet, nn):
     rec("ce_ignore", nn.CrossEntropyLoss(ignore_index=0)(a, labels), a)
     # 8. non-hot-path layers
     np.random.seed(3)
-    bn = nn.BatchNorm2d(3)
+    bn = nn.BatchNorm2d(3).to(device)
     a = leaf(4, 3, 5, 5)
     rec("batchnorm", bn(a), a, bn.weight, bn.bias)
-    out["batchnorm.running_mean"] = np.asarray(bn.running_mean.data, dtype=np.float32)
-    out["batchnorm.running_var"] = np.asarray(bn.running_var.data, dtype=np.float32)
+    out["batchnorm.running_mean"] = np.asarray(host(bn.running_mean.data), dtype=np.float32)
+    out["batchnorm.running_var"] = np.asarray(host(bn.running_var.data), dtype=np.float32)
     bn.eval()
     a = leaf(2, 3, 5, 5)
     rec("batchnorm_eval", bn(a), a)
     a = leaf(2, 3, 6, 6)
     rec("maxpool", nn.MaxPool2d(2, 2)(a), a)
-    emb = nn.Embedding(9, 4)
+    emb = nn.Embedding(9, 4).to(device)
     ids = T(np.array([[1, 2, 2], [8, 1, 0]]), dtype=np.int32)
     rec("embedding", emb(ids) * 2.0, emb.weight)
-    rms = nn.RMSNorm(6)
+    rms = nn.RMSNorm(6).to(device)
     a = leaf(2, 5, 6)
     rec("rmsnorm", rms(a), a, rms.weight)
-    ct = nn.ConvTranspose2d(3, 4, 4, 2, 1)
+    ct = nn.ConvTranspose2d(3, 4, 4, 2, 1).to(device)
     a = leaf(2, 3, 4, 4)
     rec("convtranspose", ct(a), a, ct.weight, ct.bias)
-    cv = nn.Conv2d(3, 5, 3, 2, 1)
+    cv = nn.Conv2d(3, 5, 3, 2, 1).to(device)
     a = leaf(2, 3, 7, 7)
     rec("conv_s2", cv(a), a, cv.weight, cv.bias)
     drop = nn.Dropout(0.3)
     drop.eval()
     a = leaf(3, 3)
     rec("dropout_eval", drop(a) * 2, a)
-    lin = nn.Linear(6, 5)
+    lin = nn.Linear(6, 5).to(device)
     a = leaf(2, 3, 6)
     rec("linear3d", lin(a), a, lin.weight, lin.bias)
     return out
