@@ -39,6 +39,38 @@ for p in (os.path.join(ROOT, "numpy-nn-model_b200"), ROOT):
 
 import numpy as np  # noqa: E402
 
+_T0 = time.perf_counter()
+
+
+def hb(phase):
+    """Per-phase heartbeat: a hang then leaves its last phase in the log tail (stderr; every rank also appends to
+    $BENCH_HB_DIR/hb_r<rank>.log when that directory is set)."""
+    rank = int(os.environ.get("RANK", "0"))
+    msg = f"[bench r{rank} +{time.perf_counter() - _T0:6.1f}s] {phase}"
+    if rank == 0:
+        print(msg, file=sys.stderr, flush=True)
+    d = os.environ.get("BENCH_HB_DIR")
+    if d:
+        try:
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, f"hb_r{rank}.log"), "a") as f:
+                f.write(msg + "\n")
+        except OSError:
+            pass
+
+
+def arm_watchdog(seconds):
+    """A hung collective must end the run with stacks on stderr, not sit until the driver's limit: SIGTERM dumps every
+    thread's stack; after `seconds` the process dumps them itself and exits non-zero."""
+    import faulthandler
+    import signal
+    try:
+        faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
+    except (AttributeError, ValueError):
+        pass
+    if seconds > 0:
+        faulthandler.dump_traceback_later(seconds, exit=True)
+
 # N > 1: persistent GEMM grids leave this many SMs' worth of room for NCCL (0 = use every SM); see DESIGN.md section 6
 DEFAULT_DP_GEMM_SMS = 0
 MLP = dict(name="mlp_784_128_10", d_in=784, d_hid=128, d_out=10, batch=4096, lr=1e-3)
@@ -359,9 +391,13 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (our arm) needs a B200; there is no CPU fallback. Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local)
+    arm_watchdog(args.watchdog)
+    hb(f"init (world {world})")
     if world > 1:
+        import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a lost rank / mismatched collective aborts after 2 minutes instead of spinning forever
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     b200.require_device()
     b200.set_precision("bf16")
     gemm_sms = args.gemm_sms if args.gemm_sms >= 0 else DEFAULT_DP_GEMM_SMS
@@ -390,17 +426,28 @@ def run_ours(args):
     # ---- warm-up (eager) then capture the whole step as a CUDA graph ------------------------------
     W = max(args.warmup, 3)
     overlap = bucket is not None and not args.no_overlap
+    hb("eager warm-up")
     for i in range(W):
         train_step(*wl.inputs)
         if overlap and i == 0:
             bucket.overlap_backward()  # live set known after one step: hook the chunked, overlapped all-reduce
     torch.cuda.synchronize()
+
+    def all_ranks_ok(ok):
+        """Every decision that changes the collective schedule is taken by ALL ranks together (a rank-local `except`
+        that switched one rank to another all-reduce pattern would deadlock the others)."""
+        if world == 1:
+            return bool(ok)
+        f = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
+
     graphed, graph_err = None, None
     if not args.no_graph:
         for attempt in range(2):
+            hb(f"graph capture (attempt {attempt}, overlap={overlap})")
             try:
-                graphed = b200.GraphedStep(train_step, wl.inputs, optimizer=opt, warmup=2)
-                break
+                graphed = b200.GraphedStep(train_step, wl.inputs, optimizer=opt, warmup=2, pdl_retry=(world == 1))
             except Exception as e:  # report, never hide
                 graph_err = f"{type(e).__name__}: {e}"[:300]
                 graphed = None
@@ -408,14 +455,20 @@ def run_ours(args):
                     torch.cuda.synchronize()
                 except Exception:
                     pass
-                if not overlap:
-                    break
-                # retry the capture once with the plain end-of-backward all-reduce
-                overlap = False
-                bucket = GradBucket(params)
-                for p_ in params:
-                    p_._grad_ready = None
-                    p_._grad_buffer = None
+            if all_ranks_ok(graphed is not None):
+                break
+            if graph_err is None:
+                graph_err = "capture failed on another rank"
+            graphed = None
+            hb(f"capture failed somewhere ({graph_err}); all ranks fall back together")
+            if not overlap:
+                break
+            # retry the capture once, on every rank, with the plain end-of-backward all-reduce
+            overlap = False
+            bucket = GradBucket(params)
+            for p_ in params:
+                p_._grad_ready = None
+                p_._grad_buffer = None
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if wl.flush_l2 else None  # 2x L2
 
@@ -427,11 +480,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    hb("graph warm-up" if graphed is not None else "eager warm-up 2")
     for _ in range(W):
         if flush is not None:
             flush.zero_()
         one_step()
     barrier()
+    hb("timed region")
 
     # ---- timed: K steps, each bracketed by CUDA events, L2 flushed in between ---------------------
     K = args.steps
@@ -467,6 +522,7 @@ def run_ours(args):
     dev_s = float(t.item())
     value = B * world * K / dev_s
 
+    hb("e2e")
     # ---- e2e: host batches through the public API, H2D + D2H inside the timed region --------------
     n_host = len(wl.host)
 
@@ -496,6 +552,7 @@ def run_ours(args):
     h2d = sum(h.numel() * h.element_size() for h in wl.host[0])
     d2h = 4
 
+    hb("roofline probes")
     try:
         roof = wl.roofline(pk, b200)
     except Exception as e:  # a failed probe must not lose the step measurements above
@@ -503,6 +560,7 @@ def run_ours(args):
                 "error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
+        hb("cpu baseline")
         use_all_host_threads()
         cpu, cpu_sample = wl.cpu()
         blas, cores = host_threads()
@@ -554,6 +612,8 @@ def main():
     ap.add_argument("--gemm-sms", type=int, default=-1,
                     help="N>1: SMs the persistent GEMM grids are sized for (rest is left to NCCL's CTAs); 0 = all, -1 = default")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one flat all-reduce after backward instead of overlapped chunks")
+    ap.add_argument("--watchdog", type=int, default=600,
+                    help="seconds after which a still-running bench dumps all thread stacks and exits non-zero (0 = off)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager public-API step instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

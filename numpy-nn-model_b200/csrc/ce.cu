@@ -75,8 +75,12 @@ ce_rows_kernel(const float* __restrict__ logits, const int* __restrict__ targets
     if (lane == 0) {
         const float lse = m + logf(s);
         lse_out[row] = lse;
-        const int t = targets[row];
-        row_loss[row] = (t == ignore_index) ? 0.f : (lse - x[t]);   // -log_softmax[target]
+        // targets are range-checked: negative labels wrap like NumPy's x[arange, t]; anything else outside [0, C)
+        // (the reference raises IndexError, losses.py:107) poisons the row with NaN instead of reading out of bounds
+        int t = targets[row];
+        const bool ignored = t == ignore_index;  // decided on the raw label, like `y != ignore_index` (losses.py:104)
+        if (!ignored && t < 0 && t >= -C) t += C;
+        row_loss[row] = ignored ? 0.f : ((t >= 0 && t < C) ? (lse - x[t]) : __int_as_float(0x7fc00000));   // -log_softmax[target]
     }
 }
 
@@ -117,17 +121,20 @@ ce_backward_kernel(const float* __restrict__ logits, const int* __restrict__ tar
     pdl_trigger();
     pdl_wait();
     const long long r = blockIdx.y;
-    const int t = targets[r];
+    int t = targets[r];
+    const bool ignored = t == ignore_index;
+    if (!ignored && t < 0 && t >= -C) t += C;  // NumPy wrap, as in the forward kernel
     const float* x = logits + r * C;
     float* d = dlogits + r * C;
     const int c0 = blockIdx.x * (256 * 4 * 4);
     const int c1 = min(c0 + 256 * 4 * 4, C);
-    if (t == ignore_index) {
+    if (ignored) {
         for (int c = c0 + threadIdx.x; c < c1; c += 256) d[c] = 0.f;
         return;
     }
     const float l = lse[r];
-    const float sc = (inv_denom ? *inv_denom : 1.0f) * (upstream_per_row ? upstream[r] : upstream[0]);
+    float sc = (inv_denom ? *inv_denom : 1.0f) * (upstream_per_row ? upstream[r] : upstream[0]);
+    if (t < 0 || t >= C) sc = __int_as_float(0x7fc00000);  // out-of-range label: NaN row, matching the poisoned loss
     if (vec) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {

@@ -683,7 +683,9 @@ class GraphedStep:
     have taken their first eager step during warm-up) before capture.
     """
 
-    def __init__(self, fn, inputs, optimizer=None, warmup=3):
+    def __init__(self, fn, inputs, optimizer=None, warmup=3, pdl_retry=True):
+        """pdl_retry=False: a failed capture raises at once (multi-rank callers must agree on any retry
+        collectively -- see bench.py -- because `fn` contains collectives)."""
         require_device()
         self.inputs = list(inputs)
         self.fn = fn
@@ -707,6 +709,8 @@ class GraphedStep:
                 optimizer.t = t_before
             # programmatic-dependent-launch edges are the one capture ingredient older drivers may refuse:
             # retry once with plain stream serialization before giving up
+            if not pdl_retry:
+                raise
             prev = lib().nnb_set_pdl(0)
             if not prev:
                 raise

@@ -60,6 +60,7 @@ class GradBucket:
         self._pending = []       # per chunk: gradients still missing this step
         self._launched = []      # per chunk: async work handle (or True) once issued this step
         self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._defer = 0          # > 0 inside `accumulate()`: ready-hooks do not launch anything
 
     def _slice(self, i):
         return self.flat[int(self.offsets[i]): int(self.offsets[i + 1])]
@@ -148,11 +149,34 @@ class GradBucket:
             self._pending = [len(m) for m in self._chunks]
             self._launched = [None] * len(self._chunks)
 
+    def accumulate(self):
+        """Context manager for steps that call ``backward()`` MORE THAN ONCE before the optimizer (gradient
+        accumulation, GAN-style real/fake losses): chunks are not launched from the ready-hooks, so every backward
+        accumulates into ``param.grad`` as usual and ``all_reduce()`` reduces everything afterwards.
+        Without it an overlapped chunk is reduced as soon as the FIRST backward has produced it; a second
+        backward touching the same parameters raises instead of silently dropping its gradient."""
+        bucket = self
+
+        class _Ctx:
+            def __enter__(self):
+                bucket._defer += 1
+                return bucket
+
+            def __exit__(self, *exc):
+                bucket._defer -= 1
+
+        return _Ctx()
+
     def _on_ready(self, param):
         i = self._index.get(id(param))
         c = self._chunk_of.get(i)
-        if c is None or self._launched[c] is not None:
+        if c is None or self._defer:
             return
+        if self._launched[c] is not None:
+            raise RuntimeError(
+                "GradBucket.overlap_backward(): a second backward() reached a parameter whose gradient chunk is "
+                "already being all-reduced. Overlap mode supports one backward() per optimizer step; wrap steps "
+                "with several backward() calls in `with bucket.accumulate():` (reduces after the last one).")
         self._pending[c] -= 1
         if self._pending[c] == 0:
             members = self._chunks[c]
