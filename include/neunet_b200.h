@@ -163,6 +163,21 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
  * RMSNorm: RMSNormForward/Backward (experimental/rmsnorm/rmsnorm.cu:116-140, 282-308),
  *        semantics neunet/nn/layers/rmsnorm.py:39-94. dw/db are full column sums over rows.
  */
+/* Fused forms (north_star: "fused with the bias/Swish/RMSNorm/Softmax epilogues"):
+ * nnb_rmsnorm_forward_fused: S = X (+ dropout(A) when A != NULL, written to S), Y = rmsnorm(S) * w (+ b), X_std,
+ *        and optionally the bf16 planes of Y for the next nnb_linear_forward_staged (RMSNorm as the Linear's
+ *        prologue: the GEMM operand is produced by the norm itself). cols <= 1024, cols % 4 == 0 (8 with planes),
+ *        else NNB_ERR_UNSUPPORTED (callers then use the plain entry points).
+ * nnb_rmsnorm_backward_acc: like nnb_rmsnorm_backward, dX = dX_add + d/dX when dX_add != NULL (the residual
+ *        branch's gradient is accumulated in the same pass instead of a separate add, autograd.py:85-93). */
+int nnb_rmsnorm_forward_fused(const float* X, const float* A, float p, uint64_t seed, uint32_t call_id,
+                              uint64_t epoch, const uint64_t* epoch_dev, float* S, const float* w, const float* b,
+                              float* Y, float* X_std, void* Y_staged_out, int prec, int64_t rows, int64_t cols,
+                              float eps, cudaStream_t stream);
+int nnb_rmsnorm_backward_acc(const float* gY, const float* X, const float* w, const float* X_std,
+                             const float* X_norm, const float* dX_add, float* dX, float* dw, float* db,
+                             int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream);
 int nnb_swish_forward(const float* x, float* y, int64_t n, float beta, cudaStream_t stream);
 int nnb_swish_backward(const float* x, const float* grad, float* dx, int64_t n, float beta,
                        cudaStream_t stream);
@@ -189,6 +204,36 @@ int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bi
                           int rounds, float* us_per_launch, int* launches_per_gemm,
                           cudaStream_t stream);
 
+/* ---- Fused attention for short sequences (row N4 of SURVEY.md 8f) -------------------------------
+ * examples/gpt.ipynb cell 2 l.25-40 as ONE kernel per direction:
+ *   scores = q . kT / scale; scores = where(mask, fill, scores); p = softmax(scores, -1);
+ *   attn = dropout(p); out = attn . v
+ * replacing two Tensor.matmul (neunet/autograd.py:192-230), a division, where (autograd.py:658-684),
+ * nn.Softmax (activations.py:437-459) and nn.Dropout (layers/dropout.py:17-46). fp32 arithmetic on the CUDA
+ * cores (exact like the reference; per head the products are <= 64 x 64 x 64).
+ * q: logical (B,H,Tq,D), kT: logical (B,H,D,Tk), v: logical (B,H,Tk,D), dO: logical (B,H,Tq,D), each with four
+ * element strides (any layout). mask (nullable) is described by mask_kind: 1 = float tensor, masked where != 0;
+ * 2 = int32 tensor, masked where == mask_cmp; 3 = float tensor, masked where == mask_cmp; strides over
+ * (B,H,Tq,Tk), 0 on broadcast axes. attn: (B,H,Tq,Tk) contiguous (post-dropout, what the example returns).
+ * out / dQ: (B,Tq,H,D) contiguous; dK / dV: (B,Tk,H,D) contiguous -- the memory order of the example's
+ * reshape/transpose views, so no copy is needed either side. out_staged (nullable): bf16 planes [B*Tq][H*D].
+ * Dropout: p in [0,1), mask = Philox(seed, call_id, epoch | *epoch_dev) over the flat attn index, regenerated in
+ * backward (nothing O(T^2) is saved). Limits: Tq, Tk, D <= 64, Tk % 4 == D % 4 == 0 (nnb_attention_supported),
+ * otherwise NNB_ERR_UNSUPPORTED and the caller runs the un-fused ops. */
+int nnb_attention_supported(int64_t Tq, int64_t Tk, int64_t D);
+int nnb_attention_forward(const float* Q, const int64_t q_strides[4], const float* KT, const int64_t kt_strides[4],
+                          const float* V, const int64_t v_strides[4], const void* mask, int mask_kind, float mask_cmp,
+                          const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
+                          uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, float* attn, float* out,
+                          void* out_staged, int prec, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D,
+                          cudaStream_t stream);
+int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const float* KT, const int64_t kt_strides[4],
+                           const float* V, const int64_t v_strides[4], const void* mask, int mask_kind, float mask_cmp,
+                           const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
+                           uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, const float* dO,
+                           const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t B, int64_t H,
+                           int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream);
+
 /* ---- Dropout with a device RNG (row N4 of SURVEY.md 8f) ----------------------------------------
  * neunet/nn/layers/dropout.py:17-46: y = x * mask, mask ~ Bernoulli(1-p) / (1-p); backward is the
  * same call on the upstream gradient. The mask is not materialised: it is Philox4x32-10 of
@@ -199,6 +244,14 @@ int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bi
 int nnb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t call_id,
                 uint64_t epoch, const uint64_t* epoch_dev, cudaStream_t stream);
 int nnb_rng_advance(uint64_t* epoch_dev, cudaStream_t stream);
+/* y = (residual +) dropout(x) over a [rows, cols] matrix -- the example's `x = x + self.dropout(a)`
+ * (examples/gpt.ipynb cell 5 l.12-13) in one pass -- and, when Y_staged_out is non-NULL, also the bf16
+ * planes of y (nnb_weight_staged_bytes(rows, cols, prec) bytes, 256-byte aligned, cols % 8 == 0) that a
+ * following nnb_linear_forward_staged consumes, so the consumer needs no staging pass.
+ * residual may be NULL. Backward of the dropout branch is nnb_dropout on the upstream gradient. */
+int nnb_dropout_fused(const float* x, const float* residual, float* y, int64_t rows, int64_t cols, float p,
+                      uint64_t seed, uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev,
+                      void* Y_staged_out, int prec, cudaStream_t stream);
 
 /* ---- fused CrossEntropyLoss (row N3 of SURVEY.md 8f, first half) --------------------------------
  * LogSoftmax(axis=1) + NLLLoss with unit class weights (neunet/nn/losses.py:59-126); native analogue

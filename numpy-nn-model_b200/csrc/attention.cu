@@ -1,0 +1,456 @@
+// Fused attention for short sequences (row N4 of SURVEY.md 8f): one kernel does
+//     scores = q . k^T / scale;  scores = where(mask, fill, scores);  p = softmax(scores, -1);
+//     attn = dropout(p);  out = attn . v
+// (examples/gpt.ipynb cell 2 l.25-40 calls these as separate Tensor ops: two Tensor.matmul
+// (neunet/autograd.py:192-230), a division, where, nn.Softmax (activations.py:437-459) and nn.Dropout
+// (layers/dropout.py:17-46)), and one kernel does the whole backward chain. The Python side
+// (neunet/autograd.py here) recognises the chain on deferred tensors and calls these instead.
+//
+// One CTA owns one (batch, head): Tq, Tk, D <= 64, so Q, K, V, the score tile and the gradients of one head
+// live in shared memory and the O(T^2) intermediates never travel to HBM (only `attn`, which the API
+// returns, is written). All arithmetic is fp32 FMA on the CUDA cores: per head the products are
+// 64 x 64 x 64 -- a 128-row tensor-core tile would be half padding and every operand would need its own
+// bf16 staging launch -- and the result is fp32-exact like the reference. The dropout mask is regenerated
+// from its Philox ticket in backward (philox.cuh), indexed like the stand-alone kernel over the contiguous
+// (B, H, Tq, Tk) `attn` tensor. Outputs are written in (B, T, H, D) memory order -- the layout the
+// surrounding reshape/transpose views of the example expect, so no `.contiguous()` copy is ever made --
+// and `out` can also be emitted as bf16 planes [B*Tq][H*D] for the following nn.Linear.
+#include <cfloat>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace nnb {
+namespace {
+
+constexpr int T = 64;    // tile edge: Tq, Tk, D <= T
+constexpr int LD = 68;   // padded pitch (floats): 16-byte aligned rows, column walks spread over banks
+
+struct AttnView {
+    const float* p;
+    long long s[4];  // element strides of the logical 4-D tensor
+};
+
+struct AttnMask {
+    const void* p;     // null: no mask
+    int kind;          // 1: float tensor, masked where value != 0; 2: int32 tensor == cmp; 3: float tensor == cmp
+    float cmp;
+    long long s[4];    // strides over (B, H, Tq, Tk); 0 on broadcast axes
+    float fill;
+};
+
+struct AttnArgs {
+    AttnView q, kt, v;     // q: (B,H,Tq,D); kt: (B,H,D,Tk); v: (B,H,Tk,D)
+    AttnMask m;
+    float scale;           // scores are DIVIDED by it, like the example
+    int drop;              // 0: no dropout
+    DropArgs d;
+    int H, Tq, Tk, D;
+};
+
+__device__ __forceinline__ bool masked(const AttnMask& m, long long off) {
+    if (m.kind == 2) return (float)static_cast<const int*>(m.p)[off] == m.cmp;
+    const float x = static_cast<const float*>(m.p)[off];
+    return m.kind == 1 ? x != 0.f : x == m.cmp;
+}
+
+// smem tile [T][LD] <- logical (rows R, cols C) matrix at p with strides (sr, sc); zero padded.
+// transposed: element (r, c) lands at dst[c][r]. Threads walk whichever global axis is contiguous.
+__device__ __forceinline__ void load_tile(float* dst, const float* p, long long sr, long long sc, int R, int C,
+                                          bool transposed, int tid, int nthreads) {
+    const bool col_fast = sc == 1 || sr != 1;
+    for (int e = tid; e < T * T; e += nthreads) {
+        const int r = col_fast ? e / T : e % T, c = col_fast ? e % T : e / T;
+        const float x = (r < R && c < C) ? p[r * sr + c * sc] : 0.f;
+        dst[transposed ? c * LD + r : r * LD + c] = x;
+    }
+}
+
+// acc[TM][TN] += sum_k A(m0 + i, k) * B(k, n0 + j); B is stored [k][n] (n contiguous, float4 reads);
+// A is stored [k][m] when A_KM (float4 reads) or [m][k] (scalar reads; a warp touches <= 4 distinct rows,
+// the rest is broadcast).
+template <int TM, int TN, bool A_KM>
+__device__ __forceinline__ void tile_fma(float (&acc)[TM][TN], const float* __restrict__ A, const float* __restrict__ B,
+                                         int K, int m0, int n0) {
+    for (int k = 0; k < K; ++k) {
+        float a[TM], b[TN];
+        if (A_KM) {
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(A + k * LD + m0 + i);
+                a[i] = t4.x; a[i + 1] = t4.y; a[i + 2] = t4.z; a[i + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = A[(m0 + i) * LD + k];
+        }
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(B + k * LD + n0 + j);
+            b[j] = t4.x; b[j + 1] = t4.y; b[j + 2] = t4.z; b[j + 3] = t4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+}
+
+template <int TM, int TN>
+__device__ __forceinline__ void zero_acc(float (&acc)[TM][TN]) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+}
+
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float half_warp_max(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Row phase shared by forward and backward: S (scaled, masked scores, [q][key]) -> P = softmax rows, in place.
+// A half-warp owns a row: lane l holds keys 4l..4l+3 (Tk % 4 == 0). Returns this lane's four probabilities.
+__device__ __forceinline__ void softmax_row(float* Srow, int Tk, int l, float (&p)[4]) {
+    const int k0 = 4 * l;
+    float4 s = *reinterpret_cast<const float4*>(Srow + k0);
+    float sv[4] = {s.x, s.y, s.z, s.w};
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (k0 + j < Tk) mx = fmaxf(mx, sv[j]);
+    mx = half_warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        p[j] = (k0 + j < Tk) ? expf(sv[j] - mx) : 0.f;
+        sum += p[j];
+    }
+    sum = half_warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = p[j] / sum;
+}
+
+// S[q][key] = (Q . K^T)[q][key] / scale, masked -> smem. 256 threads, 4 x 4 outputs each.
+__device__ __forceinline__ void scores_to_smem(const AttnArgs& a, const float* Qt, const float* Kt, float* S, int b, int h,
+                                               int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+    zero_acc(acc);
+    tile_fma<4, 4, true>(acc, Qt, Kt, a.D, ty * 4, tx * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = ty * 4 + i;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int key = tx * 4 + j;
+            float s = acc[i][j] / a.scale;
+            if (a.m.p != nullptr && q < a.Tq && key < a.Tk &&
+                masked(a.m, b * a.m.s[0] + h * a.m.s[1] + q * a.m.s[2] + key * a.m.s[3]))
+                s = a.m.fill;
+            o[j] = s;
+        }
+        *reinterpret_cast<float4*>(S + q * LD + tx * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a, float* __restrict__ attn, float* __restrict__ out,
+                                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+    extern __shared__ __align__(16) float sm[];
+    float* Qt = sm;                 // [d][q]
+    float* Kt = Qt + T * LD;        // [d][key]
+    float* Vn = Kt + T * LD;        // [key][d]
+    float* S = Vn + T * LD;         // [q][key]
+    float* Pt = S + T * LD;         // [key][q]  (post-dropout probabilities, A operand of P.V)
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
+    load_tile(Qt, a.q.p + b * a.q.s[0] + h * a.q.s[1], a.q.s[2], a.q.s[3], a.Tq, a.D, true, tid, 256);
+    load_tile(Kt, a.kt.p + b * a.kt.s[0] + h * a.kt.s[1], a.kt.s[2], a.kt.s[3], a.D, a.Tk, false, tid, 256);
+    load_tile(Vn, a.v.p + b * a.v.s[0] + h * a.v.s[1], a.v.s[2], a.v.s[3], a.Tk, a.D, false, tid, 256);
+    __syncthreads();
+    scores_to_smem(a, Qt, Kt, S, b, h, tid);
+    __syncthreads();
+    {
+        const uint64_t epoch = a.drop ? drop_epoch(a.d) : 0;
+        const int l = tid & 15;
+        for (int q = tid >> 4; q < T; q += 16) {
+            float p[4] = {0.f, 0.f, 0.f, 0.f};
+            if (q < a.Tq) {
+                softmax_row(S + q * LD, a.Tk, l, p);
+                if (4 * l < a.Tk) {
+                    const long long e = ((long long)bh * a.Tq + q) * a.Tk + 4 * l;
+                    if (a.drop) {
+                        uint32_t r[4];
+                        drop_words(a.d, epoch, e >> 2, r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) p[j] = r[j] >= a.d.thresh ? p[j] * a.d.scale : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(attn + e) = make_float4(p[0], p[1], p[2], p[3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Pt[(4 * l + j) * LD + q] = p[j];
+        }
+    }
+    __syncthreads();
+    {
+        const int ty = tid >> 4, tx = tid & 15;
+        float acc[4][4];
+        zero_acc(acc);
+        tile_fma<4, 4, true>(acc, Pt, Vn, a.Tk, ty * 4, tx * 4);
+        const int dd = tx * 4;
+        if (dd < a.D) {
+            const long long hd = (long long)a.H * a.D;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = ty * 4 + i;
+                if (q >= a.Tq) continue;
+                const long long off = ((long long)b * a.Tq + q) * hd + (long long)h * a.D + dd;  // (B, Tq, H, D)
+                *reinterpret_cast<float4*>(out + off) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (out_hi != nullptr) {
+                    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        hi[j] = __float2bfloat16_rn(acc[i][j]);
+                        lo[j] = __float2bfloat16_rn(acc[i][j] - __bfloat162float(hi[j]));
+                    }
+                    *reinterpret_cast<uint2*>(out_hi + off) = *reinterpret_cast<const uint2*>(hi);
+                    if (out_lo != nullptr) *reinterpret_cast<uint2*>(out_lo + off) = *reinterpret_cast<const uint2*>(lo);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// Recomputes S and P from q, k (no O(T^2) tensor is read back), then
+//   dPd = dO . V^T;  dP = dPd * mask / (1 - p);  dS = P * (dP - sum_key dP * P), 0 where masked, / scale
+//   dV = (P * mask / (1 - p))^T . dO;  dQ = dS . K;  dK = dS^T . Q
+// Teams of 64 threads (8 x 8 outputs each) run the independent products side by side.
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const AttnView dO, float* __restrict__ dQ,
+                                                       float* __restrict__ dK, float* __restrict__ dV) {
+    extern __shared__ __align__(16) float sm[];
+    float* Qt = sm;                  // [d][q]     A of S (k-major)
+    float* Qn = Qt + T * LD;         // [q][d]     B of dK
+    float* Kt = Qn + T * LD;         // [d][key]   B of S
+    float* Kn = Kt + T * LD;         // [key][d]   B of dQ
+    float* Vt = Kn + T * LD;         // [d][key]   B of dPd
+    float* dOn = Vt + T * LD;        // [q][d]     A of dPd (row-major), B of dV
+    float* P = dOn + T * LD;         // [q][key]   S -> P -> P*mask/(1-p)
+    float* dS = P + T * LD;          // [q][key]   dPd -> dS
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
+    const float* qp = a.q.p + b * a.q.s[0] + h * a.q.s[1];
+    const float* kp = a.kt.p + b * a.kt.s[0] + h * a.kt.s[1];
+    load_tile(Qt, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, true, tid, 256);
+    load_tile(Qn, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, false, tid, 256);
+    load_tile(Kt, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, false, tid, 256);
+    load_tile(Kn, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, true, tid, 256);
+    load_tile(Vt, a.v.p + b * a.v.s[0] + h * a.v.s[1], a.v.s[2], a.v.s[3], a.Tk, a.D, true, tid, 256);
+    load_tile(dOn, dO.p + b * dO.s[0] + h * dO.s[1], dO.s[2], dO.s[3], a.Tq, a.D, false, tid, 256);
+    __syncthreads();
+    // phase 1: threads 0..127 -> S, threads 128..255 -> dPd  (8 x 4 outputs each)
+    {
+        const int t = tid & 127, tm = t >> 4, tn = t & 15;
+        float acc[8][4];
+        zero_acc(acc);
+        if (tid < 128) {
+            tile_fma<8, 4, true>(acc, Qt, Kt, a.D, tm * 8, tn * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = tm * 8 + i;
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int key = tn * 4 + j;
+                    float s = acc[i][j] / a.scale;
+                    if (a.m.p != nullptr && q < a.Tq && key < a.Tk &&
+                        masked(a.m, b * a.m.s[0] + h * a.m.s[1] + q * a.m.s[2] + key * a.m.s[3]))
+                        s = a.m.fill;
+                    o[j] = s;
+                }
+                *reinterpret_cast<float4*>(P + q * LD + tn * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        } else {
+            tile_fma<8, 4, false>(acc, dOn, Vt, a.D, tm * 8, tn * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(dS + (tm * 8 + i) * LD + tn * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+    __syncthreads();
+    // phase 2: rows
+    {
+        const uint64_t epoch = a.drop ? drop_epoch(a.d) : 0;
+        const int l = tid & 15;
+        for (int q = tid >> 4; q < T; q += 16) {
+            float p[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f}, pd[4] = {0.f, 0.f, 0.f, 0.f};
+            if (q < a.Tq) {
+                softmax_row(P + q * LD, a.Tk, l, p);
+                const float4 g4 = *reinterpret_cast<const float4*>(dS + q * LD + 4 * l);
+                float dp[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pd[j] = p[j];
+                if (a.drop && 4 * l < a.Tk) {
+                    uint32_t r[4];
+                    drop_words(a.d, epoch, (((long long)bh * a.Tq + q) * a.Tk + 4 * l) >> 2, r);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool keep = r[j] >= a.d.thresh;
+                        dp[j] = keep ? dp[j] * a.d.scale : 0.f;
+                        pd[j] = keep ? p[j] * a.d.scale : 0.f;
+                    }
+                }
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t += (4 * l + j < a.Tk) ? dp[j] * p[j] : 0.f;
+                t = half_warp_sum(t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int key = 4 * l + j;
+                    float v = (key < a.Tk) ? (dp[j] - t) * p[j] : 0.f;
+                    if (a.m.p != nullptr && key < a.Tk &&
+                        masked(a.m, b * a.m.s[0] + h * a.m.s[1] + q * a.m.s[2] + key * a.m.s[3]))
+                        v = 0.f;  // where(): masked scores receive no gradient
+                    ds[j] = v / a.scale;
+                }
+            }
+            *reinterpret_cast<float4*>(P + q * LD + 4 * l) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+            *reinterpret_cast<float4*>(dS + q * LD + 4 * l) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+        }
+    }
+    __syncthreads();
+    // phase 3: team 0 -> dV = Pd^T . dO, team 1 -> dQ = dS . K, team 2 -> dK = dS^T . Q   (8 x 8 outputs each)
+    {
+        const int team = tid >> 6, t = tid & 63, tm = t >> 3, tn = t & 7;
+        if (team < 3) {
+            float acc[8][8];
+            zero_acc(acc);
+            float* dst;
+            int rows;
+            if (team == 0) { tile_fma<8, 8, true>(acc, P, dOn, a.Tq, tm * 8, tn * 8); dst = dV; rows = a.Tk; }
+            else if (team == 1) { tile_fma<8, 8, false>(acc, dS, Kn, a.Tk, tm * 8, tn * 8); dst = dQ; rows = a.Tq; }
+            else { tile_fma<8, 8, true>(acc, dS, Qn, a.Tq, tm * 8, tn * 8); dst = dK; rows = a.Tk; }
+            const long long hd = (long long)a.H * a.D;
+            const int T_out = rows;  // (B, T_out, H, D) memory order
+            if (dst != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = tm * 8 + i;
+                    if (r >= rows) continue;
+                    float* o = dst + ((long long)b * T_out + r) * hd + (long long)h * a.D + tn * 8;
+                    if (tn * 8 + 3 < a.D) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                    if (tn * 8 + 7 < a.D) *reinterpret_cast<float4*>(o + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+                }
+            }
+        }
+    }
+}
+
+int fill_args(AttnArgs& a, const float* Q, const int64_t* qs, const float* KT, const int64_t* ks, const float* V,
+              const int64_t* vs, const void* mask, int mask_kind, float mask_cmp, const int64_t* ms, float fill,
+              float scale, float p, uint64_t seed, uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev,
+              int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D) {
+    NNB_REQUIRE(Q && KT && V && qs && ks && vs, "nnb_attention: null pointer");
+    NNB_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0 && D > 0, "nnb_attention: non-positive dimension");
+    if (!(Tq <= T && Tk <= T && D <= T && Tk % 4 == 0 && D % 4 == 0))
+        return fail(NNB_ERR_UNSUPPORTED, "nnb_attention: the fused kernel needs Tq, Tk, D <= 64 with Tk %% 4 == D %% 4 == 0");
+    NNB_REQUIRE(B * H < (1ll << 31), "nnb_attention: too many heads");
+    NNB_REQUIRE(mask == nullptr || (ms != nullptr && mask_kind >= 1 && mask_kind <= 3), "nnb_attention: bad mask description");
+    NNB_REQUIRE(scale != 0.f, "nnb_attention: scale must be non-zero");
+    NNB_REQUIRE(p >= 0.f && p < 1.f, "nnb_attention: p must be in [0, 1)");
+    a.q.p = Q; a.kt.p = KT; a.v.p = V;
+    for (int i = 0; i < 4; ++i) { a.q.s[i] = qs[i]; a.kt.s[i] = ks[i]; a.v.s[i] = vs[i]; a.m.s[i] = mask ? ms[i] : 0; }
+    a.m.p = mask; a.m.kind = mask_kind; a.m.cmp = mask_cmp; a.m.fill = fill;
+    a.scale = scale;
+    a.drop = p > 0.f ? 1 : 0;
+    a.d = make_drop_args(p, seed, call_id, epoch, epoch_dev);
+    a.H = (int)H; a.Tq = (int)Tq; a.Tk = (int)Tk; a.D = (int)D;
+    return NNB_OK;
+}
+
+}  // namespace
+}  // namespace nnb
+
+using namespace nnb;
+
+extern "C" {
+
+int nnb_attention_supported(int64_t Tq, int64_t Tk, int64_t D) {
+    return (Tq > 0 && Tk > 0 && D > 0 && Tq <= T && Tk <= T && D <= T && Tk % 4 == 0 && D % 4 == 0) ? 1 : 0;
+}
+
+int nnb_attention_forward(const float* Q, const int64_t q_strides[4], const float* KT, const int64_t kt_strides[4],
+                          const float* V, const int64_t v_strides[4], const void* mask, int mask_kind, float mask_cmp,
+                          const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
+                          uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, float* attn, float* out,
+                          void* out_staged, int prec, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D,
+                          cudaStream_t stream) {
+    AttnArgs a;
+    int rc = fill_args(a, Q, q_strides, KT, kt_strides, V, v_strides, mask, mask_kind, mask_cmp, mask_strides, fill, scale, p,
+                       seed, call_id, epoch, epoch_dev, B, H, Tq, Tk, D);
+    if (rc) return rc;
+    NNB_REQUIRE(attn && out, "nnb_attention_forward: null output");
+    NNB_REQUIRE(((reinterpret_cast<uintptr_t>(attn) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "nnb_attention_forward: outputs must be 16-byte aligned");
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    if (out_staged != nullptr) {
+        NNB_REQUIRE((H * D) % 8 == 0, "nnb_attention_forward: staged output needs H*D %% 8 == 0");
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(out_staged) & 255) == 0, "nnb_attention_forward: out_staged must be 256-byte aligned");
+        NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_attention_forward: bad prec");
+        hi = static_cast<__nv_bfloat16*>(out_staged);
+        if (prec == NNB_PREC_BF16X3)
+            lo = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(out_staged) + staged_plane_bytes(1, B * Tq, H * D));
+    }
+    const size_t smem = (size_t)5 * T * LD * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        NNB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    NNB_CUDA_OK(launch_pdl(attn_fwd_kernel, dim3((unsigned)(B * H)), dim3(256), smem, stream, a, attn, out, hi, lo));
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const float* KT, const int64_t kt_strides[4],
+                           const float* V, const int64_t v_strides[4], const void* mask, int mask_kind, float mask_cmp,
+                           const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
+                           uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, const float* dO,
+                           const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t B, int64_t H,
+                           int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream) {
+    AttnArgs a;
+    int rc = fill_args(a, Q, q_strides, KT, kt_strides, V, v_strides, mask, mask_kind, mask_cmp, mask_strides, fill, scale, p,
+                       seed, call_id, epoch, epoch_dev, B, H, Tq, Tk, D);
+    if (rc) return rc;
+    NNB_REQUIRE(dO && do_strides, "nnb_attention_backward: null dO");
+    NNB_REQUIRE(((reinterpret_cast<uintptr_t>(dQ) | reinterpret_cast<uintptr_t>(dK) | reinterpret_cast<uintptr_t>(dV)) & 15) == 0,
+                "nnb_attention_backward: outputs must be 16-byte aligned");
+    AttnView g;
+    g.p = dO;
+    for (int i = 0; i < 4; ++i) g.s[i] = do_strides[i];
+    const size_t smem = (size_t)8 * T * LD * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        NNB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    NNB_CUDA_OK(launch_pdl(attn_bwd_kernel, dim3((unsigned)(B * H)), dim3(256), smem, stream, a, g, dQ, dK, dV));
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+}  // extern "C"

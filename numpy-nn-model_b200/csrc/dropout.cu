@@ -9,53 +9,65 @@
 // CUDA-graph replays must not repeat masks, so the epoch may live in device memory (`epoch_dev`):
 // the graph bakes the pointer, nnb_rng_advance() bumps the value between replays.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nnb {
 namespace {
 
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        philox_round(c, k0, k1);
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-
-// keep iff u32 >= p * 2^32  (P[keep] = 1 - p to within 2^-32)
-__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                      long long n, uint32_t thresh, float scale,
-                                                      uint64_t seed, uint32_t call_id, uint64_t epoch_host,
-                                                      const unsigned long long* __restrict__ epoch_dev, int vec) {
+// y = (residual +) dropout(x); optionally also the bf16 planes of y (hi [+ lo]) for the next Linear, so the
+// consumer needs no staging pass. keep iff word >= p * 2^32  (P[keep] = 1 - p to within 2^-32).
+template <bool PLANES>
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                      float* __restrict__ y, long long n, const DropArgs d,
+                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                      int vec) {
     pdl_trigger();
     pdl_wait();
-    const uint64_t epoch = epoch_dev ? (uint64_t)*epoch_dev : epoch_host;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint64_t epoch = drop_epoch(d);
     const long long nvec = (n + 3) >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
          i += (long long)gridDim.x * blockDim.x) {
-        uint32_t c[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32) ^ (call_id * 0x9E3779B1u), (uint32_t)epoch,
-                         (uint32_t)(epoch >> 32)};
-        philox4x32_10(c, k0, k1);
+        uint32_t c[4];
+        drop_words(d, epoch, i, c);
         const long long e = i << 2;
         if (vec && e + 3 < n) {
             float4 v = *reinterpret_cast<const float4*>(x + e);
-            v.x = c[0] >= thresh ? v.x * scale : 0.f;
-            v.y = c[1] >= thresh ? v.y * scale : 0.f;
-            v.z = c[2] >= thresh ? v.z * scale : 0.f;
-            v.w = c[3] >= thresh ? v.w * scale : 0.f;
+            v.x = c[0] >= d.thresh ? v.x * d.scale : 0.f;
+            v.y = c[1] >= d.thresh ? v.y * d.scale : 0.f;
+            v.z = c[2] >= d.thresh ? v.z * d.scale : 0.f;
+            v.w = c[3] >= d.thresh ? v.w * d.scale : 0.f;
+            if (res != nullptr) {
+                const float4 r = *reinterpret_cast<const float4*>(res + e);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
             *reinterpret_cast<float4*>(y + e) = v;
+            if (PLANES) {
+                const float xv[4] = {v.x, v.y, v.z, v.w};
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split2(xv[j], h[j], l[j]);
+                *reinterpret_cast<uint2*>(hi + e) = *reinterpret_cast<const uint2*>(h);
+                if (lo != nullptr) *reinterpret_cast<uint2*>(lo + e) = *reinterpret_cast<const uint2*>(l);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (e + j < n) y[e + j] = c[j] >= thresh ? x[e + j] * scale : 0.f;
+                if (e + j < n) {
+                    float v = c[j] >= d.thresh ? x[e + j] * d.scale : 0.f;
+                    if (res != nullptr) v += res[e + j];
+                    y[e + j] = v;
+                    if (PLANES) {
+                        __nv_bfloat16 h, l;
+                        split2(v, h, l);
+                        hi[e + j] = h;
+                        if (lo != nullptr) lo[e + j] = l;
+                    }
+                }
         }
     }
 }
@@ -69,22 +81,40 @@ using namespace nnb;
 
 extern "C" {
 
-int nnb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t call_id,
-                uint64_t epoch, const uint64_t* epoch_dev, cudaStream_t stream) {
+int nnb_dropout_fused(const float* x, const float* residual, float* y, int64_t rows, int64_t cols, float p,
+                      uint64_t seed, uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev,
+                      void* Y_staged_out, int prec, cudaStream_t stream) {
     NNB_REQUIRE(x && y, "nnb_dropout: null pointer");
-    NNB_REQUIRE(n > 0, "nnb_dropout: bad size");
+    NNB_REQUIRE(rows > 0 && cols > 0, "nnb_dropout: bad size");
     NNB_REQUIRE(p >= 0.f && p < 1.f, "nnb_dropout: p must be in [0, 1)");
-    const double t = (double)p * 4294967296.0;
-    const uint32_t thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-    const float scale = (float)(1.0 / (1.0 - (double)p));
-    const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const int64_t n = rows * cols;
+    const DropArgs d = make_drop_args(p, seed, call_id, epoch, epoch_dev);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const int vec = al16(x) && al16(y) && (residual == nullptr || al16(residual));
     const long long nvec = (n + 3) / 4;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(nvec, 256), (long long)num_sms() * 16));
-    NNB_CUDA_OK(launch_pdl(dropout_kernel, dim3(blocks), dim3(256), 0, stream, x, y, (long long)n, thresh, scale, seed,
-                           call_id, epoch, reinterpret_cast<const unsigned long long*>(epoch_dev), vec));
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    if (Y_staged_out != nullptr) {
+        // planes are [rows][ld = round_up(cols, 8)]: only a pitch equal to cols lets the flat kernel write them
+        NNB_REQUIRE(cols % 8 == 0, "nnb_dropout: staged output needs cols % 8 == 0");
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(Y_staged_out) & 255) == 0, "nnb_dropout: Y_staged_out must be 256-byte aligned");
+        NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_dropout: bad prec");
+        hi = static_cast<__nv_bfloat16*>(Y_staged_out);
+        if (prec == NNB_PREC_BF16X3)
+            lo = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(Y_staged_out) + staged_plane_bytes(1, rows, cols));
+        NNB_CUDA_OK(launch_pdl(dropout_kernel<true>, dim3(blocks), dim3(256), 0, stream, x, residual, y, (long long)n, d, hi, lo, vec));
+    } else {
+        NNB_CUDA_OK(launch_pdl(dropout_kernel<false>, dim3(blocks), dim3(256), 0, stream, x, residual, y, (long long)n, d, hi, lo, vec));
+    }
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
+}
+
+int nnb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t call_id,
+                uint64_t epoch, const uint64_t* epoch_dev, cudaStream_t stream) {
+    NNB_REQUIRE(n > 0, "nnb_dropout: bad size");
+    return nnb_dropout_fused(x, nullptr, y, 1, n, p, seed, call_id, epoch, epoch_dev, nullptr, NNB_PREC_BF16, stream);
 }
 
 int nnb_rng_advance(uint64_t* epoch_dev, cudaStream_t stream) {

@@ -7,6 +7,7 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "workspace.cuh"
 
 namespace nnb {
@@ -142,6 +143,73 @@ __global__ void rmsnorm_fwd_kernel(const float* __restrict__ X, const float* __r
     }
 }
 
+// Fused forward for cols <= 1024, cols % 4 == 0 (one warp per row, the row lives in registers):
+//   S = X (+ dropout(A))        -- optional residual prologue: `x = x + dropout(a)` then `norm(x)` (gpt cell 5)
+//   Y = S / sqrt(mean(S^2) + eps) * w (+ b), X_std, and optionally the bf16 planes of Y for the next Linear
+// so the residual add, the dropout, the norm and the operand staging of the following GEMM are ONE pass.
+template <int NJ4>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_fused_kernel(
+    const float* __restrict__ X, const float* __restrict__ A, const DropArgs d, float* __restrict__ S,
+    const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ Y, float* __restrict__ Xstd,
+    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long rows, int cols, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const uint64_t epoch = A != nullptr ? drop_epoch(d) : 0;
+    float4 x[NJ4];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ4; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        if (c < cols) {
+            x[j] = *reinterpret_cast<const float4*>(X + row * cols + c);
+            if (A != nullptr) {
+                float4 a = *reinterpret_cast<const float4*>(A + row * cols + c);
+                uint32_t r[4];
+                drop_words(d, epoch, (row * cols + c) >> 2, r);
+                a.x = r[0] >= d.thresh ? a.x * d.scale : 0.f;
+                a.y = r[1] >= d.thresh ? a.y * d.scale : 0.f;
+                a.z = r[2] >= d.thresh ? a.z * d.scale : 0.f;
+                a.w = r[3] >= d.thresh ? a.w * d.scale : 0.f;
+                x[j].x += a.x; x[j].y += a.y; x[j].z += a.z; x[j].w += a.w;
+                *reinterpret_cast<float4*>(S + row * cols + c) = x[j];
+            }
+            ss += x[j].x * x[j].x + x[j].y * x[j].y + x[j].z * x[j].z + x[j].w * x[j].w;
+        } else {
+            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    ss = warp_sum(ss);
+    const float std = sqrtf(ss / (float)cols + eps);
+    if (lane == 0 && Xstd) Xstd[row] = std;
+#pragma unroll
+    for (int j = 0; j < NJ4; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        if (c >= cols) continue;
+        const float4 wv = *reinterpret_cast<const float4*>(w + c);
+        float4 y;
+        y.x = x[j].x / std * wv.x; y.y = x[j].y / std * wv.y; y.z = x[j].z / std * wv.z; y.w = x[j].w / std * wv.w;
+        if (b != nullptr) {
+            const float4 bv = *reinterpret_cast<const float4*>(b + c);
+            y.x += bv.x; y.y += bv.y; y.z += bv.z; y.w += bv.w;
+        }
+        *reinterpret_cast<float4*>(Y + row * cols + c) = y;
+        if (hi != nullptr) {
+            const float yv[4] = {y.x, y.y, y.z, y.w};
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                h[k] = __float2bfloat16_rn(yv[k]);
+                l[k] = __float2bfloat16_rn(yv[k] - __bfloat162float(h[k]));
+            }
+            *reinterpret_cast<uint2*>(hi + row * cols + c) = *reinterpret_cast<const uint2*>(h);
+            if (lo != nullptr) *reinterpret_cast<uint2*>(lo + row * cols + c) = *reinterpret_cast<const uint2*>(l);
+        }
+    }
+}
+
 __global__ void rmsnorm_bwd_dx_kernel(const float* __restrict__ gY, const float* __restrict__ X,
                                       const float* __restrict__ w, const float* __restrict__ Xstd,
                                       float* __restrict__ dX, long long rows, int cols) {
@@ -187,7 +255,7 @@ template <int NJ4>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_fused_kernel(
     const float* __restrict__ gY, const float* __restrict__ X, const float* __restrict__ w,
     const float* __restrict__ Xstd, float* __restrict__ dX, float* __restrict__ pw,
-    float* __restrict__ pb, long long rows, int cols, int rows_per_block) {
+    float* __restrict__ pb, long long rows, int cols, int rows_per_block, const float* __restrict__ dXadd) {
     __shared__ float red[8][NJ4 * 128 + 4];
     pdl_trigger();
     pdl_wait();
@@ -234,6 +302,10 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_fused_kernel(
                 d.y = (wv[j].y * g[j].y * std - x[j].y * cc) * inv2;
                 d.z = (wv[j].z * g[j].z * std - x[j].z * cc) * inv2;
                 d.w = (wv[j].w * g[j].w * std - x[j].w * cc) * inv2;
+                if (dXadd != nullptr) {  // accumulate onto the gradient X already holds (residual branch)
+                    const float4 e = *reinterpret_cast<const float4*>(dXadd + r * cols + c);
+                    d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+                }
                 *reinterpret_cast<float4*>(dX + r * cols + c) = d;
             }
             aw[j].x += g[j].x * (x[j].x / std); aw[j].y += g[j].y * (x[j].y / std);
@@ -370,6 +442,39 @@ int nnb_rmsnorm_forward(const float* X, const float* w, const float* b, float* Y
     return NNB_OK;
 }
 
+int nnb_rmsnorm_forward_fused(const float* X, const float* A, float p, uint64_t seed, uint32_t call_id,
+                              uint64_t epoch, const uint64_t* epoch_dev, float* S, const float* w, const float* b,
+                              float* Y, float* X_std, void* Y_staged_out, int prec, int64_t rows, int64_t cols,
+                              float eps, cudaStream_t stream) {
+    NNB_REQUIRE(X && w && Y, "nnb_rmsnorm_forward_fused: null pointer");
+    NNB_REQUIRE(rows > 0 && cols > 0, "nnb_rmsnorm_forward_fused: bad shape");
+    NNB_REQUIRE(A == nullptr || S != nullptr, "nnb_rmsnorm_forward_fused: the residual prologue needs the sum output S");
+    NNB_REQUIRE(A == nullptr || (p >= 0.f && p < 1.f), "nnb_rmsnorm_forward_fused: p must be in [0, 1)");
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!(cols <= 1024 && cols % 4 == 0 && al16(X) && al16(w) && al16(Y) && (!A || (al16(A) && al16(S))) && (!b || al16(b)) &&
+          (Y_staged_out == nullptr || cols % 8 == 0)))
+        return fail(NNB_ERR_UNSUPPORTED, "nnb_rmsnorm_forward_fused: needs cols <= 1024, cols %% 4 == 0 (8 with planes), 16-byte aligned rows");
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    if (Y_staged_out != nullptr) {
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(Y_staged_out) & 255) == 0, "nnb_rmsnorm_forward_fused: Y_staged_out must be 256-byte aligned");
+        NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_rmsnorm_forward_fused: bad prec");
+        hi = static_cast<__nv_bfloat16*>(Y_staged_out);
+        if (prec == NNB_PREC_BF16X3)
+            lo = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(Y_staged_out) + staged_plane_bytes(1, rows, cols));
+    }
+    const DropArgs d = make_drop_args(A ? p : 0.f, seed, call_id, epoch, epoch_dev);
+    const dim3 grid((unsigned)ceil_div(rows * 32, 256)), block(256);
+    const long long rows_ll = rows;
+    const int cols_i = (int)cols, nj4 = (int)ceil_div(cols, 128);
+    if (nj4 <= 1) NNB_CUDA_OK(launch_pdl(rmsnorm_fwd_fused_kernel<1>, grid, block, 0, stream, X, A, d, S, w, b, Y, X_std, hi, lo, rows_ll, cols_i, eps));
+    else if (nj4 <= 2) NNB_CUDA_OK(launch_pdl(rmsnorm_fwd_fused_kernel<2>, grid, block, 0, stream, X, A, d, S, w, b, Y, X_std, hi, lo, rows_ll, cols_i, eps));
+    else if (nj4 <= 4) NNB_CUDA_OK(launch_pdl(rmsnorm_fwd_fused_kernel<4>, grid, block, 0, stream, X, A, d, S, w, b, Y, X_std, hi, lo, rows_ll, cols_i, eps));
+    else NNB_CUDA_OK(launch_pdl(rmsnorm_fwd_fused_kernel<8>, grid, block, 0, stream, X, A, d, S, w, b, Y, X_std, hi, lo, rows_ll, cols_i, eps));
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
 size_t nnb_rmsnorm_workspace_bytes(int64_t rows, int64_t cols) {
     (void)rows;
     return (size_t)(2 * RMS_MAX_PARTS * cols * 4 + 512);
@@ -379,11 +484,19 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
                          const float* X_norm, float* dX, float* dw, float* db, int64_t rows,
                          int64_t cols, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream) {
+    return nnb_rmsnorm_backward_acc(gY, X, w, X_std, X_norm, nullptr, dX, dw, db, rows, cols, workspace, workspace_bytes, stream);
+}
+
+int nnb_rmsnorm_backward_acc(const float* gY, const float* X, const float* w, const float* X_std,
+                             const float* X_norm, const float* dX_add, float* dX, float* dw, float* db,
+                             int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream) {
     (void)X_norm;  // recomputed as X / X_std: cheaper than reading a second [rows, cols] array
     NNB_REQUIRE(gY && X && w && X_std && dX, "nnb_rmsnorm_backward: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_backward: bad shape");
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    const bool fused = cols <= 1024 && (cols % 4) == 0 && al16(gY) && al16(X) && al16(w) && al16(dX);
+    const bool fused = cols <= 1024 && (cols % 4) == 0 && al16(gY) && al16(X) && al16(w) && al16(dX) && (!dX_add || al16(dX_add));
+    NNB_REQUIRE(fused || dX_add == nullptr, "nnb_rmsnorm_backward_acc: dX_add needs the fused path (cols <= 1024, cols %% 4 == 0)");
     float *pw = nullptr, *pb = nullptr;
     if (dw) {
         Bump ws(workspace, workspace_bytes);
@@ -400,10 +513,10 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
         const dim3 fg((unsigned)parts), fb(256);
         const long long rows_ll = rows;
         const int cols_i = (int)cols;
-        if (nj4 <= 1) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<1>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
-        else if (nj4 <= 2) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<2>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
-        else if (nj4 <= 4) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<4>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
-        else NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<8>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb));
+        if (nj4 <= 1) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<1>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb, dX_add));
+        else if (nj4 <= 2) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<2>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb, dX_add));
+        else if (nj4 <= 4) NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<4>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb, dX_add));
+        else NNB_CUDA_OK(launch_pdl(rmsnorm_bwd_fused_kernel<8>, fg, fb, 0, stream, gY, X, w, X_std, dX, pw, pb, rows_ll, cols_i, rpb, dX_add));
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());
         if (dw) {

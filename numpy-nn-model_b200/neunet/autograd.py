@@ -15,6 +15,7 @@ without the reference's extra copy, and ``matmul`` on ``"cuda"`` calls the tcgen
 """
 from __future__ import annotations
 
+import os
 from typing import Any
 
 import numpy as np
@@ -27,6 +28,27 @@ def _is_arr(x):
     return isinstance(x, np.ndarray) or _be.is_device_array(x)
 
 
+# ---- deferred evaluation on "cuda" (epilogue / prologue fusion across the example's separate op calls) ------------
+# The examples call q.k^T, "/ scale", where(mask), Softmax, Dropout, ".v", Linear -> Swish, "x + dropout(a)" -> RMSNorm
+# as separate Tensor ops (examples/gpt.ipynb cells 2-5). To run them as the fused kernels of neunet.b200 WITHOUT
+# changing the example code, a few op results on "cuda" are *deferred*: the Tensor exists at once (shape, tape
+# links), its array is produced on first read of ``.data``. A consumer that recognises a still-pending producer
+# launches ONE fused kernel instead (and never forces the producer); anything else that reads ``.data`` simply
+# runs the producer's own kernel, so results are identical either way up to fp32 round-off.
+# NEUNET_B200_FUSE=0 / set_fusion(False) restores strictly eager execution.
+_FUSION = {"on": os.environ.get("NEUNET_B200_FUSE", "1") != "0"}
+
+
+def set_fusion(on: bool) -> bool:
+    prev = _FUSION["on"]
+    _FUSION["on"] = bool(on)
+    return prev
+
+
+def fusion_enabled() -> bool:
+    return _FUSION["on"]
+
+
 class Tensor:
     __array_priority__ = 1000  # NumPy scalars/arrays defer to Tensor's reflected operators
 
@@ -36,6 +58,8 @@ class Tensor:
         self.xp = get_xp(device)
         if isinstance(data, Tensor):
             data = data.data
+        elif isinstance(data, (int, float)) and not isinstance(data, bool):
+            self._pyscalar = data  # fused kernels take constants by value (no device read-back)
         want = np.float32 if dtype is None else dtype
         if device == "cpu":
             if _be.is_device_array(data):
@@ -158,6 +182,10 @@ class Tensor:
 
     # ---- arithmetic -------------------------------------------------------------------------------
     def add(self, t):
+        if self.device == "cuda" and _FUSION["on"] and isinstance(t, Tensor):
+            fused = _defer_add_dropout(self, t)
+            if fused is not None:
+                return fused
         return self._binary(t, "add", lambda a, b: a + b, lambda a, b, g: g, lambda a, b, g: g)
 
     def sub(self, t):
@@ -167,6 +195,13 @@ class Tensor:
         return self._binary(t, "mul", lambda a, b: a * b, lambda a, b, g: g * b.data, lambda a, b, g: g * a.data)
 
     def div(self, t):
+        if _pending(self, "matmul") and isinstance(t, (int, float)) and not isinstance(t, bool) and t != 0:
+            # `scores / scale` on a not-yet-launched q.k^T: stays pending so the attention kernel can absorb it
+            src, c = self, float(t)
+            out = _Deferred.make(lambda: src.data / c, self.shape, (self, c), "div", self.requires_grad,
+                                 _f_kind="div", _f_src=self, _f_c=c)
+            out.grad_fn = _div_scalar_grad
+            return out
         return self._binary(t, "div", lambda a, b: a / b, lambda a, b, g: g / b.data,
                             lambda a, b, g: -g * a.data / (b.data ** 2))
 
@@ -193,13 +228,32 @@ class Tensor:
         rg = self.requires_grad or t.requires_grad
         xp = self.xp
         staged = None
-        if rg and self.device == "cuda" and self.data.ndim >= 2 and t.data.ndim >= 2:
+        held = {}
+        if self.device == "cuda" and _FUSION["on"] and self.ndim >= 2 and t.ndim >= 2:
             from . import b200
-            # keep the bf16 planes of both operands: backward (dA = G.B^T, dB = A^T.G) reads the same planes
-            data, staged = b200.matmul(self.data, t.data, keep_staged=True)
+            fused = _try_fused_attention(self, t)
+            if fused is not None:
+                return fused
+            if self.shape[-1] != t.shape[-2]:
+                raise ValueError(f"matmul: shapes {self.shape} and {t.shape} not aligned")
+            a_t, b_t = self, t
+
+            def thunk():
+                if rg:
+                    # keep the bf16 planes of both operands: backward (dA = G.B^T, dB = A^T.G) reads the same planes
+                    data, held["staged"] = b200.matmul(a_t.data, b_t.data, keep_staged=True)
+                    return data
+                return b200.matmul(a_t.data, b_t.data)
+            oshape = tuple(np.broadcast_shapes(self.shape[:-2], t.shape[:-2])) + (self.shape[-2], t.shape[-1])
+            out = _Deferred.make(thunk, oshape, (self, t) if rg else None, "matmul", rg, _f_kind="matmul", _f_a=self, _f_b=t)
         else:
-            data = xp.matmul(self.data, t.data)
-        out = Tensor._wrap(data, (self, t) if rg else None, "matmul", rg, self.device)
+            if rg and self.device == "cuda" and self.data.ndim >= 2 and t.data.ndim >= 2:
+                from . import b200
+                data, staged = b200.matmul(self.data, t.data, keep_staged=True)
+                held["staged"] = staged
+            else:
+                data = xp.matmul(self.data, t.data)
+            out = Tensor._wrap(data, (self, t) if rg else None, "matmul", rg, self.device)
         if not rg:
             return out
 
@@ -207,6 +261,7 @@ class Tensor:
             from . import b200
 
             def grad_fn(a: "Tensor", b: "Tensor", grad):
+                staged = held.get("staged")
                 ad, bd = a.data, b.data
                 if ad.ndim == 1 and bd.ndim == 1:  # vector . vector: no contraction left
                     if a.requires_grad:
@@ -373,7 +428,15 @@ class Tensor:
         shape = shape[0] if len(shape) == 1 else shape
         if isinstance(shape, int):
             shape = (shape,)
-        out = Tensor._wrap(self.data.reshape(tuple(shape)), (self,), "reshape", self.requires_grad, self.device, cast=False)
+        if _pending(self):
+            # a view of a pending result stays pending (q/k/v head splits must not force their Linear one by one)
+            src, shp = self, _resolve_shape(tuple(shape), self.size)
+            out = _Deferred.make(lambda: src.data.reshape(shp), shp, (self,), "reshape",
+                                 self.requires_grad, _f_kind="view", _f_src=self)
+        else:
+            out = Tensor._wrap(self.data.reshape(tuple(shape)), (self,), "reshape", self.requires_grad, self.device, cast=False)
+            if self.device == "cuda" and getattr(self, "_b200_xst", None) is not None:
+                out._b200_xst = self._b200_xst
 
         def grad_fn(a: "Tensor", grad):
             if a.requires_grad:
@@ -387,7 +450,14 @@ class Tensor:
             axes = tuple(range(self.data.ndim))[::-1]
         axes = tuple(axes)
         xp = self.xp
-        out = Tensor._wrap(xp.transpose(self.data, axes), (self, axes), "transpose", self.requires_grad, self.device)
+        if _pending(self):
+            src = self
+            out = _Deferred.make(lambda: xp.transpose(src.data, axes), tuple(self.shape[a] for a in axes),
+                                 (self, axes), "transpose", self.requires_grad, _f_kind="view", _f_src=self)
+        else:
+            out = Tensor._wrap(xp.transpose(self.data, axes), (self, axes), "transpose", self.requires_grad, self.device)
+            if self.device == "cuda" and getattr(self, "_b200_xst", None) is not None:
+                out._b200_xst = self._b200_xst
 
         def grad_fn(a: "Tensor", axes, grad):
             # NB: like the reference (autograd.py:618-620) the gradient is permuted by `axes` again,
@@ -426,9 +496,17 @@ class Tensor:
         t = self.ensure_tensor(t)
         rg = self.requires_grad or t.requires_grad
         xp = self.xp
-        cond = condition.data != 0 if self.device == "cuda" else condition.data
-        out = Tensor._wrap(xp.where(cond, self.data, t.data), (self, condition, t) if rg else None, "where", rg,
-                           self.device)
+        if (self.device == "cuda" and (_pending(t, "div") or _pending(t, "matmul")) and not self.requires_grad
+                and not condition.requires_grad and getattr(self, "_pyscalar", None) is not None and self.ndim == 0):
+            # where(mask, constant, scores) on pending attention scores: stays pending (absorbed by the attention kernel)
+            a_t, c_t, b_t = self, condition, t
+            out = _Deferred.make(lambda: xp.where(c_t.data != 0, a_t.data, b_t.data),
+                                 tuple(np.broadcast_shapes(condition.shape, t.shape)), (self, condition, t) if rg else None,
+                                 "where", rg, _f_kind="where", _f_fill=float(self._pyscalar), _f_cond=condition, _f_src=t)
+        else:
+            cond = condition.data != 0 if self.device == "cuda" else condition.data
+            out = Tensor._wrap(xp.where(cond, self.data, t.data), (self, condition, t) if rg else None, "where", rg,
+                               self.device)
         if rg:
             def grad_fn(a: "Tensor", condition: "Tensor", b: "Tensor", grad):
                 c = condition.data != 0 if a.device == "cuda" else condition.data
@@ -441,6 +519,13 @@ class Tensor:
 
     # ---- comparisons (non-differentiable, float32 0/1 results like the reference) -----------------------
     def _compare(self, t, op, fn):
+        if (op == "equal" and self.device == "cuda" and _FUSION["on"] and isinstance(t, (int, float))
+                and not isinstance(t, bool) and not _pending(self)
+                and self.data.dtype in (_be.torch.int32, _be.torch.float32)):
+            # `mask == 0`: pending, so the attention kernel can test the mask itself instead of reading a 0/1 tensor
+            src, c = self, t
+            return _Deferred.make(lambda: (src.data == c).to(_be.torch.float32), self.shape, None, op, False,
+                                  _f_kind="eq_scalar", _f_base=self, _f_value=float(t))
         t = self.ensure_tensor(t)
         return Tensor._wrap(fn(self.data, t.data), None, op, False, self.device)
 
@@ -614,6 +699,186 @@ class Tensor:
                         if ent[1] == 0:
                             del uses[id(a)]
                             a._grad_ready(a)
+
+
+class _Deferred(Tensor):
+    """A "cuda" result whose array is produced on first read of ``.data`` (see the note on deferred
+    evaluation at the top of this file). ``_f_kind`` and the other ``_f_*`` attributes describe the
+    producer to consumers that can absorb it into a fused kernel."""
+
+    @classmethod
+    def make(cls, thunk, shape, args, op, requires_grad, **meta):
+        t = cls.__new__(cls)
+        d = t.__dict__
+        d["_data"] = None
+        d["_thunk"] = thunk
+        d["_shape"] = tuple(int(v) for v in shape)
+        d["xp"] = get_xp("cuda")
+        d["grad"] = None
+        d["op"] = op
+        d["args"] = args
+        d["requires_grad"] = requires_grad
+        d["device"] = "cuda"
+        d["grad_fn"] = _no_grad_fn
+        d.update(meta)
+        return t
+
+    @property
+    def data(self):
+        d = self._data
+        if d is None:
+            thunk = self._thunk
+            d = thunk()
+            if self._data is None:  # a fused consumer may have delivered the array meanwhile
+                self._data = d
+            else:
+                d = self._data
+            self._thunk = None
+            if self.__dict__.get("_f_kind") == "view":
+                # views inherit the ready-made bf16 operand planes of their source (validated by
+                # pointer / version / shape at the consuming nn.Linear, so a mismatching entry is ignored)
+                planes = self._f_src.__dict__.get("_b200_xst")
+                if planes is not None:
+                    self.__dict__["_b200_xst"] = planes
+        return d
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._thunk = None
+
+    @property
+    def pending(self):
+        return self._data is None
+
+    @property
+    def shape(self):
+        return self._shape if self._data is None else tuple(self._data.shape)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def dtype(self):
+        if self._data is None:
+            return np.dtype(np.float32)
+        return _be.to_numpy_dtype(self._data.dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+
+def _pending(t, kind=None):
+    return (isinstance(t, _Deferred) and t._data is None and _FUSION["on"]
+            and (kind is None or t.__dict__.get("_f_kind") == kind))
+
+
+def _resolve_shape(shape, size):
+    shape = tuple(int(v) for v in shape)
+    if -1 in shape:
+        known = int(np.prod([v for v in shape if v != -1])) or 1
+        shape = tuple(size // known if v == -1 else v for v in shape)
+    return shape
+
+
+def _div_scalar_grad(a, c, grad):
+    if a.requires_grad:
+        a.apply_grad(grad / c)
+
+
+def _defer_add_dropout(x, t):
+    """`x + dropout(a)` (either order) with the dropout still pending: one kernel, and the sum itself stays
+    pending so that a following RMSNorm can absorb it as its prologue."""
+    if _pending(t, "dropout") and not _pending(x, "dropout"):
+        res, drop = x, t
+    elif _pending(x, "dropout") and not _pending(t, "dropout"):
+        res, drop = t, x
+    else:
+        return None
+    if tuple(res.shape) != tuple(drop.shape) or res.device != "cuda" or drop._f_ticket is None:
+        return None
+    from . import b200
+    a_t, p, ticket = drop._f_src, drop._f_p, drop._f_ticket
+    rg = res.requires_grad or a_t.requires_grad
+    def thunk():
+        if len(res.shape) not in (2, 3):
+            return b200.dropout_apply(a_t.data, p, ticket, residual=res.data)
+        y, planes = b200.dropout_apply(a_t.data, p, ticket, residual=res.data, want_planes=True)
+        out._b200_xst = planes  # the last residual sum of the stack feeds fc_out directly
+        return y
+    out = _Deferred.make(thunk, res.shape, (res, a_t, drop.args[1]) if rg else None, "add_dropout", rg,
+                         _f_kind="add_dropout", _f_x=res, _f_a=a_t, _f_p=p, _f_ticket=ticket)
+
+    def grad_fn(xr, a, mask, grad):
+        if xr.requires_grad:
+            xr.apply_grad(grad)
+        if a.requires_grad:
+            a.apply_grad(b200.dropout_apply(grad, mask.p, mask.ticket))
+    out.grad_fn = grad_fn
+    return out
+
+
+def _try_fused_attention(attn, v):
+    """`matmul(dropout(softmax(where(mask, fill, (q @ kT) / scale))), v)` with every intermediate still pending
+    -> ONE kernel (neunet.b200.attention_forward); None when the pattern or the size limits do not match."""
+    if not _pending(attn):
+        return None
+    p, ticket, sm = 0.0, None, attn
+    if attn._f_kind == "dropout":
+        p, ticket, sm = attn._f_p, attn._f_ticket, attn._f_src
+    if not _pending(sm, "softmax"):
+        return None
+    src = sm._f_src
+    mask, fill = None, 0.0
+    if _pending(src, "where"):
+        cond, fill = src._f_cond, src._f_fill
+        src = src._f_src
+        if _pending(cond, "eq_scalar"):
+            base = cond._f_base.data
+            mask = (base, 2 if base.dtype == _be.torch.int32 else 3, cond._f_value)
+        else:
+            mask = (cond.data, 1, 0.0)
+    scale = 1.0
+    if _pending(src, "div"):
+        scale, src = src._f_c, src._f_src
+    if not _pending(src, "matmul"):
+        return None
+    q_t, kt_t = src._f_a, src._f_b
+    if not (q_t.ndim == 4 and kt_t.ndim == 4 and v.ndim == 4):
+        return None
+    B, H, Tq, D = q_t.shape
+    Tk = kt_t.shape[3]
+    if kt_t.shape != (B, H, D, Tk) or v.shape != (B, H, Tk, D) or attn.shape != (B, H, Tq, Tk):
+        return None
+    from . import b200
+    if not b200.attention_supported(Tq, Tk, D):
+        return None
+    if mask is not None:
+        ms = tuple(mask[0].shape)
+        if len(ms) > 4 or any(a != 1 and a != b for a, b in zip(ms[::-1], (B, H, Tq, Tk)[::-1])):
+            return None
+    out, attn_data, planes = b200.attention_forward(q_t.data, kt_t.data, v.data, mask, fill, scale, p, ticket,
+                                                    want_planes=True)
+    attn.data = attn_data  # what the example returns as `attn`: delivered by the fused kernel
+    rg = q_t.requires_grad or kt_t.requires_grad or v.requires_grad
+    node = Tensor._wrap(out, (q_t, kt_t, v) if rg else None, "attention", rg, "cuda", cast=False)
+    node._b200_xst = planes
+    if rg:
+        def grad_fn(q, kt, vv, grad):
+            dq, dkt, dv = b200.attention_backward(q.data, kt.data, vv.data, mask, fill, scale, p, ticket, grad)
+            if q.requires_grad:
+                q.apply_grad(dq)
+            if kt.requires_grad:
+                kt.apply_grad(dkt)
+            if vv.requires_grad:
+                vv.apply_grad(dv)
+        node.grad_fn = grad_fn
+    return node
 
 
 def _assign_last_wins(full, index, grad):

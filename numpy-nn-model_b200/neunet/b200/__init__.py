@@ -115,6 +115,22 @@ _SIGNATURES = {
                                       POINTER(c_int), c_void_p]),
     "nnb_dropout": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_uint64, c_uint32, c_uint64, c_void_p, c_void_p]),
     "nnb_rng_advance": (c_int, [c_void_p, c_void_p]),
+    "nnb_dropout_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_uint64, c_uint32, c_uint64,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "nnb_rmsnorm_forward_fused": (c_int, [c_void_p, c_void_p, c_float, c_uint64, c_uint32, c_uint64, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                          c_float, c_void_p]),
+    "nnb_rmsnorm_backward_acc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "nnb_attention_supported": (c_int, [c_int64, c_int64, c_int64]),
+    "nnb_attention_forward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
+                                      c_void_p, c_int, c_float, POINTER(c_int64), c_float, c_float, c_float, c_uint64,
+                                      c_uint32, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                      c_int64, c_int64, c_int64, c_void_p]),
+    "nnb_attention_backward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
+                                       c_void_p, c_int, c_float, POINTER(c_int64), c_float, c_float, c_float, c_uint64,
+                                       c_uint32, c_uint64, c_void_p, c_void_p, POINTER(c_int64), c_void_p, c_void_p,
+                                       c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "nnb_cross_entropy_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
     "nnb_cross_entropy_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
@@ -557,21 +573,59 @@ def softmax_backward(y, grad, axis=-1):
     return dx
 
 
-def rmsnorm_forward(x, w, b=None, eps=1e-6):
-    """Returns (Y, X_std) with X_std shaped (..., 1). X_norm is not materialised: the backward
-    recomputes X / X_std (one fewer [rows, cols] round-trip through HBM)."""
+def planes_key(t2d, prec=None):
+    """Cache key under which `linear_forward` looks for ready-made bf16 planes of a [M, K] activation."""
+    M, K = t2d.shape
+    return (t2d.data_ptr(), t2d._version, _state["prec"] if prec is None else prec, int(M), int(K), _cache_scope())
+
+
+def _new_planes(rows, cols):
+    """(buffer, prec) for the bf16 planes of a [rows, cols] activation, or (None, prec) when TMA cannot tile it."""
+    prec = _state["prec"]
+    if cols % 8 != 0:
+        return None, prec
+    buf = torch.empty(lib().nnb_weight_staged_bytes(rows, cols, prec), dtype=torch.uint8, device="cuda")
+    buf._b200_prec = prec
+    return buf, prec
+
+
+def rmsnorm_forward(x, w, b=None, eps=1e-6, add_dropout=None, want_planes=False):
+    """Returns (Y, X_std, S, planes): X_std shaped (..., 1); X_norm is not materialised (the backward recomputes
+    X / X_std). add_dropout = (a, p, ticket): the norm runs on S = x + dropout(a) and S is returned (else None).
+    planes: ((key, buffer) for `linear_forward`'s operand cache) when want_planes and the fused kernel applies."""
     require_device()
     x = _f32c(x)
     cols = x.shape[-1]
     rows = x.numel() // cols
     y = torch.empty_like(x)
     std = torch.empty(x.shape[:-1] + (1,), dtype=torch.float32, device="cuda")
-    _check(lib().nnb_rmsnorm_forward(_ptr(x), _ptr(_f32c(w)), _ptr(_f32c(b)) if b is not None else None, _ptr(y),
-                                     _ptr(std), None, rows, cols, float(eps), _stream()), "nnb_rmsnorm_forward")
-    return y, std
+    w, b = _f32c(w), (_f32c(b) if b is not None else None)
+    fusable = cols <= 1024 and cols % 4 == 0 and x.data_ptr() % 16 == 0
+    if not fusable:
+        if add_dropout is not None:
+            a, p, ticket = add_dropout
+            x = dropout_apply(a, p, ticket, residual=x)
+            s_out = x
+        else:
+            s_out = None
+        _check(lib().nnb_rmsnorm_forward(_ptr(x), _ptr(w), _ptr(b), _ptr(y), _ptr(std), None, rows, cols, float(eps),
+                                         _stream()), "nnb_rmsnorm_forward")
+        return y, std, s_out, None
+    buf, prec = _new_planes(rows, cols) if want_planes else (None, _state["prec"])
+    a_t, s_out, p, seed, call_id, epoch, dev = None, None, 0.0, 0, 0, 0, None
+    if add_dropout is not None:
+        a_t, p, (seed, call_id, epoch, dev) = add_dropout
+        a_t = _f32c(a_t)
+        s_out = torch.empty_like(x)
+    _check(lib().nnb_rmsnorm_forward_fused(_ptr(x), _ptr(a_t), float(p), seed, call_id, epoch, _ptr(dev), _ptr(s_out), _ptr(w),
+                                           _ptr(b), _ptr(y), _ptr(std), _ptr(buf), prec, rows, cols, float(eps), _stream()),
+           "nnb_rmsnorm_forward_fused")
+    planes = (planes_key(y.reshape(rows, cols), prec), buf) if buf is not None else None
+    return y, std, s_out, planes
 
 
-def rmsnorm_backward(grad, x, w, std, need_db=False):
+def rmsnorm_backward(grad, x, w, std, need_db=False, dx_add=None):
+    """dx_add: gradient the input already holds (same shape); the kernel returns dx_add + dX in one pass."""
     require_device()
     L = lib()
     x, grad = _f32c(x), _f32c(grad)
@@ -581,9 +635,14 @@ def rmsnorm_backward(grad, x, w, std, need_db=False):
     dw = torch.empty((cols,), dtype=torch.float32, device="cuda")
     db = torch.empty((cols,), dtype=torch.float32, device="cuda") if need_db else None
     ws = _workspace(L.nnb_rmsnorm_workspace_bytes(rows, cols))
-    _check(L.nnb_rmsnorm_backward(_ptr(grad), _ptr(x), _ptr(_f32c(w)), _ptr(_f32c(std)), None, _ptr(dx), _ptr(dw),
-                                  _ptr(db), rows, cols, _ptr(ws), ws.numel(), _stream()), "nnb_rmsnorm_backward")
-    return dx, dw, db
+    if dx_add is not None and not (cols <= 1024 and cols % 4 == 0 and tuple(dx_add.shape) == tuple(x.shape)):
+        dx_add = None
+    if dx_add is not None:
+        dx_add = _f32c(dx_add)
+    _check(L.nnb_rmsnorm_backward_acc(_ptr(grad), _ptr(x), _ptr(_f32c(w)), _ptr(_f32c(std)), None, _ptr(dx_add), _ptr(dx),
+                                      _ptr(dw), _ptr(db), rows, cols, _ptr(ws), ws.numel(), _stream()),
+           "nnb_rmsnorm_backward")
+    return dx, dw, db, dx_add is not None
 
 
 # ---- fused CrossEntropyLoss ---------------------------------------------------------------------------------------
@@ -628,15 +687,83 @@ def dropout_ticket():
     return (_rng["seed"], 0, (1 << 62) + _rng["epoch"], None)
 
 
-def dropout_apply(x, p, ticket):
-    """y = x * mask(ticket) / (1 - p): forward on activations, backward on the upstream gradient."""
+def dropout_apply(x, p, ticket, residual=None, want_planes=False):
+    """y = (residual +) x * mask(ticket) / (1 - p): forward on activations, backward on the upstream gradient.
+    With want_planes returns (y, planes) where planes = (key, buffer) for `linear_forward`'s operand cache."""
     require_device()
     x = _f32c(x)
     y = torch.empty_like(x)
     seed, call_id, epoch, dev = ticket
-    _check(lib().nnb_dropout(_ptr(x), _ptr(y), x.numel(), float(p), seed, call_id, epoch, _ptr(dev), _stream()),
-           "nnb_dropout")
+    cols = x.shape[-1] if x.ndim >= 1 and x.numel() else 1
+    rows = x.numel() // max(cols, 1)
+    buf, prec = (None, _state["prec"])
+    if want_planes and x.ndim >= 2:
+        buf, prec = _new_planes(rows, cols)
+    if residual is not None:
+        residual = _f32c(residual)
+        if tuple(residual.shape) != tuple(x.shape):
+            raise ValueError("dropout_apply: residual must have the shape of x")
+    if x.numel():
+        _check(lib().nnb_dropout_fused(_ptr(x), _ptr(residual), _ptr(y), rows, cols, float(p), seed, call_id, epoch, _ptr(dev),
+                                       _ptr(buf), prec, _stream()), "nnb_dropout_fused")
+    if want_planes:
+        return y, ((planes_key(y.reshape(rows, cols), prec), buf) if buf is not None else None)
     return y
+
+
+# ---- fused attention (short sequences) -------------------------------------------------------------------------
+def attention_supported(Tq, Tk, D):
+    return bool(lib().nnb_attention_supported(int(Tq), int(Tk), int(D)))
+
+
+def _mask_args(mask, shape4):
+    """mask = None or (tensor, kind, cmp): broadcast strides over (B, H, Tq, Tk)."""
+    if mask is None:
+        return None, 0, 0.0, None, None
+    t, kind, cmp = mask
+    want = torch.int32 if kind == 2 else torch.float32
+    if t.dtype != want:
+        t = t.to(want)
+    t = t.expand(shape4)
+    return t, kind, float(cmp), _I64x4(*[int(v) for v in t.stride()]), t
+
+
+def attention_forward(q, kT, v, mask, fill, scale, p, ticket, want_planes=False):
+    """q (B,H,Tq,D), kT (B,H,D,Tk), v (B,H,Tk,D): any strides. Returns (out, attn, planes): out is a (B,H,Tq,D)
+    VIEW of a (B,Tq,H,D)-contiguous buffer (so `.transpose(0,2,1,3).reshape(B,Tq,H*D)` is free), attn is the
+    post-dropout (B,H,Tq,Tk) tensor the example returns."""
+    require_device()
+    B, H, Tq, D = q.shape
+    Tk = kT.shape[3]
+    out = torch.empty((B, Tq, H, D), dtype=torch.float32, device="cuda")
+    attn = torch.empty((B, H, Tq, Tk), dtype=torch.float32, device="cuda")
+    buf, prec = _new_planes(B * Tq, H * D) if want_planes else (None, _state["prec"])
+    mt, kind, cmp, ms, _keep = _mask_args(mask, (B, H, Tq, Tk))
+    seed, call_id, epoch, dev = ticket if ticket is not None else (0, 0, 0, None)
+    _check(lib().nnb_attention_forward(_ptr(q), _strides4(q), _ptr(kT), _strides4(kT), _ptr(v), _strides4(v), _ptr(mt), kind,
+                                       cmp, ms, float(fill), float(scale), float(p), seed, call_id, epoch, _ptr(dev),
+                                       _ptr(attn), _ptr(out), _ptr(buf), prec, B, H, Tq, Tk, D, _stream()),
+           "nnb_attention_forward")
+    planes = (planes_key(out.reshape(B * Tq, H * D), prec), buf) if buf is not None else None
+    return out.permute(0, 2, 1, 3), attn, planes
+
+
+def attention_backward(q, kT, v, mask, fill, scale, p, ticket, grad):
+    """Returns (dq, dkT, dv) shaped like q, kT, v: views of (B,T,H,D)-contiguous buffers."""
+    require_device()
+    B, H, Tq, D = q.shape
+    Tk = kT.shape[3]
+    grad = grad if grad.dtype == torch.float32 else grad.to(torch.float32)
+    dq = torch.empty((B, Tq, H, D), dtype=torch.float32, device="cuda")
+    dk = torch.empty((B, Tk, H, D), dtype=torch.float32, device="cuda")
+    dv = torch.empty((B, Tk, H, D), dtype=torch.float32, device="cuda")
+    mt, kind, cmp, ms, _keep = _mask_args(mask, (B, H, Tq, Tk))
+    seed, call_id, epoch, dev = ticket if ticket is not None else (0, 0, 0, None)
+    _check(lib().nnb_attention_backward(_ptr(q), _strides4(q), _ptr(kT), _strides4(kT), _ptr(v), _strides4(v), _ptr(mt), kind,
+                                        cmp, ms, float(fill), float(scale), float(p), seed, call_id, epoch, _ptr(dev),
+                                        _ptr(grad), _strides4(grad), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Tq, Tk, D,
+                                        _stream()), "nnb_attention_backward")
+    return dq.permute(0, 2, 1, 3), dk.permute(0, 2, 3, 1), dv.permute(0, 2, 1, 3)
 
 
 def cross_entropy_forward(logits, targets, ignore_index=-100, reduction="mean"):

@@ -38,6 +38,11 @@ class Swish(Module):
     def forward(self, x: Tensor):
         if x.device == "cuda":
             from .. import b200
+            from ..autograd import _pending
+            if _pending(x, "linear") and not x._f_act:
+                # Swish directly on a not-yet-launched nn.Linear: it becomes the GEMM's epilogue (one kernel, and
+                # swish' is folded into the dO staging pass of the backward), exactly like nn.LinearSwish
+                return x._f_fuse_swish(float(self.beta))
             f_x = b200.swish_forward(x.data, self.beta)
         else:
             f_x = x.data * _sigmoid(np, self.beta * x.data)
@@ -63,6 +68,20 @@ class Softmax(Module):
     def forward(self, x: Tensor):
         if x.device == "cuda":
             from .. import b200
+            from ..autograd import _Deferred, _pending
+            if _pending(x) and x._f_kind in ("where", "div", "matmul") and self.axis in (-1, x.ndim - 1):
+                # softmax over pending attention scores stays pending (absorbed by the fused attention kernel)
+                axis, held = self.axis, {}
+
+                def thunk():
+                    held["y"] = b200.softmax_forward(x.data, axis)
+                    return held["y"]
+
+                def grad_fn(t, grad):
+                    t.apply_grad(b200.softmax_backward(held["y"] if "y" in held else out.data, grad, axis))
+                out = _Deferred.make(thunk, x.shape, [x], "softmax", True, _f_kind="softmax", _f_src=x)
+                out.grad_fn = grad_fn
+                return out
             f_x = b200.softmax_forward(x.data, self.axis)
         else:
             e = np.exp(x.data - np.max(x.data, axis=self.axis, keepdims=True))

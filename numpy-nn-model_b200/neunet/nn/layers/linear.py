@@ -51,6 +51,52 @@ def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, x_staged, gra
         bias.apply_grad(np.sum(grad, axis=0, keepdims=True))
 
 
+def _deferred_linear(layer, X: Tensor) -> Tensor:
+    """``Linear.forward`` on "cuda" with fusion on: the result is *pending* (neunet/autograd.py, deferred
+    evaluation). The GEMM is launched when the output is first read -- together with every other pending
+    Linear on the same input (the q/k/v projections of one RMSNorm output run back to back on the same staged
+    operand) -- unless an ``nn.Swish`` consumes it first, in which case Swish becomes the GEMM's epilogue."""
+    from ... import b200
+    from ...autograd import _Deferred
+    W, b = layer.weight, layer.bias
+    act0, beta0, training = layer._act, layer._beta, layer.training_mode()
+
+    def run(act, beta):
+        return b200.linear_forward(X.data, W.data, b.data if b is not None else None, act=act, beta=beta,
+                                   save_z=bool(act), owner=W, keep_x_staged=training, x_owner=X)
+
+    def thunk():
+        sibs = X.__dict__.get("_b200_pending_lin")
+        if sibs:  # launch the siblings right behind this one: same X planes, still hot in L2
+            X.__dict__["_b200_pending_lin"] = None
+        O, Z, xst = run(act0, beta0)
+        out.args = (X, W, b, Z, act0, beta0, xst)
+        out.data = O
+        if sibs:
+            for sib in sibs:
+                if sib is not out and sib._data is None:
+                    sib.data  # noqa: B018 -- forces the sibling's GEMM
+        return O
+
+    def fuse_swish(beta):
+        O, Z, xst = run(1, beta)
+        out.args = (X, W, b, None, 0, 1.0, xst)
+        out.data = Z  # the pre-activation is the GEMM's side output: the Linear result itself is delivered for free
+        return _LinearTensor(O, (X, W, b, Z, 1, beta, xst), "linear_swish", "cuda")
+
+    out = _Deferred.make(thunk, tuple(X.shape[:-1]) + (layer.out_features,), (X, W, b, None, act0, beta0, None), "linear", True,
+                         _f_kind="linear", _f_act=act0, _f_fuse_swish=fuse_swish)
+    out.grad_fn = _linear_grad_fn
+    try:
+        lst = X.__dict__.get("_b200_pending_lin")
+        if lst is None:
+            lst = X.__dict__["_b200_pending_lin"] = []
+        lst.append(out)
+    except AttributeError:
+        pass
+    return out
+
+
 class Linear(Module):
     def __init__(self, in_features: int, out_features: int, bias: bool = True, device="cpu"):
         self.in_features = in_features
@@ -72,6 +118,9 @@ class Linear(Module):
         b = self.bias
         if self.device == "cuda":
             from ... import b200
+            from ...autograd import fusion_enabled
+            if fusion_enabled():
+                return _deferred_linear(self, X)
             # the bf16 planes of X made for the forward GEMM are kept for wgrad (dW = dZ^T . X)
             O, Z, xst = b200.linear_forward(X.data, self.weight.data, b.data if b is not None else None,
                                             act=self._act, beta=self._beta, save_z=bool(self._act), owner=self.weight,

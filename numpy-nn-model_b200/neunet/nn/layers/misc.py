@@ -68,9 +68,32 @@ class Dropout(Module):
             raise TypeError("Input must be a tensor")
         if self.training and X.device == "cuda" and 0 <= self.p < 1:
             from ... import b200
-            mask = _DeviceMask(self.p, b200.dropout_ticket())
+            from ...autograd import _Deferred, fusion_enabled
+            mask = _DeviceMask(self.p, b200.dropout_ticket())  # the ticket is taken NOW: call order fixes the masks
+            if fusion_enabled():
+                # pending: `x + dropout(a)`, `norm(x + dropout(a))` and attention absorb it into their kernel
+                p, ticket, planes_ok = self.p, mask.ticket, X.ndim in (2, 3)
+
+                def thunk():
+                    if not planes_ok:
+                        return b200.dropout_apply(X.data, p, ticket)
+                    y, planes = b200.dropout_apply(X.data, p, ticket, want_planes=True)
+                    out._b200_xst = planes  # bf16 operand planes for a following nn.Linear
+                    return y
+                out = _Deferred.make(thunk, X.shape, (X, mask), "dropout", True, _f_kind="dropout", _f_src=X, _f_p=p,
+                                     _f_ticket=ticket)
+                out.grad_fn = _dropout_grad
+                return out
             return _StaticTensor(b200.dropout_apply(X.data, self.p, mask.ticket), (X, mask), "dropout", X.device,
                                  _dropout_grad)
+        if not self.training and X.device == "cuda":
+            from ...autograd import _Deferred, _pending
+            if _pending(X):
+                # eval mode: identity; a pending input (attention probabilities) stays pending so the fused kernel still applies
+                out = _Deferred.make(lambda: X.data, X.shape, (X, 1), "dropout", True, _f_kind="dropout", _f_src=X, _f_p=0.0,
+                                     _f_ticket=None)
+                out.grad_fn = _dropout_grad
+                return out
         if self.training:
             mask = X.xp.random.binomial(1, 1 - self.p, size=tuple(X.data.shape))
             mask = (mask.astype(np.float32) if isinstance(mask, np.ndarray) else mask) * self.scale

@@ -21,7 +21,16 @@ class _RMSNormTensor(Tensor):
 def _rmsnorm_grad_fn(X: Tensor, weight: Tensor, bias, X_std, grad):
     if X.device == "cuda":
         from ... import b200
-        dx, dw, db = b200.rmsnorm_backward(grad, X.data, weight.data, X_std, need_db=bias is not None)
+        # the gradient X already holds (residual branch) is accumulated by the same kernel: no separate add
+        prev = X.grad if (X.requires_grad and X.grad is not None and tuple(X.grad.shape) == tuple(X.data.shape)) else None
+        dx, dw, db, accumulated = b200.rmsnorm_backward(grad, X.data, weight.data, X_std, need_db=bias is not None,
+                                                        dx_add=prev)
+        if accumulated:
+            X.grad = dx
+            weight.apply_grad(dw)
+            if bias is not None:
+                bias.apply_grad(db)
+            return
     else:
         n = X.data.shape[-1]
         x = X.data
@@ -46,12 +55,25 @@ class RMSNorm(Module):
 
     def forward(self, X: Tensor) -> Tensor:
         b = self.bias
+        planes = None
         if X.device == "cuda":
             from ... import b200
-            O, std = b200.rmsnorm_forward(X.data, self.weight.data, b.data if b is not None else None, self.eps)
+            from ...autograd import _pending
+            bd = b.data if b is not None else None
+            if _pending(X, "add_dropout"):
+                # `x = x + dropout(a); norm(x)`: residual add, dropout and norm in one pass; the sum is delivered
+                # to the pending add node as a by-product
+                O, std, S, planes = b200.rmsnorm_forward(X._f_x.data, self.weight.data, bd, self.eps,
+                                                         add_dropout=(X._f_a.data, X._f_p, X._f_ticket), want_planes=True)
+                X.data = S
+            else:
+                O, std, _, planes = b200.rmsnorm_forward(X.data, self.weight.data, bd, self.eps, want_planes=True)
         else:
             std = np.sqrt(np.mean(X.data ** 2, -1, keepdims=True) + self.eps)
             O = X.data / std * self.weight.data
             if b is not None:
                 O = O + b.data
-        return _RMSNormTensor(O, (X, self.weight, b, std), "rmsnorm", X.device)
+        out = _RMSNormTensor(O, (X, self.weight, b, std), "rmsnorm", X.device)
+        if planes is not None:
+            out._b200_xst = planes  # bf16 operand planes for the nn.Linear layers that read this output
+        return out

@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU check of bench.py (round 2, call 1): heartbeat logs per rank, bounded by `timeout`; fallbacks only if the first fails.
 mkdir -p gpurun_out/n8
-export BENCH_HB_DIR=gpurun_out/n8 NCCL_DEBUG=WARN
+export BENCH_HB_DIR=gpurun_out/n8 NCCL_DEBUG=WARN NEUNET_B200_FUSE=0
 run() { # name, extra args
   name=$1; shift
   timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \

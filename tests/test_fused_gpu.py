@@ -1,0 +1,213 @@
+"""Fused kernels of round 2 on the B200, through the C-ABI: fused attention (forward + backward), dropout with
+residual / operand planes, RMSNorm with the residual-dropout prologue and operand planes, RMSNorm backward with
+gradient accumulation -- each against a plain torch fp32 composition of the reference's separate ops
+(examples/gpt.ipynb cell 2 l.25-40; neunet/nn/layers/dropout.py:17-46; rmsnorm.py:39-94) -- and, at model level, the
+fused (deferred) execution of the GPT example against the strictly eager one with the SAME dropout masks."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _b200():
+    from neunet import b200
+    b200.require_device()
+    return b200
+
+
+def _bf16_planes(buf, rows, cols, x3):
+    hi = buf[: rows * cols * 2].view(torch.bfloat16).reshape(rows, cols)
+    if not x3:
+        return hi.float()
+    off = ((rows * cols * 2 + 255) // 256) * 256
+    lo = buf[off: off + rows * cols * 2].view(torch.bfloat16).reshape(rows, cols)
+    return hi.float() + lo.float()
+
+
+def _ref_attention(q, kT, v, masked, fill, scale, keep):
+    s = torch.matmul(q, kT) / scale
+    if masked is not None:
+        s = torch.where(masked, torch.full((), fill, device=s.device), s)
+    p = torch.softmax(s, dim=-1)
+    a = p * keep
+    return a, torch.matmul(a, v)
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,D,mask_kind,p", [
+    (2, 3, 64, 64, 64, 2, 0.1),     # GPT shape, int mask tested against 0, dropout
+    (1, 2, 7, 12, 16, 1, 0.0),      # ragged tile, float condition tensor, no dropout
+    (3, 1, 33, 64, 32, 3, 0.25),    # float mask == value
+    (2, 2, 64, 64, 64, 0, 0.0),     # no mask at all
+])
+def test_attention_forward_backward_vs_torch(B, H, Tq, Tk, D, mask_kind, p):
+    b200 = _b200()
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + Tq)
+    # operands in the example's memory order: (B, T, H, D) buffers seen through transposed views
+    q = torch.randn(B, Tq, H, D, generator=g, device="cuda").permute(0, 2, 1, 3)
+    k = torch.randn(B, Tk, H, D, generator=g, device="cuda").permute(0, 2, 1, 3)
+    v = torch.randn(B, Tk, H, D, generator=g, device="cuda").permute(0, 2, 1, 3)
+    kT = k.permute(0, 1, 3, 2)
+    dO = torch.randn(B, Tq, H, D, generator=g, device="cuda").permute(0, 2, 1, 3)
+    causal = torch.tril(torch.ones(Tq, Tk, device="cuda"))
+    mask, masked = None, None
+    if mask_kind == 2:
+        base = causal.to(torch.int32).expand(B, 1, Tq, Tk).contiguous()
+        mask, masked = (base, 2, 0.0), (base == 0).expand(B, H, Tq, Tk)
+    elif mask_kind == 1:
+        cond = (causal == 0).float().expand(B, 1, Tq, Tk).contiguous()
+        mask, masked = (cond, 1, 0.0), (cond != 0).expand(B, H, Tq, Tk)
+    elif mask_kind == 3:
+        base = (causal * 5.0).expand(B, 1, Tq, Tk).contiguous()
+        mask, masked = (base, 3, 0.0), (base == 0).expand(B, H, Tq, Tk)
+    ticket = (1234, 7, 99, None)
+    keep = torch.ones(B, H, Tq, Tk, device="cuda")
+    if p > 0:
+        keep = b200.dropout_apply(keep, p, ticket)  # the same Philox ticket regenerates the same mask
+    scale, fill = float(np.sqrt(H * D)), -1e9
+    out, attn, planes = b200.attention_forward(q, kT, v, mask, fill, scale, p, ticket if p > 0 else None, want_planes=True)
+    a_ref, o_ref = _ref_attention(q, kT, v, masked, fill, scale, keep)
+    assert out.shape == (B, H, Tq, D) and out.permute(0, 2, 1, 3).is_contiguous()
+    assert (attn - a_ref).abs().max().item() <= 1e-5
+    assert (out - o_ref).abs().max().item() <= 1e-5 * max(1.0, o_ref.abs().max().item())
+    got = _bf16_planes(planes[1], B * Tq, H * D, b200.get_precision() == "bf16x3")
+    want = out.permute(0, 2, 1, 3).reshape(B * Tq, H * D)
+    assert (got - want).abs().max().item() <= (1e-4 if b200.get_precision() == "bf16x3" else 2e-2) * max(1.0, want.abs().max().item())
+    # backward against torch autograd on the same composition
+    ql, kl, vl = (t.detach().clone().requires_grad_(True) for t in (q, kT, v))
+    _, o2 = _ref_attention(ql, kl, vl, masked, fill, scale, keep)
+    o2.backward(dO)
+    dq, dkT, dv = b200.attention_backward(q, kT, v, mask, fill, scale, p, ticket if p > 0 else None, dO)
+    for got, want in ((dq, ql.grad), (dkT, kl.grad), (dv, vl.grad)):
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    assert dq.permute(0, 2, 1, 3).is_contiguous() and dkT.permute(0, 3, 1, 2).is_contiguous()
+
+
+def test_attention_rejects_unsupported_sizes():
+    b200 = _b200()
+    assert b200.attention_supported(64, 64, 64) and not b200.attention_supported(65, 64, 64)
+    assert not b200.attention_supported(8, 10, 16)  # Tk % 4 != 0
+    q = torch.randn(1, 1, 80, 16, device="cuda")
+    with pytest.raises(RuntimeError):
+        b200.attention_forward(q, q.permute(0, 1, 3, 2), q, None, 0.0, 1.0, 0.0, None)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+def test_dropout_residual_and_planes(prec):
+    b200 = _b200()
+    with b200.precision(prec):
+        x = torch.randn(6, 40, 64, device="cuda")
+        r = torch.randn(6, 40, 64, device="cuda")
+        ticket = (5, 2, 17, None)
+        plain = b200.dropout_apply(x, 0.3, ticket)
+        y, planes = b200.dropout_apply(x, 0.3, ticket, residual=r, want_planes=True)
+        assert torch.equal(y, plain + r)
+        frac = (plain == 0).float().mean().item()
+        assert 0.25 < frac < 0.35
+        got = _bf16_planes(planes[1], 240, 64, prec == "bf16x3")
+        assert (got - y.reshape(240, 64)).abs().max().item() <= (1e-4 if prec == "bf16x3" else 4e-2)
+        assert planes[0] == b200.planes_key(y.reshape(240, 64))
+
+
+@pytest.mark.parametrize("cols,with_bias", [(512, False), (96, True), (1024, False)])
+def test_rmsnorm_fused_forward_backward(cols, with_bias):
+    b200 = _b200()
+    rows = 300
+    x = torch.randn(rows, cols, device="cuda")
+    a = torch.randn(rows, cols, device="cuda")
+    w = torch.rand(cols, device="cuda") + 0.5
+    b = torch.randn(cols, device="cuda") if with_bias else None
+    ticket = (77, 1, 3, None)
+    s_ref = b200.dropout_apply(a, 0.1, ticket, residual=x)
+    y0, std0, _, _ = b200.rmsnorm_forward(s_ref, w, b, 1e-6)
+    y, std, s, planes = b200.rmsnorm_forward(x, w, b, 1e-6, add_dropout=(a, 0.1, ticket), want_planes=True)
+    assert torch.equal(s, s_ref)
+    ref = s_ref / torch.sqrt((s_ref * s_ref).mean(-1, keepdim=True) + 1e-6) * w + (b if b is not None else 0)
+    assert (y - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    assert (y - y0).abs().max().item() <= 1e-6 * max(1.0, ref.abs().max().item())
+    assert (std - std0).abs().max().item() <= 1e-6
+    got = _bf16_planes(planes[1], rows, cols, b200.get_precision() == "bf16x3")
+    assert (got - y).abs().max().item() <= (1e-4 if b200.get_precision() == "bf16x3" else 4e-2) * max(1.0, y.abs().max().item())
+    g = torch.randn(rows, cols, device="cuda")
+    prev = torch.randn(rows, cols, device="cuda")
+    dx0, dw0, db0, acc0 = b200.rmsnorm_backward(g, s, w, std, need_db=with_bias)
+    dx1, dw1, db1, acc1 = b200.rmsnorm_backward(g, s, w, std, need_db=with_bias, dx_add=prev)
+    assert not acc0 and acc1
+    assert (dx1 - (dx0 + prev)).abs().max().item() <= 1e-6 * max(1.0, dx0.abs().max().item())
+    assert torch.equal(dw0, dw1)
+
+
+def _gpt_step(fuse, dropout, prec="bf16x3", sizes=None):
+    import models as M
+    import neunet
+    import neunet.nn as nn
+    from neunet import autograd, b200
+    sizes = sizes or dict(vocab=120, d_model=64, n_heads=4, d_ff=128, n_layers=2)
+    np.random.seed(5)
+    model = M.build_gpt(neunet, nn, pad_idx=0, device="cuda", dropout=dropout, **sizes)
+    model.train()
+    rng = np.random.RandomState(1)
+    batch = rng.randint(1, sizes["vocab"], (4, 17))
+    batch[1, -3:] = 0
+    prev = autograd.set_fusion(fuse)
+    try:
+        b200.manual_seed(99)
+        b200.reset_launch_count()
+        with b200.precision(prec):
+            loss_fn = nn.CrossEntropyLoss(ignore_index=0)
+            out, attn = model.forward(batch[:, :-1])
+            logits = out.reshape(out.shape[0] * out.shape[1], out.shape[2])
+            loss = loss_fn(logits, neunet.tensor(batch[:, 1:].flatten(), device="cuda", dtype=neunet.int32))
+            loss.backward()
+        torch.cuda.synchronize()
+        return (float(loss.data.item()), out.data.clone(), attn.data.clone(),
+                [None if p.grad is None else p.grad.clone() for p in model.parameters()], b200.launch_count())
+    finally:
+        autograd.set_fusion(prev)
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_gpt_fused_execution_equals_eager_with_same_masks(dropout):
+    """Same seeds -> same Philox tickets in the same order -> identical masks: the deferred/fused step must reproduce
+    the eager step to contraction round-off (bf16x3; max-norm relative error)."""
+    eager = _gpt_step(False, dropout)
+    fused = _gpt_step(True, dropout)
+    assert abs(eager[0] - fused[0]) <= 1e-4 * abs(eager[0])
+    for got, want in ((fused[1], eager[1]), (fused[2], eager[2])):
+        assert (got - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1e-3)
+    for got, want in zip(fused[3], eager[3]):
+        assert (got is None) == (want is None)
+        if got is not None:
+            assert (got - want).abs().max().item() <= 2e-4 * max(want.abs().max().item(), 1e-3)
+    assert fused[4] < eager[4]  # fewer native launches, and none of the array back-end's where/div/copy kernels in between
+
+
+def test_fused_step_captures_into_a_cuda_graph():
+    import models as M
+    import neunet
+    import neunet.nn as nn
+    from neunet import b200, optim
+    np.random.seed(2)
+    model = M.build_gpt(neunet, nn, vocab=64, d_model=64, n_heads=4, d_ff=128, n_layers=1, pad_idx=0, device="cuda", dropout=0.1)
+    model.train()
+    opt = optim.Adam(model.parameters(), lr=1e-3)
+    loss_fn = nn.CrossEntropyLoss(ignore_index=0)
+    T = 16
+    ids = neunet.tensor(np.random.randint(1, 64, (2, T)), dtype=np.int32, device="cuda")
+    tgt = neunet.tensor(np.random.randint(1, 64, (2 * T,)), dtype=np.int32, device="cuda")
+    mask = neunet.tensor(np.broadcast_to(np.tril(np.ones((T, T))), (2, T, T)).copy(), dtype=np.int32, device="cuda")
+
+    def step(i, t):
+        opt.zero_grad()
+        out, _ = model.decoder(i, mask)
+        loss = loss_fn(out.reshape(2 * T, 64), t)
+        loss.backward()
+        opt.step()
+        return loss
+    with b200.precision("bf16"):
+        for _ in range(2):
+            step(ids, tgt)
+        g = b200.GraphedStep(step, [ids, tgt], optimizer=opt, warmup=1)
+        losses = [float(g.replay().item()) for _ in range(5)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
