@@ -502,24 +502,27 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         wall = time.perf_counter() - wall0
-        # keep the GPU busy a little longer so nvidia-smi (100 ms period) sees clocks under this load
-        t_end = time.perf_counter() + 1.0
-        while time.perf_counter() < t_end:
+        if flush is not None:
+            dev_s = sum(a.elapsed_time(b) for a, b in ev) / 1e3  # the flush kernels sit between the per-step event pairs
+        else:
+            dev_s = ev[0][0].elapsed_time(ev[K - 1][1]) / 1e3    # first start -> last end: K whole steps back to back
+        t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t.item())
+        # keep the GPU busy ~1 s longer so nvidia-smi (100 ms period) sees clocks under this load. The number of
+        # extra steps is derived from the AGREED (max over ranks) step time: every step contains collectives, so
+        # all ranks must run the same count (round 1 looped on each rank's own clock here and hung at 8 GPUs).
+        hb("clock-sampling tail")
+        for _ in range(int(min(2000, max(1, round(1.0 / max(dev_s / K, 1e-5)))))):
             one_step()
-        torch.cuda.synchronize()
-    if flush is not None:
-        dev_s = sum(a.elapsed_time(b) for a, b in ev) / 1e3  # the flush kernels sit between the per-step event pairs
-    else:
-        dev_s = ev[0][0].elapsed_time(ev[K - 1][1]) / 1e3    # first start -> last end: K whole steps back to back
+        barrier()
     # launches per step: count one eager step (graph replays do not pass through the counter)
+    hb("launch count (one eager step)")
     b200.reset_launch_count()
     train_step(*wl.inputs)
     torch.cuda.synchronize()
     launches_per_step = b200.launch_count()
-    t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s = float(t.item())
     value = B * world * K / dev_s
 
     hb("e2e")

@@ -109,17 +109,20 @@ def gpt_train_step(neunet, nn, model, optimizer, batch, pad_idx=0):
     return loss, logits
 
 
-def build_conv_classifier(neunet, nn, device="cpu", side=12):
-    """Conv(1->4) LeakyReLU MaxPool Conv(4->6) LeakyReLU MaxPool BatchNorm2d flatten Linear Sigmoid
-    (README.md:227-258 scaled from 28x28 / 8,16 channels)."""
+def build_conv_classifier(neunet, nn, device="cpu", side=12, channels=(4, 6)):
+    """Conv(1->c1) LeakyReLU MaxPool Conv(c1->c2) LeakyReLU MaxPool BatchNorm2d flatten Linear Sigmoid
+    (README.md:227-258; the README / notebook model is side=28, channels=(8, 16); the default is a scaled-down copy
+    the reference finishes in seconds)."""
+    c1, c2 = channels
+
     class Net(nn.Module):
         def __init__(self):
-            self.conv1 = nn.Conv2d(1, 4, 3, 1, 1)
-            self.conv2 = nn.Conv2d(4, 6, 3, 1, 1)
+            self.conv1 = nn.Conv2d(1, c1, 3, 1, 1)
+            self.conv2 = nn.Conv2d(c1, c2, 3, 1, 1)
             self.act = nn.LeakyReLU()
             self.pool = nn.MaxPool2d(2, 2)
-            self.bn = nn.BatchNorm2d(6)
-            self.fc = nn.Linear(6 * (side // 4) ** 2, 10)
+            self.bn = nn.BatchNorm2d(c2)
+            self.fc = nn.Linear(c2 * (side // 4) ** 2, 10)
             self.out = nn.Sigmoid()
 
         def forward(self, x):
@@ -167,3 +170,93 @@ def build_unet(neunet, nn, device="cpu", ch=(8, 16), temb=8):
             return self.output_conv(u)
 
     return UNet().to(device)
+
+
+def build_ddpm_unet(neunet, nn, device="cpu", image_channels=3, image_size=32, down_channels=(128, 256, 512, 1024),
+                    up_channels=(1024, 512, 256, 128), time_emb_dim=32):
+    """examples/ddpm.ipynb cells 5-7 verbatim in structure (ResBlock, sinusoidal time encoding, SimpleUNet): for a
+    power-of-two image size the input layer is Conv2d 3x3 p1, every down block ends in Conv2d 4x4 s2 p1, every up block
+    takes the skip-concatenated input and ends in ConvTranspose2d 4x4 s2 p1, the output layer is ConvTranspose2d 3x3 p1.
+    Defaults = cell 8 (3x32x32, down (128,256,512,1024), up (1024,512,256,128))."""
+    class ResBlock(nn.Module):
+        def __init__(self, cin, cout, up=False):
+            self.time_embedding = nn.Linear(time_emb_dim, cout)
+            if up:
+                self.conv1 = nn.Conv2d(2 * cin, cout, kernel_size=(3, 3), padding=(1, 1))
+                self.transform = nn.ConvTranspose2d(cout, cout, kernel_size=(4, 4), stride=(2, 2), padding=(1, 1))
+            else:
+                self.conv1 = nn.Conv2d(cin, cout, kernel_size=(3, 3), padding=(1, 1))
+                self.transform = nn.Conv2d(cout, cout, kernel_size=(4, 4), stride=(2, 2), padding=(1, 1))
+            self.conv2 = nn.Conv2d(cout, cout, kernel_size=(3, 3), padding=(1, 1))
+            self.relu1, self.relu2, self.relu3 = nn.LeakyReLU(alpha=0.01), nn.LeakyReLU(alpha=0.01), nn.LeakyReLU(alpha=0.01)
+            self.bnorm1 = nn.BatchNorm2d(cout, momentum=0.1, eps=1e-5)
+            self.bnorm2 = nn.BatchNorm2d(cout, momentum=0.1, eps=1e-5)
+
+        def forward(self, x, t):
+            x = self.conv1.forward(x)
+            h = self.relu1.forward(x)
+            h = self.bnorm1.forward(h)
+            t = self.time_embedding.forward(t)
+            time_emb = self.relu2.forward(t)
+            time_emb = time_emb[(...,) + (None,) * 2]
+            h = h + time_emb
+            h = self.conv2.forward(h)
+            h = self.relu3.forward(h)
+            h = self.bnorm2.forward(h)
+            return self.transform.forward(h)
+
+    class TimeEncoding(nn.Module):
+        def __init__(self, max_len, d_model):
+            pe = np.zeros((max_len, d_model))
+            position = np.arange(0, max_len)[:, np.newaxis]
+            div_term = np.exp(np.arange(0, d_model, 2) * (-np.log(10000.0) / d_model))
+            pe[:, 0::2] = np.sin(position * div_term)
+            pe[:, 1::2] = np.cos(position * div_term)
+            self.pe = neunet.tensor(pe[:, np.newaxis, :].astype(np.float32), requires_grad=False, device=device)
+
+        def forward(self, x):
+            return x + self.pe[: x.shape[0], :]
+
+    class SimpleUNet(nn.Module):
+        def __init__(self):
+            self.time_embedding = nn.Sequential(TimeEncoding(1000, time_emb_dim), nn.Linear(time_emb_dim, time_emb_dim),
+                                                nn.LeakyReLU())
+            if image_size & (image_size - 1) != 0:
+                self.input_conv = nn.ConvTranspose2d(image_channels, down_channels[0], kernel_size=(5, 5))
+                self.output_conv = nn.Conv2d(up_channels[-1], image_channels, kernel_size=(5, 5))
+            else:
+                self.input_conv = nn.Conv2d(image_channels, down_channels[0], kernel_size=(3, 3), padding=(1, 1))
+                self.output_conv = nn.ConvTranspose2d(up_channels[-1], image_channels, kernel_size=(3, 3), padding=(1, 1))
+            self.down_layers = nn.ModuleList([ResBlock(down_channels[i], down_channels[i + 1])
+                                              for i in range(len(down_channels) - 1)])
+            self.up_layers = nn.ModuleList([ResBlock(up_channels[i], up_channels[i + 1], up=True)
+                                            for i in range(len(up_channels) - 1)])
+
+        def forward(self, x, t):
+            if not isinstance(t, neunet.Tensor):
+                t = neunet.tensor(np.asarray(t, dtype=np.float32)[:, None, None], requires_grad=False, device=x.device)
+            t = self.time_embedding.forward(t)
+            t = t.reshape(t.shape[0], -1)
+            x = self.input_conv.forward(x)
+            residual_inputs = []
+            for down_layer in self.down_layers:
+                x = down_layer.forward(x, t)
+                residual_inputs.append(x)
+            for up_layer in self.up_layers:
+                residual_x = residual_inputs.pop()
+                x = neunet.concatenate(*(x, residual_x), axis=1)
+                x = up_layer.forward(x, t)
+            return self.output_conv.forward(x)
+
+    return SimpleUNet().to(device)
+
+
+def ddpm_train_step(neunet, nn, model, optimizer, x0, noise, t_frac, a_bar_sqrt, one_minus_a_bar_sqrt):
+    """One step of examples/ddpm.ipynb cell 4 (Algorithm 1): x_t = sqrt(a_bar_t) x0 + sqrt(1 - a_bar_t) eps (per-sample
+    coefficients given as arrays broadcast over (B,1,1,1)), MSE between the predicted and the true noise."""
+    x_t = a_bar_sqrt * x0 + one_minus_a_bar_sqrt * noise
+    pred = model.forward(neunet.tensor(x_t, requires_grad=False, device=x0.device), t_frac)
+    loss = nn.MSELoss()(pred, noise)
+    loss.backward()
+    optimizer.step()
+    return loss, pred

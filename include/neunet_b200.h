@@ -204,6 +204,34 @@ int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bi
                           int rounds, float* us_per_launch, int* launches_per_gemm,
                           cudaStream_t stream);
 
+/* ---- Fused LeakyReLU + BatchNorm2d over NCHW fp32 (row N2 of SURVEY.md 8f) -----------------------
+ * a = leaky_relu(x, alpha) (neunet/nn/activations.py:73-93; alpha = 1 gives plain BatchNorm2d),
+ * y = (a - mean_c) * inv_std_c * w_c + b_c with batch statistics over (B, H, W), ddof 0
+ * (neunet/nn/layers/batchnorm2d.py:57-115; backward :11-55). The reference runs these as ~12 array passes per
+ * conv -> LeakyReLU -> BatchNorm2d group of the DDPM ResBlock (examples/ddpm.ipynb cell 5 l.41-55).
+ *   forward : nnb_bn_stats -> sums[2C] fp64 {sum a, sum a^2}; (SyncBN: the caller all-reduces sums and passes the
+ *             global count) -> nnb_bn_finalize: mean, inv_std = 1/sqrt(var + eps), and, when non-NULL,
+ *             running = momentum * running + (1 - momentum) * stat (the reference's convention, :87-88)
+ *             -> nnb_bn_apply. w / b may be NULL (affine = False).
+ *   backward: nnb_bn_backward_stats -> sums[2C] {sum g, sum g * xhat} -> nnb_bn_backward_apply:
+ *             dx = lrelu'(x) * inv_std * (w g - mean(w g) - xhat * mean(w g xhat)), dw = sum g xhat, db = sum g
+ *             (dx / dw / db nullable, so the parameter gradients can be taken from LOCAL sums before a SyncBN
+ *             all-reduce of sums). Only x, mean, inv_std are kept from forward.
+ * workspace: nnb_bn_workspace_bytes(B, C) bytes for the per-channel partial sums (deterministic order). */
+size_t nnb_bn_workspace_bytes(int64_t B, int64_t C);
+int nnb_bn_stats(const float* x, int64_t B, int64_t C, int64_t HW, float alpha, double* sums, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+int nnb_bn_finalize(const double* sums, double count, int64_t C, float eps, float momentum, float* mean,
+                    float* inv_std, float* running_mean, float* running_var, cudaStream_t stream);
+int nnb_bn_apply(const float* x, const float* mean, const float* inv_std, const float* w, const float* b,
+                 int64_t B, int64_t C, int64_t HW, float alpha, float* y, cudaStream_t stream);
+int nnb_bn_backward_stats(const float* x, const float* grad, const float* mean, const float* inv_std, int64_t B,
+                          int64_t C, int64_t HW, float alpha, double* sums, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream);
+int nnb_bn_backward_apply(const float* x, const float* grad, const float* mean, const float* inv_std, const float* w,
+                          const double* sums, double count, int64_t B, int64_t C, int64_t HW, float alpha,
+                          float* dx, float* dw, float* db, cudaStream_t stream);
+
 /* ---- Fused attention for short sequences (row N4 of SURVEY.md 8f) -------------------------------
  * examples/gpt.ipynb cell 2 l.25-40 as ONE kernel per direction:
  *   scores = q . kT / scale; scores = where(mask, fill, scores); p = softmax(scores, -1);

@@ -122,6 +122,16 @@ _SIGNATURES = {
                                           c_float, c_void_p]),
     "nnb_rmsnorm_backward_acc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "nnb_bn_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "nnb_bn_stats": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_bn_finalize": (c_int, [c_void_p, c_double, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "nnb_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                             c_void_p, c_void_p]),
+    "nnb_bn_backward_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_bn_backward_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int64,
+                                      c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nnb_attention_supported": (c_int, [c_int64, c_int64, c_int64]),
     "nnb_attention_forward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                       c_void_p, c_int, c_float, POINTER(c_int64), c_float, c_float, c_float, c_uint64,
@@ -709,6 +719,86 @@ def dropout_apply(x, p, ticket, residual=None, want_planes=False):
     if want_planes:
         return y, ((planes_key(y.reshape(rows, cols), prec), buf) if buf is not None else None)
     return y
+
+
+# ---- fused LeakyReLU + BatchNorm2d ------------------------------------------------------------------------------
+_bn = {"sync": False}
+
+
+def set_sync_batchnorm(on: bool) -> bool:
+    """SyncBN: batch statistics (and their gradients) are all-reduced over the data-parallel ranks, so an N-rank run
+    normalises exactly like one process on the global batch. Off by default: per-shard
+    statistics, like running the reference once per shard."""
+    prev = _bn["sync"]
+    _bn["sync"] = bool(on)
+    return prev
+
+
+def _bn_world():
+    if not _bn["sync"]:
+        return 1
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def bn_forward(x, w, b, alpha, eps, momentum, running_mean=None, running_var=None, stats=None):
+    """y = BatchNorm2d(leaky_relu(x, alpha)) over NCHW x. Training (stats None): batch statistics, running stats updated
+    in place; eval: stats = (mean, inv_std). Returns (y, mean, inv_std)."""
+    require_device()
+    L = lib()
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    HW = H * W
+    y = torch.empty_like(x)
+    if stats is None:
+        mean = torch.empty(C, dtype=torch.float32, device="cuda")
+        inv = torch.empty(C, dtype=torch.float32, device="cuda")
+        sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+        ws = _workspace(L.nnb_bn_workspace_bytes(B, C))
+        _check(L.nnb_bn_stats(_ptr(x), B, C, HW, float(alpha), _ptr(sums), _ptr(ws), ws.numel(), _stream()), "nnb_bn_stats")
+        world = _bn_world()
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(sums)
+        _check(L.nnb_bn_finalize(_ptr(sums), float(B * HW * world), C, float(eps), float(momentum), _ptr(mean), _ptr(inv),
+                                 _ptr(running_mean), _ptr(running_var), _stream()), "nnb_bn_finalize")
+    else:
+        mean, inv = stats
+    _check(L.nnb_bn_apply(_ptr(x), _ptr(mean), _ptr(inv), _ptr(w), _ptr(b), B, C, HW, float(alpha), _ptr(y), _stream()),
+           "nnb_bn_apply")
+    return y, mean, inv
+
+
+def bn_backward(x, grad, mean, inv, w, alpha, need_dx=True, need_dw=True):
+    """Returns (dx, dw, db) for the fused LeakyReLU + BatchNorm2d (training-mode statistics)."""
+    require_device()
+    L = lib()
+    x, grad = _f32c(x), _f32c(grad)
+    B, C, H, W = x.shape
+    HW = H * W
+    sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    ws = _workspace(L.nnb_bn_workspace_bytes(B, C))
+    _check(L.nnb_bn_backward_stats(_ptr(x), _ptr(grad), _ptr(mean), _ptr(inv), B, C, HW, float(alpha), _ptr(sums), _ptr(ws),
+                                   ws.numel(), _stream()), "nnb_bn_backward_stats")
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty(C, dtype=torch.float32, device="cuda") if need_dw else None
+    db = torch.empty(C, dtype=torch.float32, device="cuda") if need_dw else None
+    world = _bn_world()
+    count = float(B * HW * world)
+    if world > 1:
+        import torch.distributed as dist
+        # parameter gradients from the LOCAL sums (the gradient all-reduce adds the ranks later); dx needs the global ones
+        if need_dw:
+            _check(L.nnb_bn_backward_apply(_ptr(x), _ptr(grad), _ptr(mean), _ptr(inv), _ptr(w), _ptr(sums), count, B, C, HW,
+                                           float(alpha), None, _ptr(dw), _ptr(db), _stream()), "nnb_bn_backward_apply")
+        dist.all_reduce(sums)
+        if need_dx:
+            _check(L.nnb_bn_backward_apply(_ptr(x), _ptr(grad), _ptr(mean), _ptr(inv), _ptr(w), _ptr(sums), count, B, C, HW,
+                                           float(alpha), _ptr(dx), None, None, _stream()), "nnb_bn_backward_apply")
+    else:
+        _check(L.nnb_bn_backward_apply(_ptr(x), _ptr(grad), _ptr(mean), _ptr(inv), _ptr(w), _ptr(sums), count, B, C, HW,
+                                       float(alpha), _ptr(dx), _ptr(dw), _ptr(db), _stream()), "nnb_bn_backward_apply")
+    return dx, dw, db
 
 
 # ---- fused attention (short sequences) -------------------------------------------------------------------------
