@@ -154,6 +154,23 @@ int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt
 int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* dO,
                         float* dX, float* dW, float* db, int prec, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream);
+/* Same contractions with the channels-last bf16 planes of X handled by the caller (round 2: "keep forward planes
+ * for backward"). Layers whose channel counts are multiples of 8 convert X once to planes [B][H][W][Cin]
+ * (nnb_conv2d_planes_bytes(desc, prec) bytes, 256-byte aligned; 0 = this geometry does not use planes):
+ *   forward_ex : X_planes != NULL -> read them (X is not converted again); else X_planes_out != NULL -> the converted
+ *                planes are written there and stay valid for backward_ex; both NULL = workspace scratch.
+ *   backward_ex: X_planes != NULL -> wgrad reads them instead of converting X again.
+ * With Cin % 64 == 0 (forward, wgrad) / Cout % 64 == 0 and stride 1 (dgrad) and a power-of-two style position grid the
+ * GEMM reads its operand STRAIGHT from the planes through 4-D TMA boxes (implicit GEMM: no `col` matrix; the conv
+ * padding is the copy engine's out-of-bounds zero fill, the conv stride its traversal stride);
+ * NNB_CONV_IMPLICIT=0 in the environment forces the materialised-`col` path. */
+size_t nnb_conv2d_planes_bytes(const nnb_conv2d_desc* desc, int prec);
+int nnb_conv2d_forward_ex(const nnb_conv2d_desc* desc, const float* X, const float* W, const float* bias,
+                          float* O, int prec, const void* X_planes, void* X_planes_out, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+int nnb_conv2d_backward_ex(const nnb_conv2d_desc* desc, const float* X, const float* W, const float* dO,
+                           float* dX, float* dW, float* db, int prec, const void* X_planes, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- epilogue ops as standalone kernels (same maths as the fused forms) ----------------------
  * Swish: cudaSwishForward/Backward (experimental/activations/swish/swish.cu:14-80),
@@ -203,6 +220,29 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
 int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bias, int sets,
                           int rounds, float* us_per_launch, int* launches_per_gemm,
                           cudaStream_t stream);
+
+/* ---- native ConvTranspose2d (row N1 of SURVEY.md 8f) -----------------------------------------------
+ * neunet/nn/layers/convtranspose2d.py:115-387: weights (out, in, kh, kw), NOT flipped; the layer is a stride-1
+ * correlation over the zero-stuffed, (k-1)-padded, padding-cropped input (:165-181, 321), so the reference multiplies
+ * s0*s1 - 1 zeros for every real tap. Here: gather form with real taps only -- the output is split into s0*s1 parity
+ * classes, each an implicit GEMM over its own tap subset read from the channels-last planes of X; dX is ONE strided
+ * implicit GEMM over dO, dW one implicit wgrad GEMM. desc: B, Cin, H, W describe the INPUT, Cout / kh / kw / stride /
+ * pad / dil the layer. Supported natively for Cin % 64 == Cout % 64 == 0, dilation 1, output_padding 0, output size
+ * divisible by the stride (nnb_conv_transpose2d_supported); otherwise NNB_ERR_UNSUPPORTED and the caller uses the
+ * zero-stuffed formulation over nnb_conv2d_* (same results). X_planes_out / X_planes: channels-last bf16 planes of
+ * X kept from forward for wgrad (nnb_conv_transpose2d_planes_bytes). */
+int nnb_conv_transpose2d_supported(const nnb_conv2d_desc* desc, int out_pad0, int out_pad1);
+int nnb_conv_transpose2d_out_shape(const nnb_conv2d_desc* desc, int out_pad0, int out_pad1, int64_t* Ho, int64_t* Wo);
+size_t nnb_conv_transpose2d_planes_bytes(const nnb_conv2d_desc* desc, int prec);
+size_t nnb_conv_transpose2d_workspace_bytes(const nnb_conv2d_desc* desc, int out_pad0, int out_pad1, int prec,
+                                            int backward);
+int nnb_conv_transpose2d_forward(const nnb_conv2d_desc* desc, int out_pad0, int out_pad1, const float* X,
+                                 const float* W, const float* bias, float* O, int prec, void* X_planes_out,
+                                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int nnb_conv_transpose2d_backward(const nnb_conv2d_desc* desc, int out_pad0, int out_pad1, const float* X,
+                                  const float* W, const float* dO, float* dX, float* dW, float* db, int prec,
+                                  const void* X_planes, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream);
 
 /* ---- Fused LeakyReLU + BatchNorm2d over NCHW fp32 (row N2 of SURVEY.md 8f) -----------------------
  * a = leaky_relu(x, alpha) (neunet/nn/activations.py:73-93; alpha = 1 gives plain BatchNorm2d),

@@ -131,9 +131,25 @@ struct GemmEpilogue {
     int64_t ldd16 = 0;
 };
 
+// Implicit-GEMM convolution: the B operand is not a staged matrix but bf16 channels-last planes
+// src[b][y][x][c] (C % 64 == 0) read through 4-D TMA boxes; a GEMM "position" is m = (b * P + p) * Q + q and
+// position (p, q) with tap (k, l) reads pixel (p * sp0 - off0 + k * dk0, q * sp1 - off1 + l * dk1), zero outside.
+//   mode 1 (forward / stride-1 dgrad): B[n = position][k = (tap, c)]   (K-major;  GEMM N = positions, K = taps * C)
+//   mode 2 (wgrad)                   : B[k = position][n = (tap, c)]   (MN-major; GEMM K = positions, N = taps * C)
+struct ConvOperand {
+    int mode = 0;
+    const __nv_bfloat16* hi = nullptr;
+    const __nv_bfloat16* lo = nullptr;
+    int64_t B = 0, C = 0, Hs = 0, Ws = 0;  // source planes
+    int64_t P = 0, Q = 0;                  // position grid per image
+    int kh = 1, kw = 1;
+    int sp0 = 1, sp1 = 1, off0 = 0, off1 = 0, dk0 = 1, dk1 = 1;
+};
+
 struct GemmProblem {
     int64_t M = 0, N = 0, K = 0, batch = 1;
     GemmOperand A, B;
+    ConvOperand conv;  // conv.mode != 0: B comes from channels-last planes (B.st is ignored)
     float* D = nullptr;
     int64_t ldd = 0, batch_stride_d = 0;
     bool reduce_batch = false;  // sum over the batch dimension into ONE output (wgrad-style)
@@ -153,5 +169,7 @@ struct GemmProblem {
 
 size_t gemm_splitk_ws_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);
 int gemm(const GemmProblem& p, cudaStream_t stream);
+// true when conv-mode boxes exist for this position grid (power-of-two style shapes; see gemm.cu: conv_rect)
+bool gemm_conv_supported(int mode, int64_t C, int64_t P, int64_t Q, int sp0, int sp1);
 
 }  // namespace nnb

@@ -10,6 +10,7 @@
 // 8->16, the DDPM 128->3 output) use direct fp32 CUDA-core kernels: a 128-wide tensor tile would
 // be >90 % padding there.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "workspace.cuh"
@@ -18,6 +19,7 @@ namespace nnb {
 namespace {
 
 int planes(int prec) { return prec == NNB_PREC_BF16X3 ? 2 : 1; }
+int g_implicit = [] { const char* e = getenv("NNB_CONV_IMPLICIT"); return e ? atoi(e) : 1; }();  // 0: always materialise `col`
 
 struct Geo {
     int B, Cin, H, W, Cout, kh, kw, Ho, Wo;
@@ -372,6 +374,115 @@ __global__ void direct_wgrad_finish_kernel(const float* __restrict__ partial, in
     dW[w] = s;
 }
 
+// ---------------------------------------------------------------- native ConvTranspose2d (row N1 of SURVEY.md 8f)
+// The reference defines ConvTranspose2d as a stride-1 correlation of the UN-flipped (out,in,kh,kw) kernel over the
+// zero-stuffed, (k-1)-padded, padding-cropped input (neunet/nn/layers/convtranspose2d.py:165-181, 321), so at
+// stride s only 1 / (s0*s1) of the multiplied taps are non-zero. Gather form with real taps only: output pixels are
+// split by parity class (y % s0, x % s1); inside a class every pixel uses the same tap subset
+//   k = k0 + j*s  with  k0 = (-(py + pad - (kh-1))) mod s,   source row u + j + e,  e = (py + pad - (kh-1) + k0) / s
+// i.e. a stride-1 correlation of X with an (nk0 x nk1)-tap kernel -> one implicit GEMM per class.
+
+// Wc[o][(j0, j1, c)] = W[o][c][k0y + j0*s0][k0x + j1*s1]
+template <bool X3>
+__global__ void stage_weight_class_kernel(const float* __restrict__ W, int Cout, int Cin, int kh, int kw, int k0y, int k0x,
+                                          int s0, int s1, int nk0, int nk1, long long ld, __nv_bfloat16* hi,
+                                          __nv_bfloat16* lo) {
+    const long long total = (long long)Cout * nk0 * nk1 * Cin;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % Cin);
+        long long t = idx / Cin;
+        const int j1 = (int)(t % nk1); t /= nk1;
+        const int j0 = (int)(t % nk0);
+        const int o = (int)(t / nk0);
+        const float v = W[(((long long)o * Cin + c) * kh + (k0y + j0 * s0)) * kw + (k0x + j1 * s1)];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const long long dst = (long long)o * ld + ((long long)j0 * nk1 + j1) * Cin + c;
+        hi[dst] = h;
+        if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// out[b][o][s0*u + py][s1*v + px] = T[(py, px)][o][(b*P + u)*Q + v] + bias[o]
+__global__ void __launch_bounds__(256) convT_interleave_kernel(const float* __restrict__ T, const float* __restrict__ bias,
+                                                               int B, int Cout, int P, int Q, int s0, int s1,
+                                                               float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const int Ho = P * s0, Wo = Q * s1;
+    const long long N = (long long)B * P * Q;
+    const long long total = (long long)B * Cout * Ho * Wo;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % Wo);
+        long long t = idx / Wo;
+        const int y = (int)(t % Ho); t /= Ho;
+        const int o = (int)(t % Cout);
+        const int b = (int)(t / Cout);
+        const int cls = (y % s0) * s1 + (x % s1);
+        float v = T[((long long)cls * Cout + o) * N + ((long long)b * P + y / s0) * Q + x / s1];
+        if (bias != nullptr) v += bias[o];
+        out[idx] = v;
+    }
+}
+
+// dW[o][c][kh-1-k'][kw-1-l'] = T[c][((k'*kw + l')*Cout + o)]
+__global__ void permute_dw_convT_kernel(const float* __restrict__ T, int Cout, int Cin, int kh, int kw, float* __restrict__ dW) {
+    const int khw = kh * kw;
+    const long long total = (long long)Cout * Cin * khw;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % khw);
+        const long long t = idx / khw;
+        const int c = (int)(t % Cin);
+        const int o = (int)(t / Cin);
+        dW[idx] = T[((long long)c * khw + (khw - 1 - tap)) * Cout + o];
+    }
+}
+
+struct TGeo {          // transposed-conv geometry: X (B,Cin,H,W) -> O (B,Cout,Ho,Wo)
+    Geo g;             // g.H/W = input, g.Ho/Wo = OUTPUT of the transposed conv, g.pt/pl = padding, s, d, kh, kw
+    int P, Q;          // per-class position grid = Ho / s0, Wo / s1
+};
+
+int make_tgeo(const nnb_conv2d_desc* d, int op0, int op1, TGeo* t) {
+    NNB_REQUIRE(d, "conv_transpose2d: null descriptor");
+    NNB_REQUIRE(d->B > 0 && d->Cin > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->kh > 0 && d->kw > 0,
+                "conv_transpose2d: non-positive dimension");
+    NNB_REQUIRE(d->stride[0] > 0 && d->stride[1] > 0 && d->dil[0] > 0 && d->dil[1] > 0, "conv_transpose2d: bad stride/dilation");
+    Geo& g = t->g;
+    g.B = (int)d->B; g.Cin = (int)d->Cin; g.H = (int)d->H; g.W = (int)d->W; g.Cout = (int)d->Cout;
+    g.kh = (int)d->kh; g.kw = (int)d->kw; g.s0 = d->stride[0]; g.s1 = d->stride[1];
+    g.pt = d->pad[0]; g.pl = d->pad[2]; g.d0 = d->dil[0]; g.d1 = d->dil[1];
+    const int dk0 = g.d0 * (g.kh - 1) + 1, dk1 = g.d1 * (g.kw - 1) + 1;
+    // convtranspose2d.py:165-181: stuffed size s*H - (s-1) + output_padding, padded by (dk-1) each side, cropped by the padding,
+    // then a stride-1 valid correlation
+    const long long ho = (long long)g.s0 * g.H - (g.s0 - 1) + op0 + 2 * (dk0 - 1) - d->pad[0] - d->pad[1] - (dk0 - 1);
+    const long long wo = (long long)g.s1 * g.W - (g.s1 - 1) + op1 + 2 * (dk1 - 1) - d->pad[2] - d->pad[3] - (dk1 - 1);
+    NNB_REQUIRE(ho > 0 && wo > 0, "conv_transpose2d: empty output");
+    g.Ho = (int)ho; g.Wo = (int)wo;
+    t->P = g.Ho / g.s0; t->Q = g.Wo / g.s1;
+    return NNB_OK;
+}
+
+bool tconv_native(const TGeo& t, int op0, int op1) {
+    const Geo& g = t.g;
+    return g_implicit && op0 == 0 && op1 == 0 && g.d0 == 1 && g.d1 == 1 && (g.Cin % 64) == 0 && (g.Cout % 64) == 0 &&
+           (g.Ho % g.s0) == 0 && (g.Wo % g.s1) == 0 && g.kh >= g.s0 && g.kw >= g.s1 &&
+           gemm_conv_supported(1, g.Cin, t.P, t.Q, 1, 1) &&            // forward classes (positions = class grid)
+           gemm_conv_supported(1, g.Cout, g.H, g.W, g.s0, g.s1) &&     // dgrad (positions = input pixels, strided reads of dO)
+           gemm_conv_supported(2, g.Cout, g.H, g.W, g.s0, g.s1);       // wgrad
+}
+
+// taps of parity class `par` along one axis
+void class_taps(int par, int pad, int k, int s, int* k0, int* nk, int* e) {
+    int r = (par + pad - (k - 1)) % s;
+    if (r < 0) r += s;
+    *k0 = (s - r) % s;
+    *nk = (k - *k0 + s - 1) / s;
+    *e = (par + pad - (k - 1) + *k0) / s;  // exact
+}
+
 int grid_for(long long n, int threads) {
     return (int)std::max<long long>(1, std::min<long long>(ceil_div(n, threads), (long long)num_sms() * 32));
 }
@@ -426,6 +537,34 @@ Staged as_staged(const Planes& p, int64_t rows, int64_t cols) {
 }
 
 bool use_nhwc(const Geo& g) { return !use_direct(g) && (g.Cin % 8) == 0 && (g.Cout % 8) == 0; }
+
+// Implicit GEMM (no materialised `col`): the GEMM's B operand is read straight from the channels-last planes through
+// 4-D TMA boxes (gemm.cu, ConvOperand). Needs 64-channel k-blocks and a position grid that tiles into pixel boxes.
+bool implicit_fwd(const Geo& g) {
+    return g_implicit && use_nhwc(g) && (g.Cin % 64) == 0 && gemm_conv_supported(1, g.Cin, g.Ho, g.Wo, g.s0, g.s1) &&
+           gemm_conv_supported(2, g.Cin, g.Ho, g.Wo, g.s0, g.s1);
+}
+bool implicit_dgrad(const Geo& g) {  // stride-1 layers: dX is a plain correlation of dO with the flipped kernel
+    return g_implicit && use_nhwc(g) && (g.Cout % 64) == 0 && g.s0 == 1 && g.s1 == 1 &&
+           gemm_conv_supported(1, g.Cout, g.H, g.W, 1, 1);
+}
+
+ConvOperand conv_operand(int mode, const Planes& src, int64_t B, int64_t C, int64_t Hs, int64_t Ws, int64_t P, int64_t Q,
+                         int kh, int kw, int sp0, int sp1, int off0, int off1, int dk0, int dk1) {
+    ConvOperand c;
+    c.mode = mode; c.hi = src.hi; c.lo = src.lo;
+    c.B = B; c.C = C; c.Hs = Hs; c.Ws = Ws; c.P = P; c.Q = Q; c.kh = kh; c.kw = kw;
+    c.sp0 = sp0; c.sp1 = sp1; c.off0 = off0; c.off1 = off1; c.dk0 = dk0; c.dk1 = dk1;
+    return c;
+}
+
+size_t nhwc_bytes(int64_t positions, int64_t C) { return (size_t)round_up(positions * C * 2, 256); }
+Planes planes_at(void* buf, int64_t positions, int64_t C, int prec) {
+    Planes p;
+    p.hi = static_cast<__nv_bfloat16*>(buf);
+    p.lo = prec == NNB_PREC_BF16X3 ? reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(buf) + nhwc_bytes(positions, C)) : nullptr;
+    return p;
+}
 
 Planes take_nhwc(Bump& ws, int64_t positions, int64_t C, int prec) {
     Planes p;
@@ -496,22 +635,34 @@ size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backwa
             b += (size_t)round_up((int64_t)g.Cout * Kc * 4, 256);
         }
     }
-    b += p * staged_plane_bytes(1, M, Kc);  // col(X)
+    if (!implicit_fwd(g)) b += p * staged_plane_bytes(1, M, Kc);  // col(X)
     if (!backward) {
         b += p * staged_plane_bytes(1, g.Cout, Kc);  // W
         b += gemm_splitk_ws_bytes(g.Cout, M, Kc, 1);
     } else {
-        b += p * staged_plane_bytes(1, g.Cout, M);   // g'
-        b += p * staged_plane_bytes(1, Mx, Kg);      // colT(g)
+        if (!use_nhwc(g)) b += p * staged_plane_bytes(1, g.Cout, M);   // g'
+        if (!implicit_dgrad(g)) b += p * staged_plane_bytes(1, Mx, Kg);      // colT(g)
         b += p * staged_plane_bytes(1, g.Cin, Kg);   // Wr
         b += std::max(gemm_splitk_ws_bytes(g.Cout, Kc, M, 1), gemm_splitk_ws_bytes(g.Cin, Mx, Kg, 1));
     }
     return b;
 }
 
+size_t nnb_conv2d_planes_bytes(const nnb_conv2d_desc* d, int prec) {
+    Geo g{};
+    if (make_geo(d, &g) || !use_nhwc(g)) return 0;
+    return planes(prec) * nhwc_bytes((int64_t)g.B * g.H * g.W, g.Cin);
+}
+
 int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* bias,
                        float* O, int prec, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
+    return nnb_conv2d_forward_ex(d, X, Wt, bias, O, prec, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+int nnb_conv2d_forward_ex(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* bias,
+                          float* O, int prec, const void* X_planes, void* X_planes_out, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
     NNB_REQUIRE(X && Wt && O, "nnb_conv2d_forward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_forward: bad prec");
     Geo g{};
@@ -527,15 +678,44 @@ int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt
     const bool x3 = prec == NNB_PREC_BF16X3;
     const int64_t HWo = (int64_t)g.Ho * g.Wo, M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
     Bump ws(workspace, workspace_bytes);
-    Planes col = take_planes(ws, M, Kc, prec);
+    const bool implicit = implicit_fwd(g);
+    Planes col{nullptr, nullptr};
+    if (!implicit) col = take_planes(ws, M, Kc, prec);
     Planes wp = take_planes(ws, g.Cout, Kc, prec);
     if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_forward: workspace too small (need >= %zu)", ws.off);
     Staged wst;
     if (use_nhwc(g)) {
-        Planes xh = take_nhwc(ws, (int64_t)g.B * g.H * g.W, g.Cin, prec);
-        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_forward: workspace too small (need >= %zu)", ws.off);
-        rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
-        if (rc) return rc;
+        // channels-last bf16 planes of X: taken from the caller (a producer emitted them), written into the caller's
+        // buffer (kept for the backward pass), or scratch
+        const int64_t xpos = (int64_t)g.B * g.H * g.W;
+        Planes xh;
+        if (X_planes != nullptr) {
+            xh = planes_at(const_cast<void*>(X_planes), xpos, g.Cin, prec);
+        } else {
+            if (X_planes_out != nullptr) {
+                NNB_REQUIRE((reinterpret_cast<uintptr_t>(X_planes_out) & 255) == 0, "nnb_conv2d_forward: X_planes_out must be 256-byte aligned");
+                xh = planes_at(X_planes_out, xpos, g.Cin, prec);
+            } else {
+                xh = take_nhwc(ws, xpos, g.Cin, prec);
+                if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_forward: workspace too small (need >= %zu)", ws.off);
+            }
+            rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
+            if (rc) return rc;
+        }
+        if (implicit) {
+            rc = run_stage_weight_klc(Wt, g, false, wp, staged_ld(Kc), x3, stream);
+            if (rc) return rc;
+            GemmProblem p;
+            p.M = g.Cout; p.N = M; p.K = Kc;
+            p.A.st = as_staged(wp, g.Cout, Kc);
+            p.conv = conv_operand(1, xh, g.B, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1);
+            p.D = O; p.ldd = HWo;
+            p.col_group = HWo; p.group_stride = (int64_t)g.Cout * HWo;
+            p.epi.bias = bias; p.bias_per_row = true;
+            p.splitk_ws_bytes = ws.remaining();
+            p.splitk_ws = static_cast<float*>(ws.take(p.splitk_ws_bytes));
+            return gemm(p, stream);
+        }
         GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
                          M, staged_ld(Kc), col.hi, col.lo};
         rc = run_gather_nhwc(a, x3, stream);
@@ -567,6 +747,12 @@ int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt
 int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* dO,
                         float* dX, float* dW, float* db, int prec, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream) {
+    return nnb_conv2d_backward_ex(d, X, Wt, dO, dX, dW, db, prec, nullptr, workspace, workspace_bytes, stream);
+}
+
+int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* dO,
+                           float* dX, float* dW, float* db, int prec, const void* X_planes, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
     NNB_REQUIRE(X && Wt && dO && dW, "nnb_conv2d_backward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_backward: bad prec");
     Geo g{};
@@ -603,36 +789,51 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
     const bool x3 = prec == NNB_PREC_BF16X3;
     const int64_t M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
     const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
-    Planes col = take_planes(ws, M, Kc, prec);
-    Planes gp = take_planes(ws, g.Cout, M, prec);
+    const bool imp_w = implicit_fwd(g), imp_d = dX != nullptr && implicit_dgrad(g);
+    Planes col{nullptr, nullptr};
+    if (!imp_w) col = take_planes(ws, M, Kc, prec);
+    Planes gp{nullptr, nullptr};
+    if (!use_nhwc(g)) gp = take_planes(ws, g.Cout, M, prec);
     Planes colg{nullptr, nullptr}, wr{nullptr, nullptr};
     if (dX) {
-        colg = take_planes(ws, Mx, Kg, prec);
+        if (!imp_d) colg = take_planes(ws, Mx, Kg, prec);
         wr = take_planes(ws, g.Cin, Kg, prec);
     }
     if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
     if (use_nhwc(g)) {
-        // channels-last path: X and dO become bf16 [positions][C] planes once; dO's planes are wgrad's
-        // A operand as they are (MN-major: rows = reduction) and the gather source of dgrad
-        Planes xh = take_nhwc(ws, (int64_t)g.B * g.H * g.W, g.Cin, prec);
+        // channels-last path: X and dO become bf16 [positions][C] planes once (X's are reused from forward when the
+        // caller kept them); dO's planes are wgrad's A operand as they are (MN-major: rows = reduction) and the
+        // source of dgrad
+        Planes xh;
+        if (X_planes != nullptr) xh = planes_at(const_cast<void*>(X_planes), (int64_t)g.B * g.H * g.W, g.Cin, prec);
+        else xh = take_nhwc(ws, (int64_t)g.B * g.H * g.W, g.Cin, prec);
         Planes gh = take_nhwc(ws, M, g.Cout, prec);
         float* dwt = static_cast<float*>(ws.take((size_t)round_up((int64_t)g.Cout * Kc * 4, 256)));
         if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
         const size_t skb = ws.remaining();
         float* skp = static_cast<float*>(ws.take(skb));
-        rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
-        if (rc) return rc;
+        if (X_planes == nullptr) {
+            rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
+            if (rc) return rc;
+        }
         rc = run_to_nhwc(dO, g.B, g.Cout, (int)HWo, gh, x3, stream);
         if (rc) return rc;
-        GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
-                         M, staged_ld(Kc), col.hi, col.lo};
-        rc = run_gather_nhwc(a, x3, stream);
-        if (rc) return rc;
+        if (!imp_w) {
+            GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+                             M, staged_ld(Kc), col.hi, col.lo};
+            rc = run_gather_nhwc(a, x3, stream);
+            if (rc) return rc;
+        }
         {   // wgrad: T[o][(k,l,c)] = sum_m gh[m][o] * col[m][(k,l,c)], then T -> dW[o][c][k][l]
             GemmProblem p;
             p.M = g.Cout; p.N = Kc; p.K = M;
             p.A.st = as_staged(gh, M, g.Cout); p.A.mn_major = true;
-            p.B.st = as_staged(col, M, Kc); p.B.mn_major = true;
+            if (imp_w) {
+                p.B.mn_major = true;
+                p.conv = conv_operand(2, xh, g.B, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1);
+            } else {
+                p.B.st = as_staged(col, M, Kc); p.B.mn_major = true;
+            }
             p.D = dwt; p.ldd = Kc;
             p.splitk_ws = skp; p.splitk_ws_bytes = skb;
             rc = gemm(p, stream);
@@ -643,18 +844,24 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
             NNB_CUDA_OK(cudaGetLastError());
         }
         if (dX) {
-            GatherNhwcArgs ga{gh.hi, gh.lo, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
-                              g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1, g.s0, g.s1,
-                              Mx, staged_ld(Kg), colg.hi, colg.lo};
-            rc = run_gather_nhwc(ga, x3, stream);
-            if (rc) return rc;
+            if (!imp_d) {
+                GatherNhwcArgs ga{gh.hi, gh.lo, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
+                                  g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1, g.s0, g.s1,
+                                  Mx, staged_ld(Kg), colg.hi, colg.lo};
+                rc = run_gather_nhwc(ga, x3, stream);
+                if (rc) return rc;
+            }
             rc = run_stage_weight_klc(Wt, g, true, wr, staged_ld(Kg), x3, stream);
             if (rc) return rc;
             const int64_t HW = (int64_t)g.H * g.W;
             GemmProblem p;
             p.M = g.Cin; p.N = Mx; p.K = Kg;
             p.A.st = as_staged(wr, g.Cin, Kg);
-            p.B.st = as_staged(colg, Mx, Kg);
+            if (imp_d)  // positions = pixels of dX, source = dO planes, flipped taps (the weights are staged flipped)
+                p.conv = conv_operand(1, gh, g.B, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
+                                      g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1);
+            else
+                p.B.st = as_staged(colg, Mx, Kg);
             p.D = dX; p.ldd = HW;
             p.col_group = HW; p.group_stride = (int64_t)g.Cin * HW;
             p.splitk_ws = skp; p.splitk_ws_bytes = skb;
@@ -708,6 +915,184 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
         p.splitk_ws = sk; p.splitk_ws_bytes = sk_bytes;
         rc = gemm(p, stream);
         if (rc) return rc;
+    }
+    return NNB_OK;
+}
+
+int nnb_conv_transpose2d_supported(const nnb_conv2d_desc* d, int out_pad0, int out_pad1) {
+    TGeo t{};
+    if (make_tgeo(d, out_pad0, out_pad1, &t)) return 0;
+    return tconv_native(t, out_pad0, out_pad1) ? 1 : 0;
+}
+
+int nnb_conv_transpose2d_out_shape(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, int64_t* Ho, int64_t* Wo) {
+    TGeo t{};
+    int rc = make_tgeo(d, out_pad0, out_pad1, &t);
+    if (rc) return rc;
+    if (Ho) *Ho = t.g.Ho;
+    if (Wo) *Wo = t.g.Wo;
+    return NNB_OK;
+}
+
+size_t nnb_conv_transpose2d_planes_bytes(const nnb_conv2d_desc* d, int prec) {
+    if (!d || d->B <= 0 || d->Cin <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    return planes(prec) * nhwc_bytes(d->B * d->H * d->W, d->Cin);
+}
+
+size_t nnb_conv_transpose2d_workspace_bytes(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, int prec, int backward) {
+    TGeo t{};
+    if (make_tgeo(d, out_pad0, out_pad1, &t)) return 0;
+    const Geo& g = t.g;
+    const size_t p = planes(prec);
+    const int64_t xpos = (int64_t)g.B * g.H * g.W, opos = (int64_t)g.B * g.Ho * g.Wo;
+    const int64_t Kfull = (int64_t)g.kh * g.kw;
+    size_t b = 16384 + (size_t)round_up((int64_t)CHANNEL_SUM_CHUNKS * g.Cout * 4, 256);
+    b += p * nhwc_bytes(xpos, g.Cin);
+    if (!backward) {
+        b += (size_t)round_up(opos * g.Cout * 4, 256);                          // class outputs
+        b += p * staged_plane_bytes(1, g.Cout, Kfull * g.Cin);                  // class weights (all classes together <= full kernel)
+        b += 4 * 256 * p;
+        b += gemm_splitk_ws_bytes(g.Cout, xpos, Kfull * g.Cin, 1);
+    } else {
+        b += p * nhwc_bytes(opos, g.Cout);                                       // dO planes
+        b += p * staged_plane_bytes(1, g.Cin, Kfull * g.Cout);                   // flipped weights
+        b += (size_t)round_up((int64_t)g.Cin * Kfull * g.Cout * 4, 256);         // T
+        b += std::max(gemm_splitk_ws_bytes(g.Cin, xpos, Kfull * g.Cout, 1), gemm_splitk_ws_bytes(g.Cin, Kfull * g.Cout, xpos, 1));
+    }
+    return b;
+}
+
+int nnb_conv_transpose2d_forward(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, const float* X, const float* Wt,
+                                 const float* bias, float* O, int prec, void* X_planes_out, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream) {
+    NNB_REQUIRE(X && Wt && O, "nnb_conv_transpose2d_forward: null pointer");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv_transpose2d_forward: bad prec");
+    TGeo t{};
+    int rc = make_tgeo(d, out_pad0, out_pad1, &t);
+    if (rc) return rc;
+    if (!tconv_native(t, out_pad0, out_pad1))
+        return fail(NNB_ERR_UNSUPPORTED, "nnb_conv_transpose2d_forward: geometry outside the native gather form "
+                                          "(needs Cin, Cout %% 64 == 0, dilation 1, no output padding, Ho %% stride == 0)");
+    const Geo& g = t.g;
+    const bool x3 = prec == NNB_PREC_BF16X3;
+    const int64_t xpos = (int64_t)g.B * g.H * g.W, N = (int64_t)g.B * t.P * t.Q;
+    Bump ws(workspace, workspace_bytes);
+    Planes xh;
+    if (X_planes_out != nullptr) {
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(X_planes_out) & 255) == 0, "nnb_conv_transpose2d_forward: X_planes_out must be 256-byte aligned");
+        xh = planes_at(X_planes_out, xpos, g.Cin, prec);
+    } else {
+        xh = take_nhwc(ws, xpos, g.Cin, prec);
+    }
+    float* T = static_cast<float*>(ws.take((size_t)round_up((int64_t)g.s0 * g.s1 * g.Cout * N * 4, 256)));
+    if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_forward: workspace too small (need >= %zu)", ws.off);
+    rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
+    if (rc) return rc;
+    for (int py = 0; py < g.s0; ++py) {
+        for (int px = 0; px < g.s1; ++px) {
+            int k0y, nk0, ey, k0x, nk1, ex;
+            class_taps(py, g.pt, g.kh, g.s0, &k0y, &nk0, &ey);
+            class_taps(px, g.pl, g.kw, g.s1, &k0x, &nk1, &ex);
+            const int64_t Kc = (int64_t)nk0 * nk1 * g.Cin;
+            Bump cws = ws;  // per-class scratch is reused: the stream serialises the classes
+            Planes wc = take_planes(cws, g.Cout, Kc, prec);
+            if (!cws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_forward: workspace too small (need >= %zu)", cws.off);
+            const long long total = (long long)g.Cout * Kc;
+            if (x3) stage_weight_class_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, k0y, k0x, g.s0, g.s1, nk0, nk1, staged_ld(Kc), wc.hi, wc.lo);
+            else stage_weight_class_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, k0y, k0x, g.s0, g.s1, nk0, nk1, staged_ld(Kc), wc.hi, wc.lo);
+            count_launch();
+            NNB_CUDA_OK(cudaGetLastError());
+            GemmProblem p;
+            p.M = g.Cout; p.N = N; p.K = Kc;
+            p.A.st = as_staged(wc, g.Cout, Kc);
+            p.conv = conv_operand(1, xh, g.B, g.Cin, g.H, g.W, t.P, t.Q, nk0, nk1, 1, 1, -ey, -ex, 1, 1);
+            p.D = T + ((int64_t)(py * g.s1 + px) * g.Cout) * N; p.ldd = N;
+            p.splitk_ws_bytes = cws.remaining();
+            p.splitk_ws = static_cast<float*>(cws.take(p.splitk_ws_bytes));
+            rc = gemm(p, stream);
+            if (rc) return rc;
+        }
+    }
+    const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
+    NNB_CUDA_OK(launch_pdl(convT_interleave_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, (const float*)T, bias, g.B, g.Cout,
+                           t.P, t.Q, g.s0, g.s1, O));
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_conv_transpose2d_backward(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, const float* X, const float* Wt,
+                                  const float* dO, float* dX, float* dW, float* db, int prec, const void* X_planes,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NNB_REQUIRE(X && Wt && dO && dW, "nnb_conv_transpose2d_backward: null pointer");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv_transpose2d_backward: bad prec");
+    TGeo t{};
+    int rc = make_tgeo(d, out_pad0, out_pad1, &t);
+    if (rc) return rc;
+    if (!tconv_native(t, out_pad0, out_pad1))
+        return fail(NNB_ERR_UNSUPPORTED, "nnb_conv_transpose2d_backward: geometry outside the native gather form");
+    const Geo& g = t.g;
+    const bool x3 = prec == NNB_PREC_BF16X3;
+    const int64_t xpos = (int64_t)g.B * g.H * g.W, opos = (int64_t)g.B * g.Ho * g.Wo, HWo = (int64_t)g.Ho * g.Wo;
+    const int64_t Kg = (int64_t)g.kh * g.kw * g.Cout;
+    Bump ws(workspace, workspace_bytes);
+    if (db) {
+        const int chunks = std::min(CHANNEL_SUM_CHUNKS, g.B);
+        float* part = static_cast<float*>(ws.take((size_t)CHANNEL_SUM_CHUNKS * g.Cout * 4));
+        if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_backward: workspace too small (need >= %zu)", ws.off);
+        channel_sum_kernel<<<dim3((unsigned)g.Cout, (unsigned)chunks), 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, part);
+        direct_wgrad_finish_kernel<<<(unsigned)ceil_div(g.Cout, 256), 256, 0, stream>>>(part, g.Cout, chunks, db);
+        count_launch(2);
+        NNB_CUDA_OK(cudaGetLastError());
+    }
+    Planes xh;
+    if (X_planes != nullptr) xh = planes_at(const_cast<void*>(X_planes), xpos, g.Cin, prec);
+    else xh = take_nhwc(ws, xpos, g.Cin, prec);
+    Planes gh = take_nhwc(ws, opos, g.Cout, prec);
+    Planes wf = take_planes(ws, g.Cin, Kg, prec);
+    float* T = static_cast<float*>(ws.take((size_t)round_up((int64_t)g.Cin * Kg * 4, 256)));
+    if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_backward: workspace too small (need >= %zu)", ws.off);
+    const size_t skb = ws.remaining();
+    float* skp = static_cast<float*>(ws.take(skb));
+    if (X_planes == nullptr) {
+        rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
+        if (rc) return rc;
+    }
+    rc = run_to_nhwc(dO, g.B, g.Cout, (int)HWo, gh, x3, stream);
+    if (rc) return rc;
+    // dO read through the stride: pixel (u, v) of X with tap (k', l') meets dO[s*u - pad + k'][s*v - pad + l']
+    const ConvOperand gsrc1 = conv_operand(1, gh, g.B, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, 1, 1);
+    if (dX) {
+        // dX[c][(b,u,v)] = sum_{(k',l',o)} Wf[c][(k',l',o)] * dO[...][o],  Wf[c][(k',l',o)] = W[o][c][kh-1-k'][kw-1-l']
+        rc = run_stage_weight_klc(Wt, g, true, wf, staged_ld(Kg), x3, stream);
+        if (rc) return rc;
+        const int64_t HW = (int64_t)g.H * g.W;
+        GemmProblem p;
+        p.M = g.Cin; p.N = xpos; p.K = Kg;
+        p.A.st = as_staged(wf, g.Cin, Kg);
+        p.conv = gsrc1;
+        p.D = dX; p.ldd = HW;
+        p.col_group = HW; p.group_stride = (int64_t)g.Cin * HW;
+        p.splitk_ws = skp; p.splitk_ws_bytes = skb;
+        rc = gemm(p, stream);
+        if (rc) return rc;
+    }
+    {
+        // T[c][(k',l',o)] = sum_{(b,u,v)} X[(b,u,v)][c] * dO[(b, s*u - pad + k', s*v - pad + l')][o]
+        GemmProblem p;
+        p.M = g.Cin; p.N = Kg; p.K = xpos;
+        p.A.st = as_staged(xh, xpos, g.Cin); p.A.mn_major = true;
+        p.B.mn_major = true;
+        p.conv = gsrc1;
+        p.conv.mode = 2;
+        p.D = T; p.ldd = Kg;
+        p.splitk_ws = skp; p.splitk_ws_bytes = skb;
+        rc = gemm(p, stream);
+        if (rc) return rc;
+        const long long total = (long long)g.Cout * g.Cin * g.kh * g.kw;
+        permute_dw_convT_kernel<<<grid_for(total, 256), 256, 0, stream>>>(T, g.Cout, g.Cin, g.kh, g.kw, dW);
+        count_launch();
+        NNB_CUDA_OK(cudaGetLastError());
     }
     return NNB_OK;
 }

@@ -63,6 +63,12 @@ struct KArgs {
     int tma_store;  // 1: epilogue writes D/Z through TMA (needs 16-byte aligned rows)
     int bias_vec;   // 1: bias pointer 16-byte aligned (float4 loads)
     unsigned long long* clk_out;  // optional: CTA 0 writes {SM cycles, ns} of its lifetime (clock probe)
+    // implicit-GEMM convolution (common.cuh: ConvOperand); conv_mode 0 = plain B operand
+    int conv_mode;
+    int cv_P, cv_Q;             // position grid per image
+    int cv_bw, cv_bh;           // box extent in (q, p); the image extent follows from the rows per box
+    int cv_sp0, cv_sp1, cv_off0, cv_off1, cv_dk0, cv_dk1, cv_kw;
+    int cv_cblocks;             // C / 64
     int stages;     // operand ring depth actually used (<= Cfg::STAGES; experiments only)
     int debug;      // profiling experiments only (NNB_GEMM_DEBUG): 1 = epilogue skips the stores, 2 = also skips the TMEM loads
 };
@@ -91,6 +97,18 @@ __device__ __forceinline__ void tile_coords(int r, int num_m, int num_n, int& m_
     const int in_g = r - g * per_group;
     n_blk = in_g / gm;
     m_blk = first_m + (in_g - n_blk * gm);
+}
+
+// 4-D box origin (c, x, y, b) of the rows starting at position m0 for tap `tap`, channel block cb.
+__device__ __forceinline__ void conv_coords(const KArgs& p, int m0, int tap, int cb, int& c0, int& x0, int& y0, int& b0) {
+    const int q0 = m0 % p.cv_Q;
+    const int t = m0 / p.cv_Q;
+    const int p0 = t % p.cv_P;
+    b0 = t / p.cv_P;
+    const int kk = tap / p.cv_kw, ll = tap - kk * p.cv_kw;
+    c0 = cb * 64;
+    x0 = q0 * p.cv_sp1 - p.cv_off1 + ll * p.cv_dk1;
+    y0 = p0 * p.cv_sp0 - p.cv_off0 + kk * p.cv_dk0;
 }
 
 __device__ __forceinline__ float apply_act(float x, int act, float beta) {
@@ -220,7 +238,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                             for (int i = 0; i < BM / 64; ++i)
                                 ptx::tma_load_3d_cg<CG>(sa + i * (BK * 128), &maps.a[s], fb, m0 + i * 64, k0, ba);
                         }
-                        if (!B_MN) {
+                        if (p.conv_mode != 0) {
+                            int c0, x0, y0, b0;
+                            if (!B_MN) {
+                                // rows = BNL consecutive positions, k-block = (tap, 64 channels): ONE box
+                                const int kb = k0 / BK, tap = kb / p.cv_cblocks;
+                                conv_coords(p, n0, tap, kb - tap * p.cv_cblocks, c0, x0, y0, b0);
+                                ptx::tma_load_4d_cg<CG>(sb, &maps.b[s], fb, c0, x0, y0, b0);
+                            } else {
+                                // k-block = 64 consecutive positions; every 64-column atom is (tap, 64 channels)
+#pragma unroll
+                                for (int i = 0; i < BNL / 64; ++i) {
+                                    const int cbi = (n0 + i * 64) / 64, tap = cbi / p.cv_cblocks;
+                                    conv_coords(p, k0, tap, cbi - tap * p.cv_cblocks, c0, x0, y0, b0);
+                                    ptx::tma_load_4d_cg<CG>(sb + i * (BK * 128), &maps.b[s], fb, c0, x0, y0, b0);
+                                }
+                            }
+                        } else if (!B_MN) {
                             ptx::tma_load_3d_cg<CG>(sb, &maps.b[s], fb, k0, n0, bb);
                         } else {
 #pragma unroll
@@ -544,6 +578,40 @@ int encode_out_map(CUtensorMap* m, const float* ptr, int64_t cols, int64_t rows,
     return NNB_OK;
 }
 
+// R consecutive positions (m aligned to R) of a P x Q grid as one box (bw x bh x bb) of (q, p, image)
+bool conv_rect(int64_t R, int64_t P, int64_t Q, int sp0, int sp1, int* bw, int* bh, int* bb) {
+    int64_t w = std::min<int64_t>(Q, R);
+    if (Q % w != 0 || R % w != 0) return false;
+    int64_t h = std::min<int64_t>(P, R / w);
+    if (w < Q && h != 1) return false;        // a partial row cannot continue on the next line
+    if (P % h != 0 || (R / w) % h != 0) return false;
+    int64_t b = R / (w * h);
+    if (h < P && b != 1) return false;        // a partial image cannot continue in the next image
+    if (w * sp1 > 256 || h * sp0 > 256 || b > 256) return false;  // TMA box limits
+    *bw = (int)w; *bh = (int)h; *bb = (int)b;
+    return true;
+}
+
+// NHWC planes [B][Hs][Ws][C] as a 4-D tensor (c, x, y, b); box = 64 channels x (bw, bh, bb) pixels with the conv
+// stride as TMA traversal stride (boxDim = N * stride loads N elements, cuda.h cuTensorMapEncodeTiled)
+int encode_conv_map(CUtensorMap* m, const __nv_bfloat16* ptr, const ConvOperand& cv, int bw, int bh, int bb) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(NNB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)cv.C, (cuuint64_t)cv.Ws, (cuuint64_t)cv.Hs, (cuuint64_t)cv.B};
+    cuuint64_t strides[3] = {(cuuint64_t)cv.C * 2, (cuuint64_t)cv.Ws * cv.C * 2, (cuuint64_t)cv.Hs * cv.Ws * cv.C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(bw * cv.sp1), (cuuint32_t)(bh * cv.sp0), (cuuint32_t)bb};
+    cuuint32_t es[4] = {1, (cuuint32_t)cv.sp1, (cuuint32_t)cv.sp0, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15))
+        return fail(NNB_ERR_INVALID, "conv planes not 16-byte aligned for TMA");
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(NNB_ERR_CUDA, "cuTensorMapEncodeTiled (conv planes) failed (%d): C=%lld W=%lld H=%lld B=%lld box=%dx%dx%d stride %dx%d",
+                    (int)r, (long long)cv.C, (long long)cv.Ws, (long long)cv.Hs, (long long)cv.B, bw, bh, bb, cv.sp0, cv.sp1);
+    return NNB_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN, int CG>
 int launch(const GemmMaps& maps, const KArgs& ka, int grid, cudaStream_t stream) {
     using C = Cfg<BN, CG>;
@@ -594,6 +662,16 @@ int launch_major(bool a_mn, bool b_mn, const GemmMaps& maps, const KArgs& ka, in
 
 }  // namespace
 
+bool gemm_conv_supported(int mode, int64_t C, int64_t P, int64_t Q, int sp0, int sp1) {
+    if (C <= 0 || C % 64 != 0 || P <= 0 || Q <= 0) return false;
+    int a, b, c;
+    if (mode == 2) return conv_rect(64, P, Q, sp0, sp1, &a, &b, &c);
+    // mode 1: some tile width must be tileable (the search in gemm() skips the others)
+    for (int r : {32, 64, 128, 256})
+        if (conv_rect(r, P, Q, sp0, sp1, &a, &b, &c)) return true;
+    return false;
+}
+
 size_t gemm_splitk_ws_bytes(int64_t M, int64_t N, int64_t K, int64_t batch) {
     // worst case the heuristic may pick: <= 2 * SMs partial tiles of 128 x 256 worth of output
     (void)K;
@@ -607,7 +685,17 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     NNB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.batch > 0, "gemm: non-positive dimension");
     NNB_REQUIRE(g.D != nullptr, "gemm: null output");
     NNB_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "gemm: dim too large");
-    const bool x3 = g.A.st.lo != nullptr && g.B.st.lo != nullptr;
+    const bool conv = g.conv.mode != 0;
+    if (conv) {
+        NNB_REQUIRE(g.conv.mode == 1 || g.conv.mode == 2, "gemm: bad conv mode");
+        NNB_REQUIRE(g.conv.hi && g.conv.C > 0 && g.conv.C % 64 == 0, "gemm: conv planes need C %% 64 == 0");
+        NNB_REQUIRE(g.batch == 1 && !g.reduce_batch, "gemm: conv mode is unbatched");
+        NNB_REQUIRE((g.conv.mode == 2) == g.B.mn_major, "gemm: conv mode / B major mismatch");
+        const int64_t pos = g.conv.B * g.conv.P * g.conv.Q, kc = (int64_t)g.conv.kh * g.conv.kw * g.conv.C;
+        NNB_REQUIRE(g.conv.mode == 1 ? (g.N == pos && g.K == kc) : (g.K == pos && g.N == kc), "gemm: conv shape mismatch");
+        NNB_REQUIRE(pos < (1ll << 31), "gemm: too many conv positions");
+    }
+    const bool x3 = g.A.st.lo != nullptr && (conv ? g.conv.lo != nullptr : g.B.st.lo != nullptr);
     const bool a_mn = g.A.mn_major, b_mn = g.B.mn_major;
     const bool reduce_batch = g.reduce_batch;
     const int64_t out_batches = reduce_batch ? 1 : g.batch;
@@ -645,6 +733,10 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
                 if (force_bn && c != force_bn) continue;
                 if (cgi == 2 && c < 128) continue;
                 if (b_mn && c / cgi < 64) continue;
+                if (g.conv.mode == 1) {  // the CTA's B rows must form one pixel box
+                    int t0, t1, t2;
+                    if (!conv_rect(c / cgi, g.conv.P, g.conv.Q, g.conv.sp0, g.conv.sp1, &t0, &t1, &t2)) continue;
+                }
                 if (!force_bn && c > 32 && c / 2 >= g.N && !(b_mn && c / cgi == 64)) continue;  // half the width covers N
                 const int64_t t = ceil_div(g.M, BM * cgi) * ceil_div(g.N, c) * out_batches;
                 for (int si = 0; si < 12; ++si) {
@@ -702,13 +794,18 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
     // segment order: small terms first (lo*hi, hi*lo), then hi*hi
     const __nv_bfloat16* a_planes[3];
     const __nv_bfloat16* b_planes[3];
+    const __nv_bfloat16* b_hi = conv ? g.conv.hi : g.B.st.hi;
+    const __nv_bfloat16* b_lo = conv ? g.conv.lo : g.B.st.lo;
     if (x3) {
-        a_planes[0] = g.A.st.lo; b_planes[0] = g.B.st.hi;
-        a_planes[1] = g.A.st.hi; b_planes[1] = g.B.st.lo;
-        a_planes[2] = g.A.st.hi; b_planes[2] = g.B.st.hi;
+        a_planes[0] = g.A.st.lo; b_planes[0] = b_hi;
+        a_planes[1] = g.A.st.hi; b_planes[1] = b_lo;
+        a_planes[2] = g.A.st.hi; b_planes[2] = b_hi;
     } else {
-        a_planes[0] = g.A.st.hi; b_planes[0] = g.B.st.hi;
+        a_planes[0] = g.A.st.hi; b_planes[0] = b_hi;
     }
+    int cv_bw = 0, cv_bh = 0, cv_bb = 0;
+    if (conv && !conv_rect(g.conv.mode == 1 ? bn / cg : 64, g.conv.P, g.conv.Q, g.conv.sp0, g.conv.sp1, &cv_bw, &cv_bh, &cv_bb))
+        return fail(NNB_ERR_UNSUPPORTED, "gemm: conv position grid %lldx%lld cannot be tiled by pixel boxes", (long long)g.conv.P, (long long)g.conv.Q);
     const bool a_bcast = g.batch > 1 && g.A.st.batch <= 1;
     const bool b_bcast = g.batch > 1 && g.B.st.batch <= 1;
     for (int s = 0; s < nseg; ++s) {
@@ -725,7 +822,9 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
                             g.A.st.batch_stride, BK);
         }
         if (rc) return rc;
-        if (!b_mn) {
+        if (conv) {
+            rc = encode_conv_map(&maps.b[s], b_planes[s], g.conv, cv_bw, cv_bh, cv_bb);
+        } else if (!b_mn) {
             NNB_REQUIRE(g.B.st.rows == g.N && g.B.st.cols == g.K, "gemm: B staged shape mismatch");
             rc = encode_map(&maps.b[s], b_planes[s], g.K, g.N, g.B.st.ld, b_bcast ? 1 : g.batch,
                             g.B.st.batch_stride, bn / cg);
@@ -763,6 +862,14 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
         ka.clk_out = g.clk_out;
     }
     ka.bias_vec = g.epi.bias && (reinterpret_cast<uintptr_t>(g.epi.bias) & 15) == 0;
+    if (conv) {
+        ka.conv_mode = g.conv.mode;
+        ka.cv_P = (int)g.conv.P; ka.cv_Q = (int)g.conv.Q;
+        ka.cv_bw = cv_bw; ka.cv_bh = cv_bh;
+        ka.cv_sp0 = g.conv.sp0; ka.cv_sp1 = g.conv.sp1; ka.cv_off0 = g.conv.off0; ka.cv_off1 = g.conv.off1;
+        ka.cv_dk0 = g.conv.dk0; ka.cv_dk1 = g.conv.dk1; ka.cv_kw = g.conv.kw;
+        ka.cv_cblocks = (int)(g.conv.C / 64);
+    }
     {
         auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
         const int64_t bsd = reduce_batch ? 0 : g.batch_stride_d;

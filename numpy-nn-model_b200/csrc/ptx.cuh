@@ -173,6 +173,28 @@ __device__ __forceinline__ void tma_load_3d_cg(void* smem_dst, const CUtensorMap
     }
 }
 
+// 4-D tiled load (implicit-GEMM convolution: box = 64 channels x a rectangle of pixels x images of an NHWC plane;
+// coordinates may be negative or past the edge -- the copy engine zero-fills, which IS the conv padding).
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_cg(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                               int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    if (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+              "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+              "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+            : "memory");
+    }
+}
+
 // 2-CTA variant: data lands in this CTA's smem, the transaction bytes are signalled on the
 // barrier at the same offset in the *leader* CTA (bar address must be a shared::cluster
 // address mapped to the leader; see mapa_u32()).

@@ -102,6 +102,20 @@ _SIGNATURES = {
                                    c_void_p, c_size_t, c_void_p]),
     "nnb_conv2d_backward": (c_int, [POINTER(nnb_conv2d_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "nnb_conv2d_planes_bytes": (c_size_t, [POINTER(nnb_conv2d_desc), c_int]),
+    "nnb_conv2d_forward_ex": (c_int, [POINTER(nnb_conv2d_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_conv2d_backward_ex": (c_int, [POINTER(nnb_conv2d_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_conv_transpose2d_supported": (c_int, [POINTER(nnb_conv2d_desc), c_int, c_int]),
+    "nnb_conv_transpose2d_out_shape": (c_int, [POINTER(nnb_conv2d_desc), c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
+    "nnb_conv_transpose2d_planes_bytes": (c_size_t, [POINTER(nnb_conv2d_desc), c_int]),
+    "nnb_conv_transpose2d_workspace_bytes": (c_size_t, [POINTER(nnb_conv2d_desc), c_int, c_int, c_int, c_int]),
+    "nnb_conv_transpose2d_forward": (c_int, [POINTER(nnb_conv2d_desc), c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_conv_transpose2d_backward": (c_int, [POINTER(nnb_conv2d_desc), c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                              c_void_p]),
     "nnb_swish_forward": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "nnb_swish_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "nnb_softmax_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
@@ -505,7 +519,9 @@ def conv2d_out_hw(x_shape, w_shape, stride, pad4, dil):
     return int(ho.value), int(wo.value)
 
 
-def conv2d_forward(x, w, bias, stride, pad4, dil):
+def conv2d_forward(x, w, bias, stride, pad4, dil, keep_planes=False):
+    """Returns the NCHW output; with keep_planes a pair (output, planes) where planes is (buffer, prec) holding the
+    channels-last bf16 form of x for `conv2d_backward(..., x_planes=...)` (None when the geometry does not use planes)."""
     require_device()
     L = lib()
     x, w = _f32c(x), _f32c(w)
@@ -517,12 +533,18 @@ def conv2d_forward(x, w, bias, stride, pad4, dil):
     b = _f32c(bias).reshape(-1) if bias is not None else None
     prec = _state["prec"]
     ws = _workspace(L.nnb_conv2d_workspace_bytes(ctypes.byref(d), prec, 0))
-    _check(L.nnb_conv2d_forward(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(out), prec, _ptr(ws), ws.numel(),
-                                _stream()), "nnb_conv2d_forward")
-    return out
+    planes = None
+    if keep_planes:
+        nb = L.nnb_conv2d_planes_bytes(ctypes.byref(d), prec)
+        if nb:
+            planes = (torch.empty(nb, dtype=torch.uint8, device="cuda"), prec)
+    _check(L.nnb_conv2d_forward_ex(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(out), prec, None,
+                                   _ptr(planes[0]) if planes else None, _ptr(ws), ws.numel(), _stream()),
+           "nnb_conv2d_forward")
+    return (out, planes) if keep_planes else out
 
 
-def conv2d_backward(x, w, grad, stride, pad4, dil, need_dx=True, need_db=True):
+def conv2d_backward(x, w, grad, stride, pad4, dil, need_dx=True, need_db=True, x_planes=None):
     require_device()
     L = lib()
     x, w, grad = _f32c(x), _f32c(w), _f32c(grad)
@@ -532,8 +554,53 @@ def conv2d_backward(x, w, grad, stride, pad4, dil, need_dx=True, need_db=True):
     db = torch.empty((w.shape[0],), dtype=torch.float32, device="cuda") if need_db else None
     prec = _state["prec"]
     ws = _workspace(L.nnb_conv2d_workspace_bytes(ctypes.byref(d), prec, 1))
-    _check(L.nnb_conv2d_backward(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(grad), _ptr(dx), _ptr(dw), _ptr(db), prec,
-                                 _ptr(ws), ws.numel(), _stream()), "nnb_conv2d_backward")
+    xp_buf = x_planes[0] if (x_planes is not None and x_planes[1] == prec) else None
+    _check(L.nnb_conv2d_backward_ex(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(grad), _ptr(dx), _ptr(dw), _ptr(db), prec,
+                                    _ptr(xp_buf), _ptr(ws), ws.numel(), _stream()), "nnb_conv2d_backward")
+    return dx, dw, db
+
+
+# ---- native nn.ConvTranspose2d -------------------------------------------------------------------------------
+def conv_transpose2d_supported(x_shape, w_shape, stride, pad4, dil, out_pad):
+    d = _conv_desc(x_shape, w_shape, stride, pad4, dil)
+    return bool(lib().nnb_conv_transpose2d_supported(ctypes.byref(d), int(out_pad[0]), int(out_pad[1])))
+
+
+def conv_transpose2d_forward(x, w, bias, stride, pad4, dil, out_pad):
+    """Gather-form transposed convolution (real taps only). Returns (out, planes-of-x for backward)."""
+    require_device()
+    L = lib()
+    x, w = _f32c(x), _f32c(w)
+    d = _conv_desc(x.shape, w.shape, stride, pad4, dil)
+    op0, op1 = int(out_pad[0]), int(out_pad[1])
+    ho, wo = c_int64(), c_int64()
+    _check(L.nnb_conv_transpose2d_out_shape(ctypes.byref(d), op0, op1, ctypes.byref(ho), ctypes.byref(wo)),
+           "nnb_conv_transpose2d_out_shape")
+    out = torch.empty((x.shape[0], w.shape[0], int(ho.value), int(wo.value)), dtype=torch.float32, device="cuda")
+    b = _f32c(bias).reshape(-1) if bias is not None else None
+    prec = _state["prec"]
+    planes = (torch.empty(L.nnb_conv_transpose2d_planes_bytes(ctypes.byref(d), prec), dtype=torch.uint8, device="cuda"), prec)
+    ws = _workspace(L.nnb_conv_transpose2d_workspace_bytes(ctypes.byref(d), op0, op1, prec, 0))
+    _check(L.nnb_conv_transpose2d_forward(ctypes.byref(d), op0, op1, _ptr(x), _ptr(w), _ptr(b), _ptr(out), prec,
+                                          _ptr(planes[0]), _ptr(ws), ws.numel(), _stream()), "nnb_conv_transpose2d_forward")
+    return out, planes
+
+
+def conv_transpose2d_backward(x, w, grad, stride, pad4, dil, out_pad, need_dx=True, need_db=True, x_planes=None):
+    require_device()
+    L = lib()
+    x, w, grad = _f32c(x), _f32c(w), _f32c(grad)
+    d = _conv_desc(x.shape, w.shape, stride, pad4, dil)
+    op0, op1 = int(out_pad[0]), int(out_pad[1])
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty((w.shape[0],), dtype=torch.float32, device="cuda") if need_db else None
+    prec = _state["prec"]
+    ws = _workspace(L.nnb_conv_transpose2d_workspace_bytes(ctypes.byref(d), op0, op1, prec, 1))
+    xp_buf = x_planes[0] if (x_planes is not None and x_planes[1] == prec) else None
+    _check(L.nnb_conv_transpose2d_backward(ctypes.byref(d), op0, op1, _ptr(x), _ptr(w), _ptr(grad), _ptr(dx), _ptr(dw),
+                                           _ptr(db), prec, _ptr(xp_buf), _ptr(ws), ws.numel(), _stream()),
+           "nnb_conv_transpose2d_backward")
     return dx, dw, db
 
 

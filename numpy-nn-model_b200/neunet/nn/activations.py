@@ -141,9 +141,17 @@ class LeakyReLU(_Elementwise):
 
     def forward(self, x: Tensor):
         xp, a = x.xp, self.alpha
+        grad_fn = lambda t, alpha, grad: t.apply_grad(grad * xp.where(t.data <= 0, alpha, 1))  # noqa: E731
+        if x.device == "cuda" and x.ndim == 4:
+            from ..autograd import _Deferred, fusion_enabled
+            if fusion_enabled():
+                # pending: a BatchNorm2d that follows absorbs the activation into its kernels (DDPM ResBlock)
+                out = _Deferred.make(lambda: xp.where(x.data <= 0, a * x.data, x.data), x.shape, [x, a], "leaky_relu", True,
+                                     _f_kind="leaky_relu", _f_src=x, _f_alpha=float(a))
+                out.grad_fn = grad_fn
+                return out
         f = xp.where(x.data <= 0, a * x.data, x.data)
-        return _ActTensor(f, [x, a], "leaky_relu", x.device,
-                          lambda t, alpha, grad: t.apply_grad(grad * xp.where(t.data <= 0, alpha, 1)))
+        return _ActTensor(f, [x, a], "leaky_relu", x.device, grad_fn)
 
 
 class GELU(_Elementwise):

@@ -116,11 +116,11 @@ class _Conv2dTensor(Tensor):
         self.grad_fn = _conv2d_grad_fn
 
 
-def _conv2d_grad_fn(X: Tensor, weight: Tensor, bias, stride, pad4, dilation, grad):
+def _conv2d_grad_fn(X: Tensor, weight: Tensor, bias, stride, pad4, dilation, grad, x_planes=None):
     if X.device == "cuda":
         from ... import b200
         dx, dw, db = b200.conv2d_backward(X.data, weight.data, grad, stride, pad4, dilation,
-                                          need_dx=X.requires_grad, need_db=bias is not None)
+                                          need_dx=X.requires_grad, need_db=bias is not None, x_planes=x_planes)
     else:
         dx, dw = _cpu_backward(X.data, weight.data, grad, stride, pad4, dilation, X.requires_grad)
         db = np.sum(grad, axis=(0, 2, 3)) if bias is not None else None
@@ -157,14 +157,19 @@ class Conv2d(Module):
         self.input_size = X.shape
         pad4 = resolve_padding(self.padding, self.kernel_size, self.stride, self.dilation, X.shape[2:])
         b = self.bias
+        planes = None
         if self.device == "cuda":
             from ... import b200
-            O = b200.conv2d_forward(X.data, self.weight.data, b.data if b is not None else None,
-                                    self.stride, pad4, self.dilation)
+            # the channels-last bf16 planes of X made for the forward contraction are kept for wgrad
+            O, planes = b200.conv2d_forward(X.data, self.weight.data, b.data if b is not None else None,
+                                            self.stride, pad4, self.dilation, keep_planes=True)
         else:
             O = _cpu_forward(X.data, self.weight.data, b.data if b is not None else None,
                              self.stride, pad4, self.dilation)
-        return _Conv2dTensor(O, (X, self.weight, b, self.stride, pad4, self.dilation), "conv2d", self.device)
+        out = _Conv2dTensor(O, (X, self.weight, b, self.stride, pad4, self.dilation), "conv2d", self.device)
+        if planes is not None:
+            out.grad_fn = lambda X_, w_, b_, s_, p_, d_, grad: _conv2d_grad_fn(X_, w_, b_, s_, p_, d_, grad, x_planes=planes)
+        return out
 
     def __call__(self, X):
         return self.forward(X)

@@ -21,6 +21,17 @@ class _ConvTranspose2dTensor(Tensor):
         self.grad_fn = _convT_grad_fn
 
 
+def _convT_native_grad_fn(X: Tensor, weight, bias, stride, pad4, dilation, out_pad, planes, grad):
+    from ... import b200
+    dx, dw, db = b200.conv_transpose2d_backward(X.data, weight.data, grad, stride, pad4, dilation, out_pad,
+                                                need_dx=X.requires_grad, need_db=bias is not None, x_planes=planes)
+    if dx is not None:
+        X.apply_grad(dx)
+    weight.apply_grad(dw)
+    if bias is not None:
+        bias.apply_grad(db)
+
+
 def _convT_grad_fn(X: Tensor, Xprep: Tensor, weight, bias, dilation, unprepare, grad):
     # gradient w.r.t. the prepared input / weight / bias via the Conv2d backward ...
     _conv2d_grad_fn(Xprep, weight, bias, (1, 1), (0, 0, 0, 0), dilation, grad)
@@ -59,6 +70,16 @@ class ConvTranspose2d(Module):
         xp = X.xp
         B, C, H, W = X.shape
         s, op, pad4 = self.stride, self.output_padding, self._pad4()
+        if X.device == "cuda":
+            from ... import b200
+            if b200.conv_transpose2d_supported(X.shape, self.weight.shape, s, pad4, self.dilation, op):
+                # gather form, real taps only (no zero-stuffed copy, 1/(s0*s1) of the multiplies)
+                bd = self.bias.data if self.bias is not None else None
+                O, planes = b200.conv_transpose2d_forward(X.data, self.weight.data, bd, s, pad4, self.dilation, op)
+                out = _ConvTranspose2dTensor(O, (X, self.weight, self.bias, s, pad4, self.dilation, op, planes),
+                                             "convtranspose2d", self.device)
+                out.grad_fn = _convT_native_grad_fn
+                return out
         dk = (self.dilation[0] * (self.kernel_size[0] - 1) + 1, self.dilation[1] * (self.kernel_size[1] - 1) + 1)
         hs, ws = s[0] * H - (s[0] - 1) + op[0], s[1] * W - (s[1] - 1) + op[1]
         full = xp.zeros((B, C, hs + 2 * (dk[0] - 1), ws + 2 * (dk[1] - 1)), dtype=np.float32)

@@ -146,6 +146,8 @@ class BatchNorm2d(Module):
             raise TypeError("Input must be a tensor")
         if X.device != self.device:
             raise ValueError("Tensors must be on the same device")
+        if self.device == "cuda" and X.ndim == 4:
+            return self._forward_native(X)
         xp = X.xp
         if self.training:
             mean = xp.mean(X.data, axis=(0, 2, 3))
@@ -163,6 +165,29 @@ class BatchNorm2d(Module):
             O = self.weight.data.reshape(1, -1, 1, 1) * O + self.bias.data.reshape(1, -1, 1, 1)
         return _StaticTensor(O, (X, self.weight, self.bias, xc, inv, self.affine), "batchnorm2d", self.device, _bn2d_grad)
 
+    def _forward_native(self, X: Tensor) -> Tensor:
+        """"cuda": fused kernels (neunet.b200.bn_forward). A LeakyReLU whose result is still pending is absorbed:
+        the conv -> LeakyReLU -> BatchNorm2d group of the DDPM ResBlock is statistics + one normalising pass."""
+        from ... import b200
+        from ...autograd import _pending
+        src, alpha = X, 1.0
+        if _pending(X, "leaky_relu"):
+            src, alpha = X._f_src, X._f_alpha
+        w = self.weight.data.reshape(-1) if self.affine else None
+        b = self.bias.data.reshape(-1) if self.affine else None
+        if self.training:
+            rm, rv = self.running_mean.data, self.running_var.data
+            if not (rm.is_contiguous() and rv.is_contiguous()):
+                rm, rv = rm.contiguous(), rv.contiguous()
+                self.running_mean.data, self.running_var.data = rm, rv
+            O, mean, inv = b200.bn_forward(src.data, w, b, alpha, self.eps, self.momentum, rm, rv)
+        else:
+            mean = self.running_mean.data.reshape(-1).contiguous()
+            inv = 1 / (self.running_var.data.reshape(-1) + self.eps).sqrt()
+            O, mean, inv = b200.bn_forward(src.data, w, b, alpha, self.eps, self.momentum, stats=(mean, inv))
+        return _StaticTensor(O, (src, self.weight, self.bias, mean, inv, self.affine, alpha, self.training), "batchnorm2d",
+                             self.device, _bn2d_native_grad)
+
     def __call__(self, X):
         return self.forward(X)
 
@@ -171,6 +196,28 @@ class BatchNorm2d(Module):
 
     def eval(self):
         self.training = False
+
+
+def _bn2d_native_grad(X: Tensor, weight, bias, mean, inv, affine, alpha, training, grad):
+    from ... import b200
+    if not training:
+        # eval statistics are constants: dy/dx = lrelu'(x) * inv * w
+        w4 = weight.data.reshape(1, -1, 1, 1) if affine else 1
+        xp = X.xp
+        a = xp.where(X.data <= 0, alpha * X.data, X.data) if alpha != 1.0 else X.data
+        X.apply_grad(grad * w4 * inv.reshape(1, -1, 1, 1) * (xp.where(X.data <= 0, alpha, 1.0) if alpha != 1.0 else 1.0))
+        if affine:
+            xhat = (a - mean.reshape(1, -1, 1, 1)) * inv.reshape(1, -1, 1, 1)
+            weight.apply_grad(xp.sum(grad * xhat, axis=(0, 2, 3)).reshape(tuple(weight.data.shape)))
+            bias.apply_grad(xp.sum(grad, axis=(0, 2, 3)).reshape(tuple(bias.data.shape)))
+        return
+    w = weight.data.reshape(-1) if affine else None
+    dx, dw, db = b200.bn_backward(X.data, grad, mean, inv, w, alpha, need_dx=X.requires_grad, need_dw=affine)
+    if dx is not None:
+        X.apply_grad(dx)
+    if affine:
+        weight.apply_grad(dw.reshape(tuple(weight.data.shape)))
+        bias.apply_grad(db.reshape(tuple(bias.data.shape)))
 
 
 def _pair(v):

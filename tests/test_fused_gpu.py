@@ -211,3 +211,59 @@ def test_fused_step_captures_into_a_cuda_graph():
         g = b200.GraphedStep(step, [ids, tgt], optimizer=opt, warmup=1)
         losses = [float(g.replay().item()) for _ in range(5)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("B,C,H,W,alpha,affine", [(8, 128, 16, 16, 0.01, True), (5, 16, 7, 7, 1.0, True), (64, 256, 4, 4, 0.01, False)])
+def test_leaky_relu_batchnorm_fused_vs_torch(B, C, H, W, alpha, affine):
+    """Fused LeakyReLU + BatchNorm2d kernels vs torch fp32 (F.leaky_relu + F.batch_norm in training mode, the semantics of
+    neunet/nn/layers/batchnorm2d.py:57-115 with ddof = 0 batch statistics), forward, running stats, dx / dw / db."""
+    import torch.nn.functional as F
+    b200 = _b200()
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = torch.randn(B, C, H, W, generator=g, device="cuda") * 1.5 + 0.3
+    w = (torch.rand(C, generator=g, device="cuda") + 0.5) if affine else None
+    b = torch.randn(C, generator=g, device="cuda") if affine else None
+    rm, rv = torch.zeros(1, C, device="cuda"), torch.ones(1, C, device="cuda")
+    y, mean, inv = b200.bn_forward(x, w, b, alpha, 1e-5, 0.1, rm, rv)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True) if affine else None
+    br = b.clone().requires_grad_(True) if affine else None
+    a = F.leaky_relu(xr, alpha) if alpha != 1.0 else xr
+    ref = F.batch_norm(a, None, None, wr, br, training=True, eps=1e-5)
+    assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    am = a.detach().mean((0, 2, 3))
+    av = a.detach().var((0, 2, 3), unbiased=False)
+    assert (mean - am).abs().max().item() <= 1e-5
+    # the reference's momentum convention: running = momentum * running + (1 - momentum) * batch statistic
+    assert (rm.reshape(-1) - 0.9 * am).abs().max().item() <= 1e-5
+    assert (rv.reshape(-1) - (0.1 + 0.9 * av)).abs().max().item() <= 1e-4
+    go = torch.randn(B, C, H, W, generator=g, device="cuda")
+    ref.backward(go)
+    dx, dw, db = b200.bn_backward(x, go, mean, inv, w, alpha, need_dx=True, need_dw=affine)
+    assert (dx - xr.grad).abs().max().item() <= 5e-5 * max(1.0, xr.grad.abs().max().item())
+    if affine:
+        assert (dw - wr.grad).abs().max().item() <= 5e-5 * max(1.0, wr.grad.abs().max().item())
+        assert (db - br.grad).abs().max().item() <= 5e-5 * max(1.0, br.grad.abs().max().item())
+
+
+def test_conv_lrelu_bn_block_fused_equals_eager():
+    """conv -> LeakyReLU -> BatchNorm2d (DDPM ResBlock head) through the public API: deferred/fused vs eager."""
+    import neunet
+    import neunet.nn as nn
+    from neunet import autograd, b200
+    res = []
+    for fuse in (False, True):
+        prev = autograd.set_fusion(fuse)
+        try:
+            np.random.seed(4)
+            conv, act, bn = nn.Conv2d(8, 32, 3, 1, 1).to("cuda"), nn.LeakyReLU(0.01), nn.BatchNorm2d(32).to("cuda")
+            x = neunet.tensor(np.random.randn(6, 8, 16, 16), device="cuda", requires_grad=True)
+            with b200.precision("bf16x3"):
+                y = bn(act(conv(x)))
+                (y * y).mean().backward()
+            res.append([y.data.clone(), x.grad.clone(), conv.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone(),
+                        bn.running_var.data.clone()])
+        finally:
+            autograd.set_fusion(prev)
+    for a, b in zip(*res):
+        assert (a - b).abs().max().item() <= 1e-4 * max(b.abs().max().item(), 1e-3)
