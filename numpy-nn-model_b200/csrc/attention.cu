@@ -104,14 +104,19 @@ __device__ __forceinline__ void zero_acc(float (&acc)[TM][TN]) {
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 }
 
+// Reductions over the 16 lanes that own one row. The two half-warps of a warp own DIFFERENT rows and may diverge
+// (ragged Tq: one row live, the other padding), so each names only its own 16 lanes in the shuffle mask.
+__device__ __forceinline__ unsigned half_mask() { return (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu; }
 __device__ __forceinline__ float half_warp_sum(float v) {
+    const unsigned m = half_mask();
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
     return v;
 }
 __device__ __forceinline__ float half_warp_max(float v) {
+    const unsigned m = half_mask();
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(m, v, o));
     return v;
 }
 

@@ -200,17 +200,8 @@ class BatchNorm2d(Module):
 
 def _bn2d_native_grad(X: Tensor, weight, bias, mean, inv, affine, alpha, training, grad):
     from ... import b200
-    if not training:
-        # eval statistics are constants: dy/dx = lrelu'(x) * inv * w
-        w4 = weight.data.reshape(1, -1, 1, 1) if affine else 1
-        xp = X.xp
-        a = xp.where(X.data <= 0, alpha * X.data, X.data) if alpha != 1.0 else X.data
-        X.apply_grad(grad * w4 * inv.reshape(1, -1, 1, 1) * (xp.where(X.data <= 0, alpha, 1.0) if alpha != 1.0 else 1.0))
-        if affine:
-            xhat = (a - mean.reshape(1, -1, 1, 1)) * inv.reshape(1, -1, 1, 1)
-            weight.apply_grad(xp.sum(grad * xhat, axis=(0, 2, 3)).reshape(tuple(weight.data.shape)))
-            bias.apply_grad(xp.sum(grad, axis=(0, 2, 3)).reshape(tuple(bias.data.shape)))
-        return
+    # NB: like the reference (batchnorm2d.py:11-55) the SAME backward formula -- with its batch-sum terms -- is applied in
+    # eval mode, where mean / inv come from the running statistics
     w = weight.data.reshape(-1) if affine else None
     dx, dw, db = b200.bn_backward(X.data, grad, mean, inv, w, alpha, need_dx=X.requires_grad, need_dw=affine)
     if dx is not None:

@@ -291,6 +291,25 @@ def model_goldens():
     save("model_unet", x=x, temb=temb, noise=noise, loss=np.array(float(loss.data)), out=out.data.copy(),
          **init, **grads, **after)
 
+    # ---- examples/ddpm.ipynb's SimpleUNet (examples/models.py: build_ddpm_unet) at small widths: 8x8 images, down
+    # (8, 16, 32), up (32, 16, 8) -- same layer graph as the notebook (3 levels), one Algorithm-1 step with Adam
+    np.random.seed(0)
+    du = M.build_ddpm_unet(neunet, nn, image_size=8, down_channels=(8, 16, 32), up_channels=(32, 16, 8))
+    init = flat_params(du)
+    opt = optim.Adam(du.parameters(), lr=2e-4)
+    x0 = rng.uniform(-1, 1, (3, 3, 8, 8)).astype(f32)
+    noise = rng.randn(3, 3, 8, 8).astype(f32)
+    t_frac = np.array([0.1, 0.45, 0.9], dtype=f32)
+    a = np.array([0.95, 0.6, 0.2], dtype=f32).reshape(3, 1, 1, 1)
+    b = np.sqrt(1 - a * a).astype(f32)
+    opt.zero_grad()
+    loss, pred = M.ddpm_train_step(neunet, nn, du, opt, neunet.tensor(x0), neunet.tensor(noise), t_frac, neunet.tensor(a),
+                                   neunet.tensor(b))
+    grads = {f"g{i}": p.grad.copy() for i, p in enumerate(du.parameters())}
+    after = {f"a{i}": p.data.copy() for i, p in enumerate(du.parameters())}
+    save("model_ddpm_unet", x0=x0, noise=noise, t_frac=t_frac, a=a, b=b, loss=np.array(float(loss.data)), out=pred.data.copy(),
+         **init, **grads, **after)
+
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "models":

@@ -35,7 +35,8 @@ def install():
     names = ["require_device", "linear_forward", "linear_backward", "matmul", "matmul_backward", "softmax_forward",
              "softmax_backward", "swish_forward", "swish_backward", "rmsnorm_forward", "rmsnorm_backward", "dropout_apply",
              "attention_supported", "attention_forward", "attention_backward", "cross_entropy_forward",
-             "cross_entropy_backward", "dropout_ticket", "_cache_scope", "conv2d_forward", "conv2d_backward"]
+             "cross_entropy_backward", "dropout_ticket", "_cache_scope", "conv2d_forward", "conv2d_backward",
+             "conv_transpose2d_supported", "bn_forward", "bn_backward"]
     for n in names:
         _saved[n] = getattr(b200, n, None)
     _saved["device_prop"] = be.TorchXP.device
@@ -205,6 +206,51 @@ def install():
         if inv is None and up.numel() == len(tgt) and len(tgt) > 1:
             return d * up[:, None]
         return d * (up[0] * (inv[0] if inv is not None else 1.0))
+
+    import torch.nn.functional as F
+
+    def conv2d_forward(x, w, bias, stride, pad4, dil, keep_planes=False):
+        calls.append("conv2d_forward")
+        xp = F.pad(x, (pad4[2], pad4[3], pad4[0], pad4[1]))
+        o = F.conv2d(xp, w, bias.reshape(-1) if bias is not None else None, stride=tuple(stride), dilation=tuple(dil))
+        return (o, None) if keep_planes else o
+
+    def conv2d_backward(x, w, grad, stride, pad4, dil, need_dx=True, need_db=True, x_planes=None):
+        calls.append("conv2d_backward")
+        xl, wl = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        conv2d_forward(xl, wl, None, stride, pad4, dil).backward(grad)
+        calls.pop()
+        return (xl.grad if need_dx else None), wl.grad, (grad.sum((0, 2, 3)) if need_db else None)
+
+    def bn_forward(x, w, b, alpha, eps, momentum, running_mean=None, running_var=None, stats=None):
+        calls.append("bn_forward_lrelu" if alpha != 1.0 else "bn_forward")
+        a = torch.where(x <= 0, alpha * x, x)
+        if stats is None:
+            mean, var = a.mean((0, 2, 3)), a.var((0, 2, 3), unbiased=False)
+            inv = 1 / torch.sqrt(var + eps)
+            if running_mean is not None:
+                running_mean.mul_(momentum).add_((1 - momentum) * mean.reshape(running_mean.shape))
+                running_var.mul_(momentum).add_((1 - momentum) * var.reshape(running_var.shape))
+        else:
+            mean, inv = stats
+        y = (a - mean.reshape(1, -1, 1, 1)) * inv.reshape(1, -1, 1, 1)
+        if w is not None:
+            y = y * w.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1)
+        return y, mean, inv
+
+    def bn_backward(x, grad, mean, inv, w, alpha, need_dx=True, need_dw=True):
+        calls.append("bn_backward")
+        a = torch.where(x <= 0, alpha * x, x)
+        xh = (a - mean.reshape(1, -1, 1, 1)) * inv.reshape(1, -1, 1, 1)
+        n = x.shape[0] * x.shape[2] * x.shape[3]
+        wg = grad * (w.reshape(1, -1, 1, 1) if w is not None else 1)
+        s1, s2 = wg.sum((0, 2, 3), keepdim=True), (wg * xh).sum((0, 2, 3), keepdim=True)
+        dx = torch.where(x <= 0, alpha, 1.0) * inv.reshape(1, -1, 1, 1) * (wg - s1 / n - xh * s2 / n)
+        return dx, (grad * xh).sum((0, 2, 3)), grad.sum((0, 2, 3))
+
+    b200.conv2d_forward, b200.conv2d_backward = conv2d_forward, conv2d_backward
+    b200.conv_transpose2d_supported = lambda *a: False
+    b200.bn_forward, b200.bn_backward = bn_forward, bn_backward
 
     for n, f in dict(linear_forward=linear_forward, linear_backward=linear_backward, matmul=matmul,
                      matmul_backward=matmul_backward, softmax_forward=softmax_forward, softmax_backward=softmax_backward,

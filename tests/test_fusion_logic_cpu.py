@@ -117,3 +117,39 @@ def test_pending_results_materialise_when_read():
         finally:
             autograd.set_fusion(True)
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+def test_api_surface_and_ddpm_unet_on_the_mocked_device_match_the_reference_goldens():
+    """The whole example API surface (72 reference-generated arrays) and the DDPM UNet step through the device="cuda"
+    host logic (deferred LeakyReLU -> BatchNorm2d, eval-mode BatchNorm backward quirk, ...), kernels mocked."""
+    from conftest import load_golden
+    from test_host_vs_reference_cpu import CASES
+    import test_models
+    with mock_b200.mocked():
+        import neunet
+        import neunet.nn as nn
+        ref = load_golden("api_surface")
+        ns = {}
+        exec(CASES, ns)
+        ours = ns["run_cases"](neunet, nn, device="cuda")
+        assert sorted(ours) == sorted(ref)
+        for k in sorted(ref):
+            a, b = np.asarray(mock_b200.to_np(ours[k]), np.float64), np.asarray(ref[k], np.float64)
+            assert a.shape == b.shape, k
+            assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-12), k
+        mock_b200.calls.clear()
+
+        import models as M
+        g = load_golden("model_ddpm_unet")
+        np.random.seed(0)
+        du = M.build_ddpm_unet(neunet, nn, device="cuda", image_size=8, down_channels=(8, 16, 32), up_channels=(32, 16, 8))
+        test_models._load_params(du, g)
+        t = lambda a: neunet.tensor(a, device="cuda")  # noqa: E731
+        x_t = t(g["a"]) * t(g["x0"]) + t(g["b"]) * t(g["noise"])
+        pred = du.forward(neunet.tensor(x_t, requires_grad=False, device="cuda"), g["t_frac"])
+        loss = nn.MSELoss()(pred, t(g["noise"]))
+        loss.backward()
+        assert abs(float(mock_b200.to_np(loss.data)) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+        assert test_models._rel(pred.data, g["out"]) < 5e-5
+        test_models._check_grads_and_params(du, g, 5e-4, after=False)
+        assert "bn_forward_lrelu" in mock_b200.calls  # LeakyReLU was absorbed by the BatchNorm kernels

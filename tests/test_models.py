@@ -129,6 +129,26 @@ def _unet(device, tol):
     _check_grads_and_params(unet, g, tol * 10)
 
 
+def _ddpm_unet(device, tol):
+    """examples/ddpm.ipynb's SimpleUNet (3 levels, small widths) for one Algorithm-1 step against the unmodified reference."""
+    g = load_golden("model_ddpm_unet")
+    np.random.seed(0)
+    du = M.build_ddpm_unet(neunet, nn, device=device, image_size=8, down_channels=(8, 16, 32), up_channels=(32, 16, 8))
+    _load_params(du, g)
+    opt = Adam(du.parameters(), lr=2e-4)
+    opt.zero_grad()
+    loss, pred = M.ddpm_train_step(neunet, nn, du, opt, neunet.tensor(g["x0"], device=device),
+                                   neunet.tensor(g["noise"], device=device), g["t_frac"],
+                                   neunet.tensor(g["a"], device=device), neunet.tensor(g["b"], device=device))
+    np.testing.assert_allclose(float(loss.item()), float(g["loss"]), rtol=max(tol, 1e-5))
+    assert _rel(pred.data, g["out"]) < tol
+    _check_grads_and_params(du, g, tol * 10)
+
+
+def test_ddpm_unet_cpu():
+    _ddpm_unet("cpu", 5e-5)
+
+
 def test_gpt_cpu():
     _gpt("cpu", 2e-5)
 
@@ -155,6 +175,11 @@ def _gpu():
 @pytest.mark.gpu
 def test_gpt_gpu(_gpu):
     _gpt("cuda", 1e-4)
+
+
+@pytest.mark.gpu
+def test_ddpm_unet_gpu(_gpu):
+    _ddpm_unet("cuda", 1e-4)
 
 
 @pytest.mark.gpu
