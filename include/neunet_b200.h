@@ -216,7 +216,7 @@ int nnb_rmsnorm_backward(const float* gY, const float* X, const float* w, const 
  * exceed the 126 MB L2 in total) x `rounds`, captured into a CUDA graph and timed by CUDA events on
  * a private stream created for the measurement (ordered after the work already queued on `stream`). us_per_launch includes the split-K finishing kernel when one is used
  * (launches_per_gemm = 2). with_bias: bit 0 = add bias, bit 1 = Swish epilogue + Z side output
- * (form 0 only). Diagnostics only. */
+ * (form 0 only), bit 2 = NNB_PREC_BF16X3 operands (hi + lo planes, three products). Diagnostics only. */
 int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bias, int sets,
                           int rounds, float* us_per_launch, int* launches_per_gemm,
                           cudaStream_t stream);

@@ -69,7 +69,9 @@ __device__ __forceinline__ void load_tile(float* dst, const float* p, long long 
 // acc[TM][TN] += sum_k A(m0 + i, k) * B(k, n0 + j); B is stored [k][n] (n contiguous, float4 reads);
 // A is stored [k][m] when A_KM (float4 reads) or [m][k] (scalar reads; a warp touches <= 4 distinct rows,
 // the rest is broadcast).
-template <int TM, int TN, bool A_KM>
+// With the row-major A (scalar reads) a thread's TM rows are m0, m0 + RS, m0 + 2 RS, ...: RS = 8 makes the rows a warp
+// reads together ADJACENT (pitch 68 floats = 4 banks apart) instead of 8 rows apart (8 * 68 = 0 mod 32 banks: conflicts).
+template <int TM, int TN, bool A_KM, int RS = 1>
 __device__ __forceinline__ void tile_fma(float (&acc)[TM][TN], const float* __restrict__ A, const float* __restrict__ B,
                                          int K, int m0, int n0) {
     for (int k = 0; k < K; ++k) {
@@ -82,7 +84,7 @@ __device__ __forceinline__ void tile_fma(float (&acc)[TM][TN], const float* __re
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = A[(m0 + i) * LD + k];
+            for (int i = 0; i < TM; ++i) a[i] = A[(m0 + i * RS) * LD + k];
         }
 #pragma unroll
         for (int j = 0; j < TN; j += 4) {
@@ -289,10 +291,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const A
                 *reinterpret_cast<float4*>(P + q * LD + tn * 4) = make_float4(o[0], o[1], o[2], o[3]);
             }
         } else {
-            tile_fma<8, 4, false>(acc, dOn, Vt, a.D, tm * 8, tn * 4);
+            tile_fma<8, 4, false, 8>(acc, dOn, Vt, a.D, tm, tn * 4);  // rows tm, tm + 8, ...
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(dS + (tm * 8 + i) * LD + tn * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                *reinterpret_cast<float4*>(dS + (tm + 8 * i) * LD + tn * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
     }
     __syncthreads();
@@ -346,14 +348,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const A
             float* dst;
             int rows;
             if (team == 0) { tile_fma<8, 8, true>(acc, P, dOn, a.Tq, tm * 8, tn * 8); dst = dV; rows = a.Tk; }
-            else if (team == 1) { tile_fma<8, 8, false>(acc, dS, Kn, a.Tk, tm * 8, tn * 8); dst = dQ; rows = a.Tq; }
+            else if (team == 1) { tile_fma<8, 8, false, 8>(acc, dS, Kn, a.Tk, tm, tn * 8); dst = dQ; rows = a.Tq; }
             else { tile_fma<8, 8, true>(acc, dS, Qn, a.Tq, tm * 8, tn * 8); dst = dK; rows = a.Tk; }
             const long long hd = (long long)a.H * a.D;
             const int T_out = rows;  // (B, T_out, H, D) memory order
             if (dst != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int r = tm * 8 + i;
+                    const int r = team == 1 ? tm + 8 * i : tm * 8 + i;  // dQ's rows are interleaved (see tile_fma)
                     if (r >= rows) continue;
                     float* o = dst + ((long long)b * T_out + r) * hd + (long long)h * a.D + tn * 8;
                     if (tn * 8 + 3 < a.D) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);

@@ -79,6 +79,15 @@ extern "C" int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, 
         GemmProblem& g = probs[(size_t)s];
         g.A.st = make_staged(a, ar, ac);
         g.B.st = make_staged(b, br, bc);
+        if (with_bias & 4) {  // bf16x3: hi/lo planes, three products per k-block
+            auto* al = static_cast<__nv_bfloat16*>(bufs.get(staged_plane_bytes(1, ar, ac)));
+            auto* bl = static_cast<__nv_bfloat16*>(bufs.get(staged_plane_bytes(1, br, bc)));
+            NNB_REQUIRE(al && bl, "nnb_probe_linear_gemm: out of device memory");
+            fill_bf16_kernel<<<1024, 256, 0, stream>>>(al, (long long)(staged_plane_bytes(1, ar, ac) / 2), 23u + s);
+            fill_bf16_kernel<<<1024, 256, 0, stream>>>(bl, (long long)(staged_plane_bytes(1, br, bc) / 2), 131u + s);
+            g.A.st.lo = al;
+            g.B.st.lo = bl;
+        }
         if (form == 0) {
             g.M = M; g.N = N; g.K = K;
             if (with_bias & 1) g.epi.bias = bias;

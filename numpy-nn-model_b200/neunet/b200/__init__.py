@@ -388,14 +388,15 @@ def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, ne
 
 
 def probe_linear_gemm(M, K, N, form=0, with_bias=True, swish=False, rounds=3, sets=None):
-    """GPU-paced microseconds of one GEMM launch of an nn.Linear form (0 fwd, 1 dgrad, 2 wgrad) in bf16,
+    """GPU-paced microseconds of one GEMM launch of an nn.Linear form (0 fwd, 1 dgrad, 2 wgrad) in the current precision mode,
     over operand sets that together exceed the L2 (nnb_probe_linear_gemm). Returns (us, launches)."""
     require_device()
     per_set = 2 * (M * K + N * K + M * N) + 4 * max(M * N, M * K, N * K)  # upper bound, bytes
     if sets is None:
         sets = int(min(64, max(2, -(-(300 << 20) // per_set))))
     us, nl = c_float(0), c_int(0)
-    _check(lib().nnb_probe_linear_gemm(M, K, N, form, int(bool(with_bias)) | (2 if swish else 0), sets, rounds, ctypes.byref(us), ctypes.byref(nl),
+    flags = int(bool(with_bias)) | (2 if swish else 0) | (4 if _state["prec"] == PREC_BF16X3 else 0)
+    _check(lib().nnb_probe_linear_gemm(M, K, N, form, flags, sets, rounds, ctypes.byref(us), ctypes.byref(nl),
                                        _stream()), "nnb_probe_linear_gemm")
     return float(us.value), int(nl.value)
 
@@ -954,6 +955,18 @@ def cross_entropy_backward(saved, upstream):
     return d
 
 
+def _force(obj):
+    """Materialise deferred results (neunet/autograd.py: _Deferred) nested in lists / tuples / dicts."""
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            _force(o)
+    elif isinstance(obj, dict):
+        for o in obj.values():
+            _force(o)
+    elif hasattr(obj, "grad_fn") and hasattr(obj, "data"):
+        obj.data  # noqa: B018
+
+
 # ---- whole-step CUDA graphs ---------------------------------------------------------------------------------
 class GraphedStep:
     """Capture ``fn(*inputs)`` -- typically one whole training step (forward, loss, backward,
@@ -977,7 +990,7 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                fn(*self.inputs)
+                _force(fn(*self.inputs))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if optimizer is not None and getattr(optimizer, "_fused", None) is not None:
@@ -1014,6 +1027,7 @@ class GraphedStep:
         _rng["graph_used"] = False
         with torch.cuda.graph(self.graph):
             self.outputs = fn(*self.inputs)
+            _force(self.outputs)  # pending (deferred) results must be launched INSIDE the capture
         self._uses_rng = _rng["graph_used"]  # dropout inside: bump the device epoch before every replay
 
     def load(self, *arrays, non_blocking=True):

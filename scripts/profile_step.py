@@ -16,7 +16,7 @@ import bench  # noqa: E402  (adds the package paths)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="gpt", choices=["mlp", "gpt"])
+    ap.add_argument("--workload", default="gpt", choices=sorted(bench.WORKLOADS))
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--batch", type=int, default=0)
@@ -29,8 +29,8 @@ def main():
     b200.require_device()
     b200.set_precision("bf16")
     if args.batch:
-        (bench.GPT if args.workload == "gpt" else bench.MLP)["batch"] = args.batch
-    wl = (bench.GptWorkload if args.workload == "gpt" else bench.MlpWorkload)(neunet, nn, optim, 0)
+        bench.workload_label(args.workload)[0]["batch"] = args.batch
+    wl = bench.WORKLOADS[args.workload](neunet, nn, optim, 0)
 
     def step():
         wl.opt.zero_grad()
