@@ -208,37 +208,38 @@ __global__ void __launch_bounds__(256) gather_nhwc_kernel(const GatherNhwcArgs a
     }
 }
 
-// Wk[o][(k,l,c)] = W[o][c][k][l]; with `flip` (dgrad): Wr[i][(k',l',o)] = W[o][i][kh-1-k'][kw-1-l']
+// Wk[o][(k,l,c)] = W[o][c][k][l]; with `flip` (dgrad): Wr[i][(k',l',o)] = W[o][i][kh-1-k'][kw-1-l'].
+// One thread per (staged row r, channel c): it reads its khw taps (adjacent threads read adjacent 4*khw-byte runs
+// when the channel is W's inner index, i.e. without flip) and writes one bf16 per tap with c fastest (coalesced).
 template <bool X3>
 __global__ void stage_weight_klc_kernel(const float* __restrict__ W, int Cout, int Cin, int khw, int flip,
                                         long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    const long long total = (long long)Cout * Cin * khw;
-    const int Cc = flip ? Cout : Cin;  // channel (fastest) dimension of the staged rows
+    const int Cc = flip ? Cout : Cin;   // channel (fastest) dimension of the staged rows
+    const int R = flip ? Cin : Cout;    // staged rows
+    const long long total = (long long)R * Cc;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % Cc);
-        const long long t = idx / Cc;
-        const int tap = (int)(t % khw);
-        const int r = (int)(t / khw);
-        const float v = flip ? W[((long long)c * Cin + r) * khw + (khw - 1 - tap)]
-                             : W[((long long)r * Cin + c) * khw + tap];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const long long dst = (long long)r * ld + (long long)tap * Cc + c;
-        hi[dst] = h;
-        if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const int r = (int)(idx / Cc);
+        const float* src = flip ? W + ((long long)c * Cin + r) * khw : W + ((long long)r * Cin + c) * khw;
+        for (int tap = 0; tap < khw; ++tap) {
+            const float v = flip ? src[khw - 1 - tap] : src[tap];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const long long dst = (long long)r * ld + (long long)tap * Cc + c;
+            hi[dst] = h;
+            if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
     }
 }
 
-// dW[o][c][tap] = T[o][(tap, c)]
+// dW[o][c][tap] = T[o][(tap, c)]: one thread per (o, c) -- reads coalesced over c, writes its khw contiguous taps
 __global__ void permute_dw_kernel(const float* __restrict__ T, int Cout, int Cin, int khw, float* __restrict__ dW) {
-    const long long total = (long long)Cout * Cin * khw;
+    const long long total = (long long)Cout * Cin;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int tap = (int)(idx % khw);
-        const long long t = idx / khw;
-        const int c = (int)(t % Cin);
-        const int o = (int)(t / Cin);
-        dW[idx] = T[((long long)o * khw + tap) * Cin + c];
+        const int c = (int)(idx % Cin);
+        const int o = (int)(idx / Cin);
+        for (int tap = 0; tap < khw; ++tap) dW[idx * khw + tap] = T[((long long)o * khw + tap) * Cin + c];
     }
 }
 
@@ -252,9 +253,21 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
     const int bper = (B + gridDim.y - 1) / gridDim.y;
     const int b0 = blockIdx.y * bper, b1 = min(b0 + bper, B);
     float s = 0.f;
-    for (int b = b0; b < b1; ++b) {
-        const float* p = g + ((long long)b * C + c) * HW;
-        for (int i = threadIdx.x; i < HW; i += blockDim.x) s += p[i];
+    // the chunk's (image, pixel) pairs are walked as ONE flat range so small feature maps (4 x 4) still use every lane
+    const long long n = (long long)(b1 - b0) * HW;
+    if ((HW % 4) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        for (long long e = (long long)threadIdx.x * 4; e < n; e += 1024) {
+            const int b = b0 + (int)(e / HW);
+            const int i = (int)(e - (long long)(b - b0) * HW);
+            const float4 v = *reinterpret_cast<const float4*>(g + ((long long)b * C + c) * HW + i);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (long long e = threadIdx.x; e < n; e += 256) {
+            const int b = b0 + (int)(e / HW);
+            const int i = (int)(e - (long long)(b - b0) * HW);
+            s += g[((long long)b * C + c) * HW + i];
+        }
     }
     __shared__ float red[256];
     red[threadIdx.x] = s;
@@ -426,17 +439,16 @@ __global__ void __launch_bounds__(256) convT_interleave_kernel(const float* __re
     }
 }
 
-// dW[o][c][kh-1-k'][kw-1-l'] = T[c][((k'*kw + l')*Cout + o)]
+// dW[o][c][kh-1-k'][kw-1-l'] = T[c][((k'*kw + l')*Cout + o)]: one thread per (c, o), reads coalesced over o
 __global__ void permute_dw_convT_kernel(const float* __restrict__ T, int Cout, int Cin, int kh, int kw, float* __restrict__ dW) {
     const int khw = kh * kw;
-    const long long total = (long long)Cout * Cin * khw;
+    const long long total = (long long)Cout * Cin;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int tap = (int)(idx % khw);
-        const long long t = idx / khw;
-        const int c = (int)(t % Cin);
-        const int o = (int)(t / Cin);
-        dW[idx] = T[((long long)c * khw + (khw - 1 - tap)) * Cout + o];
+        const int o = (int)(idx % Cout);
+        const int c = (int)(idx / Cout);
+        float* dst = dW + ((long long)o * Cin + c) * khw;
+        for (int tap = 0; tap < khw; ++tap) dst[tap] = T[((long long)c * khw + (khw - 1 - tap)) * Cout + o];
     }
 }
 
@@ -508,7 +520,10 @@ int make_geo(const nnb_conv2d_desc* d, Geo* g) {
     return NNB_OK;
 }
 
-bool use_direct(const Geo& g) { return g.Cout < 32; }
+// Direct fp32 CUDA-core kernels only when BOTH the output channels and the reduction are tiny (MNIST classifier: 1 -> 8,
+// 8 -> 16): a 128-row tensor tile would be > 90 % padding there. A small Cout over a long reduction (DDPM's 128 -> 3
+// output layer, K = 1152) still belongs on the tensor cores: measured 2.2 ms per step in the direct kernels (round 2).
+bool use_direct(const Geo& g) { return g.Cout < 32 && (int64_t)g.Cin * g.kh * g.kw <= 256; }
 
 int run_gather(const GatherArgs& a, bool x3, cudaStream_t stream) {
     const long long total = a.M * ((a.Kc + 3) / 4);
@@ -595,7 +610,7 @@ int run_gather_nhwc(const GatherNhwcArgs& a, bool x3, cudaStream_t stream) {
 
 int run_stage_weight_klc(const float* W, const Geo& g, bool flip, const Planes& dst, int64_t ld, bool x3,
                          cudaStream_t stream) {
-    const long long total = (long long)g.Cout * g.Cin * g.kh * g.kw;
+    const long long total = (long long)g.Cout * g.Cin;
     if (x3) stage_weight_klc_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(W, g.Cout, g.Cin, g.kh * g.kw, flip ? 1 : 0, ld, dst.hi, dst.lo);
     else stage_weight_klc_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(W, g.Cout, g.Cin, g.kh * g.kw, flip ? 1 : 0, ld, dst.hi, dst.lo);
     count_launch();
@@ -838,7 +853,7 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
             p.splitk_ws = skp; p.splitk_ws_bytes = skb;
             rc = gemm(p, stream);
             if (rc) return rc;
-            const long long total = (long long)g.Cout * Kc;
+            const long long total = (long long)g.Cout * g.Cin;
             permute_dw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(dwt, g.Cout, g.Cin, g.kh * g.kw, dW);
             count_launch();
             NNB_CUDA_OK(cudaGetLastError());
@@ -1089,7 +1104,7 @@ int nnb_conv_transpose2d_backward(const nnb_conv2d_desc* d, int out_pad0, int ou
         p.splitk_ws = skp; p.splitk_ws_bytes = skb;
         rc = gemm(p, stream);
         if (rc) return rc;
-        const long long total = (long long)g.Cout * g.Cin * g.kh * g.kw;
+        const long long total = (long long)g.Cout * g.Cin;
         permute_dw_convT_kernel<<<grid_for(total, 256), 256, 0, stream>>>(T, g.Cout, g.Cin, g.kh, g.kw, dW);
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());

@@ -54,6 +54,25 @@ def test_conv2d_implicit_gemm_vs_torch(prec, B, Cin, Cout, HW, k, s, p):
             assert relerr(db, bias.grad) < 1e-4
 
 
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_conv2d_few_output_channels_long_reduction_vs_torch(prec):
+    """DDPM's output layer shape (128 -> 3, 3x3): few output channels over a long reduction run on the tensor cores
+    (a 3-row A tile), not in the direct kernels."""
+    b200 = _setup()
+    with b200.precision(prec):
+        gen = torch.Generator(device="cuda").manual_seed(77)
+        x = (torch.rand(8, 128, 34, 34, device="cuda", generator=gen) * 2 - 1).requires_grad_(True)
+        w = ((torch.rand(3, 128, 3, 3, device="cuda", generator=gen) * 2 - 1) / 1152 ** 0.5).requires_grad_(True)
+        bias = (torch.rand(3, device="cuda", generator=gen) - 0.5).requires_grad_(True)
+        ref = torch.nn.functional.conv2d(x, w, bias)
+        g = torch.rand(ref.shape, device="cuda", generator=gen) * 2 - 1
+        ref.backward(g)
+        out = b200.conv2d_forward(x.detach(), w.detach(), bias.detach(), (1, 1), (0, 0, 0, 0), (1, 1))
+        dx, dw, db = b200.conv2d_backward(x.detach(), w.detach(), g, (1, 1), (0, 0, 0, 0), (1, 1))
+        assert relerr(out, ref.detach()) < TOL[prec]
+        assert relerr(dx, x.grad) < TOL[prec] and relerr(dw, w.grad) < TOL[prec] and relerr(db, bias.grad) < 1e-4
+
+
 def test_conv2d_implicit_equals_materialised_col(monkeypatch):
     """Same layer through the implicit path and (fresh process env not needed: the C side reads NNB_CONV_IMPLICIT once)
     against the torch reference at both precisions is covered above; here: forward twice gives bit-identical results
