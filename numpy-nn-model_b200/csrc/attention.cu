@@ -199,6 +199,7 @@ __device__ __forceinline__ void scores_to_smem(const AttnArgs& a, const float* Q
     float acc[4][4];
     zero_acc(acc);
     tile_fma<4, 4, true>(acc, Qt, Kt, a.D, ty * 4, tx * 4);
+    __syncthreads();  // S re-uses Qt's storage: every thread must be done reading Q^T / K^T
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int q = ty * 4 + i;
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a, float* 
     float* Qt = sm;                 // [d][q]
     float* Kt = Qt + T * LD;        // [d][key]
     float* Vn = Kt + T * LD;        // [key][d]
-    float* S = Vn + T * LD;         // [q][key]
-    float* Pt = S + T * LD;         // [key][q]  (post-dropout probabilities, A operand of P.V)
+    float* S = Qt;                  // [q][key]  re-uses Q^T once the scores are in registers (3 tiles = 52 KB: 4 CTAs per SM)
+    float* Pt = Kt;                 // [key][q]  (post-dropout probabilities, A operand of P.V) re-uses K^T
     pdl_trigger();
     pdl_wait();
     const int tid = threadIdx.x;
@@ -317,8 +318,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const A
     float* Kn = Kt + T * LD;         // [key][d]   B of dQ
     float* Vt = Kn + T * LD;         // [d][key]   B of dPd
     float* dOn = Vt + T * LD;        // [q][d]     A of dPd (row-major), B of dV
-    float* P = dOn + T * LD;         // [q][key]   S -> P -> P*mask/(1-p)
-    float* dS = P + T * LD;          // [q][key]   dPd -> dS
+    float* P = Qt;                   // [q][key]   S -> P -> P*mask/(1-p); re-uses Q^T after phase 1 (6 tiles = 104 KB: 2 CTAs per SM)
+    float* dS = Kt;                  // [q][key]   dPd -> dS; re-uses K^T after phase 1
     pdl_trigger();
     pdl_wait();
     const int tid = threadIdx.x;
@@ -356,8 +357,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const A
         const int t = tid & 127, tm = t >> 4, tn = t & 15;
         float acc[8][4];
         zero_acc(acc);
+        if (tid < 128) tile_fma<8, 4, true>(acc, Qt, Kt, a.D, tm * 8, tn * 4);
+        else tile_fma<8, 4, false, 8>(acc, dOn, Vt, a.D, tm, tn * 4);  // rows tm, tm + 8, ...
+        __syncthreads();  // P / dS re-use the Q^T / K^T tiles: all reads of phase 1 are done
         if (tid < 128) {
-            tile_fma<8, 4, true>(acc, Qt, Kt, a.D, tm * 8, tn * 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int q = tm * 8 + i;
@@ -374,7 +377,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const A
                 *reinterpret_cast<float4*>(P + q * LD + tn * 4) = make_float4(o[0], o[1], o[2], o[3]);
             }
         } else {
-            tile_fma<8, 4, false, 8>(acc, dOn, Vt, a.D, tm, tn * 4);  // rows tm, tm + 8, ...
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(dS + (tm + 8 * i) * LD + tn * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -503,7 +505,7 @@ int nnb_attention_forward(const float* Q, const int64_t q_strides[4], const floa
         if (prec == NNB_PREC_BF16X3)
             lo = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(out_staged) + staged_plane_bytes(1, B * Tq, H * D));
     }
-    const size_t smem = (size_t)5 * T * LD * sizeof(float);
+    const size_t smem = (size_t)3 * T * LD * sizeof(float);
     static bool configured = false;
     if (!configured) {
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -531,7 +533,7 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
     AttnView g;
     g.p = dO;
     for (int i = 0; i < 4; ++i) g.s[i] = do_strides[i];
-    const size_t smem = (size_t)8 * T * LD * sizeof(float);
+    const size_t smem = (size_t)6 * T * LD * sizeof(float);
     static bool configured = false;
     if (!configured) {
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -776,7 +776,8 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
     const int64_t HWo = (int64_t)g.Ho * g.Wo;
     Bump ws(workspace, workspace_bytes);
     if (db) {
-        const int chunks = std::min(CHANNEL_SUM_CHUNKS, g.B);
+        // >= ~4096 elements per block: tiny feature maps otherwise drown in block-scheduling overhead
+        const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(CHANNEL_SUM_CHUNKS, g.B), ((int64_t)g.B * HWo + 4095) / 4096));
         float* part = static_cast<float*>(ws.take((size_t)CHANNEL_SUM_CHUNKS * g.Cout * 4));
         if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", ws.off);
         channel_sum_kernel<<<dim3((unsigned)g.Cout, (unsigned)chunks), 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, part);
@@ -1052,7 +1053,8 @@ int nnb_conv_transpose2d_backward(const nnb_conv2d_desc* d, int out_pad0, int ou
     const int64_t Kg = (int64_t)g.kh * g.kw * g.Cout;
     Bump ws(workspace, workspace_bytes);
     if (db) {
-        const int chunks = std::min(CHANNEL_SUM_CHUNKS, g.B);
+        // >= ~4096 elements per block: tiny feature maps otherwise drown in block-scheduling overhead
+        const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(CHANNEL_SUM_CHUNKS, g.B), ((int64_t)g.B * HWo + 4095) / 4096));
         float* part = static_cast<float*>(ws.take((size_t)CHANNEL_SUM_CHUNKS * g.Cout * 4));
         if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_backward: workspace too small (need >= %zu)", ws.off);
         channel_sum_kernel<<<dim3((unsigned)g.Cout, (unsigned)chunks), 256, 0, stream>>>(dO, g.B, g.Cout, (int)HWo, part);
