@@ -134,8 +134,10 @@ __global__ void stage_nchw_to_c_bhw_kernel(const float* __restrict__ g, int B, i
 // [Cout][Cin][kh][kw] by a small kernel.
 
 // src fp32 [B][C][HW] -> dst bf16 [B][HW][C]   (32 x 32 tiles through shared memory)
+// Cp >= C is the channel pitch of the planes (C rounded up to 8 so every pixel is a whole number of 16-byte groups);
+// the pad channels are written as zeros.
 template <bool X3>
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW,
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int Cp, int HW,
                                                            __nv_bfloat16* __restrict__ hi,
                                                            __nv_bfloat16* __restrict__ lo) {
     __shared__ float tile[32][33];
@@ -152,10 +154,10 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int hw = hw0 + r, c = c0 + tx;
-        if (hw < HW && c < C) {
-            const float v = tile[tx][r];
+        if (hw < HW && c < Cp) {
+            const float v = c < C ? tile[tx][r] : 0.f;
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const long long o = ((long long)b * HW + hw) * C + c;
+            const long long o = ((long long)b * HW + hw) * Cp + c;
             hi[o] = h;
             if (X3) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
         }
@@ -215,17 +217,19 @@ template <bool X3>
 __global__ void stage_weight_klc_kernel(const float* __restrict__ W, int Cout, int Cin, int khw, int flip,
                                         long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo) {
     const int Cc = flip ? Cout : Cin;   // channel (fastest) dimension of the staged rows
+    const int Ccp = (Cc + 7) & ~7;      // ... padded to the channel pitch of the activation planes (zeros)
     const int R = flip ? Cin : Cout;    // staged rows
-    const long long total = (long long)R * Cc;
+    const long long total = (long long)R * Ccp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % Cc);
-        const int r = (int)(idx / Cc);
-        const float* src = flip ? W + ((long long)c * Cin + r) * khw : W + ((long long)r * Cin + c) * khw;
+        const int c = (int)(idx % Ccp);
+        const int r = (int)(idx / Ccp);
+        const int cs = c < Cc ? c : 0;
+        const float* src = flip ? W + ((long long)cs * Cin + r) * khw : W + ((long long)r * Cin + cs) * khw;
         for (int tap = 0; tap < khw; ++tap) {
-            const float v = flip ? src[khw - 1 - tap] : src[tap];
+            const float v = c < Cc ? (flip ? src[khw - 1 - tap] : src[tap]) : 0.f;
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const long long dst = (long long)r * ld + (long long)tap * Cc + c;
+            const long long dst = (long long)r * ld + (long long)tap * Ccp + c;
             hi[dst] = h;
             if (X3) lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
         }
@@ -235,11 +239,12 @@ __global__ void stage_weight_klc_kernel(const float* __restrict__ W, int Cout, i
 // dW[o][c][tap] = T[o][(tap, c)]: one thread per (o, c) -- reads coalesced over c, writes its khw contiguous taps
 __global__ void permute_dw_kernel(const float* __restrict__ T, int Cout, int Cin, int khw, float* __restrict__ dW) {
     const long long total = (long long)Cout * Cin;
+    const int Cinp = (Cin + 7) & ~7;  // channel pitch of T's (tap, c) columns
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % Cin);
         const int o = (int)(idx / Cin);
-        for (int tap = 0; tap < khw; ++tap) dW[idx * khw + tap] = T[((long long)o * khw + tap) * Cin + c];
+        for (int tap = 0; tap < khw; ++tap) dW[idx * khw + tap] = T[((long long)o * khw + tap) * Cinp + c];
     }
 }
 
@@ -551,7 +556,11 @@ Staged as_staged(const Planes& p, int64_t rows, int64_t cols) {
     return s;
 }
 
-bool use_nhwc(const Geo& g) { return !use_direct(g) && (g.Cin % 8) == 0 && (g.Cout % 8) == 0; }
+// Channels-last planes for every tensor-core layer: channel counts that are not multiples of 8 (the 3-channel image of
+// the DDPM input / output layers) get a zero-padded pitch; NNB_CONV_NHWC=0 selects the generic NCHW gather instead.
+int g_nhwc = [] { const char* e = getenv("NNB_CONV_NHWC"); return e ? atoi(e) : 1; }();
+bool use_nhwc(const Geo& g) { return !use_direct(g) && (g_nhwc || ((g.Cin % 8) == 0 && (g.Cout % 8) == 0)); }
+int cpad(int c) { return (c + 7) & ~7; }
 
 // Implicit GEMM (no materialised `col`): the GEMM's B operand is read straight from the channels-last planes through
 // 4-D TMA boxes (gemm.cu, ConvOperand). Needs 64-channel k-blocks and a position grid that tiles into pixel boxes.
@@ -573,7 +582,7 @@ ConvOperand conv_operand(int mode, const Planes& src, int64_t B, int64_t C, int6
     return c;
 }
 
-size_t nhwc_bytes(int64_t positions, int64_t C) { return (size_t)round_up(positions * C * 2, 256); }
+size_t nhwc_bytes(int64_t positions, int64_t C) { return (size_t)round_up(positions * round_up(C, 8) * 2, 256); }
 Planes planes_at(void* buf, int64_t positions, int64_t C, int prec) {
     Planes p;
     p.hi = static_cast<__nv_bfloat16*>(buf);
@@ -583,17 +592,18 @@ Planes planes_at(void* buf, int64_t positions, int64_t C, int prec) {
 
 Planes take_nhwc(Bump& ws, int64_t positions, int64_t C, int prec) {
     Planes p;
-    const size_t b = (size_t)round_up(positions * C * 2, 256);
+    const size_t b = (size_t)round_up(positions * round_up(C, 8) * 2, 256);
     p.hi = static_cast<__nv_bfloat16*>(ws.take(b));
     p.lo = prec == NNB_PREC_BF16X3 ? static_cast<__nv_bfloat16*>(ws.take(b)) : nullptr;
     return p;
 }
 
 int run_to_nhwc(const float* src, int B, int C, int HW, const Planes& dst, bool x3, cudaStream_t stream) {
-    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+    const int Cp = (int)round_up(C, 8);
+    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(Cp, 32), (unsigned)B);
     NNB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv2d: too many channels / images for the layout pass");
-    if (x3) nchw_to_nhwc_kernel<true><<<grid, 256, 0, stream>>>(src, C, HW, dst.hi, dst.lo);
-    else nchw_to_nhwc_kernel<false><<<grid, 256, 0, stream>>>(src, C, HW, dst.hi, dst.lo);
+    if (x3) nchw_to_nhwc_kernel<true><<<grid, 256, 0, stream>>>(src, C, Cp, HW, dst.hi, dst.lo);
+    else nchw_to_nhwc_kernel<false><<<grid, 256, 0, stream>>>(src, C, Cp, HW, dst.hi, dst.lo);
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
@@ -610,7 +620,7 @@ int run_gather_nhwc(const GatherNhwcArgs& a, bool x3, cudaStream_t stream) {
 
 int run_stage_weight_klc(const float* W, const Geo& g, bool flip, const Planes& dst, int64_t ld, bool x3,
                          cudaStream_t stream) {
-    const long long total = (long long)g.Cout * g.Cin;
+    const long long total = (long long)round_up(g.Cout, 8) * round_up(g.Cin, 8);
     if (x3) stage_weight_klc_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(W, g.Cout, g.Cin, g.kh * g.kw, flip ? 1 : 0, ld, dst.hi, dst.lo);
     else stage_weight_klc_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(W, g.Cout, g.Cin, g.kh * g.kw, flip ? 1 : 0, ld, dst.hi, dst.lo);
     count_launch();
@@ -640,13 +650,14 @@ size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backwa
     const size_t dbp = (size_t)round_up((int64_t)CHANNEL_SUM_CHUNKS * g.Cout * 4, 256) + 256;  // db partial sums
     if (use_direct(g)) return 512 + dbp + (size_t)DIRECT_WGRAD_CHUNKS * g.Cout * g.Cin * g.kh * g.kw * 4;
     const size_t p = planes(prec);
-    const int64_t M = (int64_t)g.B * g.Ho * g.Wo, Kc = (int64_t)g.Cin * g.kh * g.kw;
-    const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
+    const int cip = use_nhwc(g) ? cpad(g.Cin) : g.Cin, cop = use_nhwc(g) ? cpad(g.Cout) : g.Cout;
+    const int64_t M = (int64_t)g.B * g.Ho * g.Wo, Kc = (int64_t)cip * g.kh * g.kw;
+    const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)cop * g.kh * g.kw;
     size_t b = 8192 + dbp;
     if (use_nhwc(g)) {  // channels-last planes of X and dO, fp32 [Cout][(k,l,c)] wgrad result
-        b += p * (size_t)round_up((int64_t)g.B * g.H * g.W * g.Cin * 2, 256);
+        b += p * (size_t)round_up((int64_t)g.B * g.H * g.W * cip * 2, 256);
         if (backward) {
-            b += p * (size_t)round_up(M * g.Cout * 2, 256);
+            b += p * (size_t)round_up(M * cop * 2, 256);
             b += (size_t)round_up((int64_t)g.Cout * Kc * 4, 256);
         }
     }
@@ -691,7 +702,8 @@ int nnb_conv2d_forward_ex(const nnb_conv2d_desc* d, const float* X, const float*
         return NNB_OK;
     }
     const bool x3 = prec == NNB_PREC_BF16X3;
-    const int64_t HWo = (int64_t)g.Ho * g.Wo, M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
+    const int cip = use_nhwc(g) ? cpad(g.Cin) : g.Cin;  // channel pitch of the planes / of col's (k, l, c) columns
+    const int64_t HWo = (int64_t)g.Ho * g.Wo, M = g.B * HWo, Kc = (int64_t)cip * g.kh * g.kw;
     Bump ws(workspace, workspace_bytes);
     const bool implicit = implicit_fwd(g);
     Planes col{nullptr, nullptr};
@@ -731,7 +743,7 @@ int nnb_conv2d_forward_ex(const nnb_conv2d_desc* d, const float* X, const float*
             p.splitk_ws = static_cast<float*>(ws.take(p.splitk_ws_bytes));
             return gemm(p, stream);
         }
-        GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+        GatherNhwcArgs a{xh.hi, xh.lo, cip, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
                          M, staged_ld(Kc), col.hi, col.lo};
         rc = run_gather_nhwc(a, x3, stream);
         if (rc) return rc;
@@ -803,8 +815,9 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
         return NNB_OK;
     }
     const bool x3 = prec == NNB_PREC_BF16X3;
-    const int64_t M = g.B * HWo, Kc = (int64_t)g.Cin * g.kh * g.kw;
-    const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)g.Cout * g.kh * g.kw;
+    const int cip = use_nhwc(g) ? cpad(g.Cin) : g.Cin, cop = use_nhwc(g) ? cpad(g.Cout) : g.Cout;
+    const int64_t M = g.B * HWo, Kc = (int64_t)cip * g.kh * g.kw;
+    const int64_t Mx = (int64_t)g.B * g.H * g.W, Kg = (int64_t)cop * g.kh * g.kw;
     const bool imp_w = implicit_fwd(g), imp_d = dX != nullptr && implicit_dgrad(g);
     Planes col{nullptr, nullptr};
     if (!imp_w) col = take_planes(ws, M, Kc, prec);
@@ -835,7 +848,7 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
         rc = run_to_nhwc(dO, g.B, g.Cout, (int)HWo, gh, x3, stream);
         if (rc) return rc;
         if (!imp_w) {
-            GatherNhwcArgs a{xh.hi, xh.lo, g.Cin, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
+            GatherNhwcArgs a{xh.hi, xh.lo, cip, g.H, g.W, g.Ho, g.Wo, g.kh, g.kw, g.s0, g.s1, g.pt, g.pl, g.d0, g.d1, 1, 1,
                              M, staged_ld(Kc), col.hi, col.lo};
             rc = run_gather_nhwc(a, x3, stream);
             if (rc) return rc;
@@ -861,7 +874,7 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
         }
         if (dX) {
             if (!imp_d) {
-                GatherNhwcArgs ga{gh.hi, gh.lo, g.Cout, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
+                GatherNhwcArgs ga{gh.hi, gh.lo, cop, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
                                   g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1, g.s0, g.s1,
                                   Mx, staged_ld(Kg), colg.hi, colg.lo};
                 rc = run_gather_nhwc(ga, x3, stream);
