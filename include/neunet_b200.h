@@ -221,6 +221,20 @@ int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bi
                           int rounds, float* us_per_launch, int* launches_per_gemm,
                           cudaStream_t stream);
 
+/* ---- gradient all-reduce over NCCL (the reference has no distributed code) -----
+ * The ONE collective of the data-parallel step: an in-place sum all-reduce of the flat fp32 gradient bucket over
+ * NVLink / NVSwitch. NCCL is resolved at run time from the libnccl.so.2 already in the process (or on the loader path):
+ * the library does not link it, and without NCCL these return NNB_ERR_UNSUPPORTED. One communicator per rank / GPU
+ * (the device current at nnb_comm_init). Rank 0 calls nnb_comm_unique_id and hands the 128 bytes to the other ranks
+ * out of band (file, MPI, torch.distributed store ...). The averaging 1 / world is not a pass of its own: it is the
+ * grad_scale of nnb_adamw_step. nnb_comm_allreduce_sum is asynchronous on `stream` and may be captured in a CUDA graph. */
+typedef struct nnb_comm nnb_comm;
+int nnb_comm_available(int* nccl_version);
+int nnb_comm_unique_id(void* id_out_128_bytes);
+int nnb_comm_init(nnb_comm** comm, const void* unique_id_128_bytes, int world, int rank);
+int nnb_comm_allreduce_sum(nnb_comm* comm, float* buf, int64_t n_elems, cudaStream_t stream);
+int nnb_comm_destroy(nnb_comm* comm);
+
 /* ---- native ConvTranspose2d (row N1 of SURVEY.md 8f) -----------------------------------------------
  * neunet/nn/layers/convtranspose2d.py:115-387: weights (out, in, kh, kw), NOT flipped; the layer is a stride-1
  * correlation over the zero-stuffed, (k-1)-padded, padding-cropped input (:165-181, 321), so the reference multiplies

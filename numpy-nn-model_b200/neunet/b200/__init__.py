@@ -116,6 +116,11 @@ _SIGNATURES = {
     "nnb_conv_transpose2d_backward": (c_int, [POINTER(nnb_conv2d_desc), c_int, c_int, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
                                               c_void_p]),
+    "nnb_comm_available": (c_int, [POINTER(c_int)]),
+    "nnb_comm_unique_id": (c_int, [c_void_p]),
+    "nnb_comm_init": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int]),
+    "nnb_comm_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "nnb_comm_destroy": (c_int, [c_void_p]),
     "nnb_swish_forward": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "nnb_swish_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "nnb_softmax_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
@@ -787,6 +792,60 @@ def dropout_apply(x, p, ticket, residual=None, want_planes=False):
     if want_planes:
         return y, ((planes_key(y.reshape(rows, cols), prec), buf) if buf is not None else None)
     return y
+
+
+# ---- gradient all-reduce inside the C-ABI (NCCL resolved at run time) -------------------------------------------------
+class NativeComm:
+    """``nnb_comm_*``: the library's own NCCL communicator for this rank. The 128-byte unique id travels through
+    `share`, a callable (bytes-or-None) -> bytes that returns rank 0's bytes on every rank; by default a
+    ``torch.distributed`` broadcast of a CPU/GPU byte tensor (any initialised backend, e.g. gloo)."""
+
+    def __init__(self, rank, world, share=None):
+        require_device()
+        L = lib()
+        if not L.nnb_comm_available(None):
+            raise RuntimeError("nnb_comm: NCCL (libnccl.so.2) is not available in this process")
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _check(L.nnb_comm_unique_id(buf), "nnb_comm_unique_id")
+        raw = bytes(buf.raw)
+        if share is None:
+            import torch.distributed as dist
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone().to(dev)
+            dist.broadcast(t, 0)
+            raw = bytes(t.cpu().numpy().tobytes())
+        else:
+            raw = share(raw if rank == 0 else None)
+        self._h = c_void_p()
+        self.rank, self.world = rank, world
+        _check(L.nnb_comm_init(ctypes.byref(self._h), ctypes.create_string_buffer(raw, 128), world, rank), "nnb_comm_init")
+        self.stream = torch.cuda.Stream()  # the collective runs beside the backward kernels
+
+    def all_reduce_(self, flat, async_op=False):
+        """In-place sum of a contiguous fp32 tensor over all ranks, on the communicator's own stream, ordered after the
+        work already queued on the current stream. Returns an event-like handle with ``wait()`` when async_op."""
+        assert flat.dtype == torch.float32 and flat.is_contiguous()
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        _check(lib().nnb_comm_allreduce_sum(self._h, _ptr(flat), flat.numel(), c_void_p(self.stream.cuda_stream)),
+               "nnb_comm_allreduce_sum")
+        flat.record_stream(self.stream)
+        comm_stream = self.stream
+
+        class _Work:
+            def wait(self_inner):
+                torch.cuda.current_stream().wait_stream(comm_stream)
+        w = _Work()
+        if not async_op:
+            w.wait()
+            return None
+        return w
+
+    def destroy(self):
+        if self._h:
+            lib().nnb_comm_destroy(self._h)
+            self._h = c_void_p()
 
 
 # ---- fused LeakyReLU + BatchNorm2d ------------------------------------------------------------------------------

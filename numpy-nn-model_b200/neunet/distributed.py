@@ -43,7 +43,10 @@ class GradBucket:
     ``param.grad`` arrays into it, runs the NCCL (or gloo, on CPU) sum all-reduce and points each
     ``param.grad`` at its slice of the reduced bucket."""
 
-    def __init__(self, params, chunk_bytes=32 << 20):
+    def __init__(self, params, chunk_bytes=32 << 20, native_comm=None):
+        """native_comm: a ``neunet.b200.NativeComm`` -- the all-reduce then goes through the library's own
+        ``nnb_comm_allreduce_sum`` (NCCL behind the C-ABI) instead of ``torch.distributed``."""
+        self.native_comm = native_comm
         self.params = list(params)
         self.sizes = [int(np.prod(p.shape)) for p in self.params]
         self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
@@ -109,6 +112,8 @@ class GradBucket:
             return None
         import torch.distributed as dist
         lo, hi = int(self.offsets[live[0]]), int(self.offsets[live[-1] + 1])
+        if self.device == "cuda" and self.native_comm is not None:
+            return self.native_comm.all_reduce_(self.flat[lo:hi], async_op=async_op)
         if self.device == "cuda":
             return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=async_op)
         import torch

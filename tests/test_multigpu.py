@@ -58,7 +58,7 @@ def _step(layers, opt, x, y, bucket=None, device="cuda"):
     return loss
 
 
-def _worker(rank, world, port, xs, ys, ret):
+def _worker(rank, world, port, xs, ys, ret, native=False):
     for p in (PKG, ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -74,7 +74,8 @@ def _worker(rank, world, port, xs, ys, ret):
     b200.set_precision("bf16x3")
     layers = _build("cuda")
     params = _params(layers)
-    bucket = GradBucket(params, chunk_bytes=16 << 10)  # several chunks per step
+    comm = b200.NativeComm(rank, world) if native else None  # nnb_comm_*: NCCL behind the C-ABI instead of torch.distributed
+    bucket = GradBucket(params, chunk_bytes=16 << 10, native_comm=comm)  # several chunks per step
     bucket.broadcast_parameters(0)
     opt = Adam(params, lr=1e-2, eps=1e-3)  # large eps: near-zero gradients must not turn round-off into sign flips
     opt.grad_scale = 1.0 / world
@@ -85,11 +86,14 @@ def _worker(rank, world, port, xs, ys, ret):
     torch.cuda.synchronize()
     ret[rank] = [p.data.cpu().numpy().copy() for p in params]
     dist.barrier()
+    if comm is not None:
+        comm.destroy()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("native", [False, True], ids=["torch.distributed", "nnb_comm"])
 @pytest.mark.parametrize("world", [2])
-def test_nccl_ranks_equal_single_gpu_on_concatenated_batch(world):
+def test_nccl_ranks_equal_single_gpu_on_concatenated_batch(world, native):
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} CUDA devices")
     import torch.multiprocessing as mp
@@ -111,7 +115,7 @@ def test_nccl_ranks_equal_single_gpu_on_concatenated_batch(world):
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, xs, ys, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, xs, ys, ret, native)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
