@@ -286,6 +286,19 @@ int nnb_bn_backward_apply(const float* x, const float* grad, const float* mean, 
                           const double* sums, double count, int64_t B, int64_t C, int64_t HW, float alpha,
                           float* dx, float* dw, float* db, cudaStream_t stream);
 
+/* ---- nn.Embedding (row N4 of SURVEY.md 8f) ----------------------------------------------------------
+ * neunet/nn/layers/embedding.py:61-75: forward = weight[ids]; backward through Tensor.__getitem__ ASSIGNS
+ * (neunet/autograd.py:909-910), so with duplicate ids the LAST occurrence wins and the other rows' gradients are dropped.
+ * nnb_embedding_backward reproduces that deterministically (atomicMax of the position per row, then the winner copies).
+ * ids: int32 or int64 device array of n entries; negative ids wrap like NumPy; ids outside [-V, V) (IndexError in the
+ * reference) yield NaN rows forward and are ignored backward. dW [V, D] is fully overwritten (zeros for untouched rows).
+ * workspace: nnb_embedding_workspace_bytes(V). */
+int nnb_embedding_forward(const float* W, const void* ids, int ids_are_int64, int64_t n, int64_t V, int64_t D, float* out,
+                          cudaStream_t stream);
+size_t nnb_embedding_workspace_bytes(int64_t V);
+int nnb_embedding_backward(const void* ids, int ids_are_int64, const float* grad, int64_t n, int64_t V, int64_t D, float* dW,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- Fused attention for short sequences (row N4 of SURVEY.md 8f) -------------------------------
  * examples/gpt.ipynb cell 2 l.25-40 as ONE kernel per direction:
  *   scores = q . kT / scale; scores = where(mask, fill, scores); p = softmax(scores, -1);

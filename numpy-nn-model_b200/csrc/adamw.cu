@@ -234,6 +234,7 @@ int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stre
 int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, int mode, float grad_scale,
                    cudaStream_t stream) {
+    NNB_RANGE("nnb_adamw_step");
     NNB_REQUIRE(opt, "nnb_adamw_step: null handle");
     NNB_REQUIRE(step >= 0, "nnb_adamw_step: step must be >= 1, or 0 to use the device-resident counter");
     NNB_REQUIRE(mode == NNB_OPT_ADAM_L2 || mode == NNB_OPT_ADAMW, "nnb_adamw_step: bad mode");

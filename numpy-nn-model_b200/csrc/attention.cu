@@ -490,6 +490,7 @@ int nnb_attention_forward(const float* Q, const int64_t q_strides[4], const floa
                           uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, float* attn, float* out,
                           void* out_staged, int prec, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D,
                           cudaStream_t stream) {
+    NNB_RANGE("nnb_attention_forward");
     AttnArgs a;
     int rc = fill_args(a, Q, q_strides, KT, kt_strides, V, v_strides, mask, mask_kind, mask_cmp, mask_strides, fill, scale, p,
                        seed, call_id, epoch, epoch_dev, B, H, Tq, Tk, D);
@@ -523,6 +524,7 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
                            uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, const float* dO,
                            const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t B, int64_t H,
                            int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream) {
+    NNB_RANGE("nnb_attention_backward");
     AttnArgs a;
     int rc = fill_args(a, Q, q_strides, KT, kt_strides, V, v_strides, mask, mask_kind, mask_cmp, mask_strides, fill, scale, p,
                        seed, call_id, epoch, epoch_dev, B, H, Tq, Tk, D);

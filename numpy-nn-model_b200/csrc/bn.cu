@@ -207,6 +207,7 @@ size_t nnb_bn_workspace_bytes(int64_t B, int64_t C) {
 
 int nnb_bn_stats(const float* x, int64_t B, int64_t C, int64_t HW, float alpha, double* sums, void* workspace,
                  size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_bn_stats");
     NNB_REQUIRE(x && sums, "nnb_bn_stats: null pointer");
     int rc = check_shape(B, C, HW, "nnb_bn_stats");
     if (rc) return rc;
@@ -215,6 +216,7 @@ int nnb_bn_stats(const float* x, int64_t B, int64_t C, int64_t HW, float alpha, 
 
 int nnb_bn_finalize(const double* sums, double count, int64_t C, float eps, float momentum, float* mean,
                     float* inv_std, float* running_mean, float* running_var, cudaStream_t stream) {
+    NNB_RANGE("nnb_bn_finalize");
     NNB_REQUIRE(sums && mean && inv_std, "nnb_bn_finalize: null pointer");
     NNB_REQUIRE(C > 0 && count > 0, "nnb_bn_finalize: bad size");
     NNB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "nnb_bn_finalize: running stats come in pairs");
@@ -227,6 +229,7 @@ int nnb_bn_finalize(const double* sums, double count, int64_t C, float eps, floa
 
 int nnb_bn_apply(const float* x, const float* mean, const float* inv_std, const float* w, const float* b,
                  int64_t B, int64_t C, int64_t HW, float alpha, float* y, cudaStream_t stream) {
+    NNB_RANGE("nnb_bn_apply");
     NNB_REQUIRE(x && mean && inv_std && y, "nnb_bn_apply: null pointer");
     int rc = check_shape(B, C, HW, "nnb_bn_apply");
     if (rc) return rc;
@@ -243,6 +246,7 @@ int nnb_bn_apply(const float* x, const float* mean, const float* inv_std, const 
 int nnb_bn_backward_stats(const float* x, const float* grad, const float* mean, const float* inv_std, int64_t B,
                           int64_t C, int64_t HW, float alpha, double* sums, void* workspace, size_t workspace_bytes,
                           cudaStream_t stream) {
+    NNB_RANGE("nnb_bn_backward_stats");
     NNB_REQUIRE(x && grad && mean && inv_std && sums, "nnb_bn_backward_stats: null pointer");
     int rc = check_shape(B, C, HW, "nnb_bn_backward_stats");
     if (rc) return rc;
@@ -252,6 +256,7 @@ int nnb_bn_backward_stats(const float* x, const float* grad, const float* mean, 
 int nnb_bn_backward_apply(const float* x, const float* grad, const float* mean, const float* inv_std, const float* w,
                           const double* sums, double count, int64_t B, int64_t C, int64_t HW, float alpha,
                           float* dx, float* dw, float* db, cudaStream_t stream) {
+    NNB_RANGE("nnb_bn_backward_apply");
     NNB_REQUIRE(x && grad && mean && inv_std && sums, "nnb_bn_backward_apply: null pointer");
     NNB_REQUIRE(count > 0, "nnb_bn_backward_apply: bad count");
     int rc = check_shape(B, C, HW, "nnb_bn_backward_apply");

@@ -166,6 +166,7 @@ extern "C" {
 int nnb_cross_entropy_forward(const float* logits, const int32_t* targets, int64_t rows, int64_t C,
                               int64_t ignore_index, int reduction, float* row_loss, float* lse,
                               float* loss_out, float* inv_denom, cudaStream_t stream) {
+    NNB_RANGE("nnb_cross_entropy_forward");
     NNB_REQUIRE(logits && targets && row_loss && lse, "nnb_cross_entropy_forward: null pointer");
     NNB_REQUIRE(rows > 0 && C > 0 && C < (1ll << 31), "nnb_cross_entropy_forward: bad shape");
     NNB_REQUIRE(reduction >= 0 && reduction <= 2, "nnb_cross_entropy_forward: bad reduction");
@@ -193,6 +194,7 @@ int nnb_cross_entropy_backward(const float* logits, const int32_t* targets, cons
                                const float* inv_denom, const float* upstream, int upstream_per_row,
                                int64_t rows, int64_t C, int64_t ignore_index, float* dlogits,
                                cudaStream_t stream) {
+    NNB_RANGE("nnb_cross_entropy_backward");
     NNB_REQUIRE(logits && targets && lse && upstream && dlogits, "nnb_cross_entropy_backward: null pointer");
     NNB_REQUIRE(rows > 0 && C > 0 && C < (1ll << 31), "nnb_cross_entropy_backward: bad shape");
     const int vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0;

@@ -114,6 +114,7 @@ int nnb_comm_init(nnb_comm** comm, const void* unique_id, int world, int rank) {
 }
 
 int nnb_comm_allreduce_sum(nnb_comm* comm, float* buf, int64_t n_elems, cudaStream_t stream) {
+    NNB_RANGE("nnb_comm_allreduce_sum");
     NNB_REQUIRE(comm && comm->comm, "nnb_comm_allreduce_sum: null communicator");
     NNB_REQUIRE(buf && n_elems > 0, "nnb_comm_allreduce_sum: bad buffer");
     ncclResult_t r = nccl().AllReduce(buf, buf, (size_t)n_elems, kNcclFloat32, kNcclSum, comm->comm, stream);

@@ -30,6 +30,21 @@ int fail(int code, const char* fmt, ...);
         if (!(cond)) return ::nnb::fail(NNB_ERR_INVALID, __VA_ARGS__); \
     } while (0)
 
+// ---- NVTX ranges around the C-ABI entry points (the reference wraps its optimizer step in
+// nvtx ranges for profiling, scripts/profile_adam.py:22-43). Header-only NVTX v3: without a profiler attached a range is
+// one relaxed load and a branch. NNB_NVTX=0 in the environment removes even that.
+bool nvtx_enabled();
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) : on(nvtx_enabled()) { if (on) nvtx_push(name); }
+    ~NvtxRange() { if (on) nvtx_pop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NNB_RANGE(name) ::nnb::NvtxRange _nnb_range_(name)
+
 // Kernel-launch accounting (bench.py reports `gpu_launches`).
 void count_launch(int n = 1);
 

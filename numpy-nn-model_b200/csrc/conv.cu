@@ -689,6 +689,7 @@ int nnb_conv2d_forward(const nnb_conv2d_desc* d, const float* X, const float* Wt
 int nnb_conv2d_forward_ex(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* bias,
                           float* O, int prec, const void* X_planes, void* X_planes_out, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_conv2d_forward_ex");
     NNB_REQUIRE(X && Wt && O, "nnb_conv2d_forward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_forward: bad prec");
     Geo g{};
@@ -780,6 +781,7 @@ int nnb_conv2d_backward(const nnb_conv2d_desc* d, const float* X, const float* W
 int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float* Wt, const float* dO,
                            float* dX, float* dW, float* db, int prec, const void* X_planes, void* workspace,
                            size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_conv2d_backward_ex");
     NNB_REQUIRE(X && Wt && dO && dW, "nnb_conv2d_backward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv2d_backward: bad prec");
     Geo g{};
@@ -994,6 +996,7 @@ size_t nnb_conv_transpose2d_workspace_bytes(const nnb_conv2d_desc* d, int out_pa
 int nnb_conv_transpose2d_forward(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, const float* X, const float* Wt,
                                  const float* bias, float* O, int prec, void* X_planes_out, void* workspace,
                                  size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_conv_transpose2d_forward");
     NNB_REQUIRE(X && Wt && O, "nnb_conv_transpose2d_forward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv_transpose2d_forward: bad prec");
     TGeo t{};
@@ -1053,6 +1056,7 @@ int nnb_conv_transpose2d_forward(const nnb_conv2d_desc* d, int out_pad0, int out
 int nnb_conv_transpose2d_backward(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, const float* X, const float* Wt,
                                   const float* dO, float* dX, float* dW, float* db, int prec, const void* X_planes,
                                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_conv_transpose2d_backward");
     NNB_REQUIRE(X && Wt && dO && dW, "nnb_conv_transpose2d_backward: null pointer");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_conv_transpose2d_backward: bad prec");
     TGeo t{};

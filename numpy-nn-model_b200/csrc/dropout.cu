@@ -84,6 +84,7 @@ extern "C" {
 int nnb_dropout_fused(const float* x, const float* residual, float* y, int64_t rows, int64_t cols, float p,
                       uint64_t seed, uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev,
                       void* Y_staged_out, int prec, cudaStream_t stream) {
+    NNB_RANGE("nnb_dropout_fused");
     NNB_REQUIRE(x && y, "nnb_dropout: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0, "nnb_dropout: bad size");
     NNB_REQUIRE(p >= 0.f && p < 1.f, "nnb_dropout: p must be in [0, 1)");

@@ -375,6 +375,7 @@ using namespace nnb;
 extern "C" {
 
 int nnb_swish_forward(const float* x, float* y, int64_t n, float beta, cudaStream_t stream) {
+    NNB_RANGE("nnb_swish_forward");
     NNB_REQUIRE(x && y && n > 0, "nnb_swish_forward: bad arguments");
     const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     NNB_CUDA_OK(launch_pdl(swish_kernel<false>, dim3(ew_grid(vec ? (n + 3) / 4 : n, 256)), dim3(256), 0, stream, x,
@@ -386,6 +387,7 @@ int nnb_swish_forward(const float* x, float* y, int64_t n, float beta, cudaStrea
 
 int nnb_swish_backward(const float* x, const float* grad, float* dx, int64_t n, float beta,
                        cudaStream_t stream) {
+    NNB_RANGE("nnb_swish_backward");
     NNB_REQUIRE(x && grad && dx && n > 0, "nnb_swish_backward: bad arguments");
     const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad) |
                       reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
@@ -398,6 +400,7 @@ int nnb_swish_backward(const float* x, const float* grad, float* dx, int64_t n, 
 
 int nnb_softmax_forward(const float* x, float* y, int64_t outer, int64_t n, int64_t inner,
                         cudaStream_t stream) {
+    NNB_RANGE("nnb_softmax_forward");
     NNB_REQUIRE(x && y, "nnb_softmax_forward: null pointer");
     NNB_REQUIRE(outer > 0 && n > 0 && inner > 0 && n < (1ll << 31), "nnb_softmax_forward: bad shape");
     if (inner == 1) {
@@ -415,6 +418,7 @@ int nnb_softmax_forward(const float* x, float* y, int64_t outer, int64_t n, int6
 
 int nnb_softmax_backward(const float* y, const float* grad, float* dx, int64_t outer, int64_t n,
                          int64_t inner, cudaStream_t stream) {
+    NNB_RANGE("nnb_softmax_backward");
     NNB_REQUIRE(y && grad && dx, "nnb_softmax_backward: null pointer");
     NNB_REQUIRE(outer > 0 && n > 0 && inner > 0 && n < (1ll << 31), "nnb_softmax_backward: bad shape");
     if (inner == 1) {
@@ -432,6 +436,7 @@ int nnb_softmax_backward(const float* y, const float* grad, float* dx, int64_t o
 
 int nnb_rmsnorm_forward(const float* X, const float* w, const float* b, float* Y, float* X_std,
                         float* X_norm, int64_t rows, int64_t cols, float eps, cudaStream_t stream) {
+    NNB_RANGE("nnb_rmsnorm_forward");
     NNB_REQUIRE(X && w && Y, "nnb_rmsnorm_forward: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_forward: bad shape");
     const long long blocks = ceil_div(rows * 32, 256);
@@ -446,6 +451,7 @@ int nnb_rmsnorm_forward_fused(const float* X, const float* A, float p, uint64_t 
                               uint64_t epoch, const uint64_t* epoch_dev, float* S, const float* w, const float* b,
                               float* Y, float* X_std, void* Y_staged_out, int prec, int64_t rows, int64_t cols,
                               float eps, cudaStream_t stream) {
+    NNB_RANGE("nnb_rmsnorm_forward_fused");
     NNB_REQUIRE(X && w && Y, "nnb_rmsnorm_forward_fused: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0, "nnb_rmsnorm_forward_fused: bad shape");
     NNB_REQUIRE(A == nullptr || S != nullptr, "nnb_rmsnorm_forward_fused: the residual prologue needs the sum output S");
@@ -491,6 +497,7 @@ int nnb_rmsnorm_backward_acc(const float* gY, const float* X, const float* w, co
                              const float* X_norm, const float* dX_add, float* dX, float* dw, float* db,
                              int64_t rows, int64_t cols, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream) {
+    NNB_RANGE("nnb_rmsnorm_backward_acc");
     (void)X_norm;  // recomputed as X / X_std: cheaper than reading a second [rows, cols] array
     NNB_REQUIRE(gY && X && w && X_std && dX, "nnb_rmsnorm_backward: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0 && cols < (1ll << 31), "nnb_rmsnorm_backward: bad shape");

@@ -49,6 +49,7 @@ size_t nnb_weight_staged_bytes(int64_t rows, int64_t cols, int prec) {
 
 int nnb_stage_weight(const float* W, int64_t rows, int64_t cols, int prec, void* dst,
                      cudaStream_t stream) {
+    NNB_RANGE("nnb_stage_weight");
     NNB_REQUIRE(W && dst, "nnb_stage_weight: null pointer");
     NNB_REQUIRE(rows > 0 && cols > 0, "nnb_stage_weight: non-positive dimension");
     NNB_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 255) == 0, "nnb_stage_weight: dst must be 256-byte aligned");
@@ -81,6 +82,7 @@ int nnb_linear_forward(const float* X, const float* W, const float* bias, float*
                        int64_t M, int64_t K, int64_t N, int act, float beta, int prec,
                        const void* W_staged, void* X_staged_out, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_linear_forward");
     NNB_REQUIRE(X && W && O, "nnb_linear_forward: null X/W/O");
     NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_forward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_forward: bad prec");
@@ -115,6 +117,7 @@ int nnb_linear_forward_staged(const void* X_staged, const void* W_staged, const 
                               float* Z, int64_t M, int64_t K, int64_t N, int act, float beta,
                               int prec, void* workspace, size_t workspace_bytes,
                               cudaStream_t stream) {
+    NNB_RANGE("nnb_linear_forward_staged");
     NNB_REQUIRE(X_staged && W_staged && O, "nnb_linear_forward_staged: null pointer");
     NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_forward_staged: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_forward_staged: bad prec");
@@ -134,6 +137,7 @@ int nnb_linear_backward(const float* X, const float* W, const float* Z, const fl
                         float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
                         float beta, int prec, const void* W_staged, const void* X_staged,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_linear_backward");
     NNB_REQUIRE((X || X_staged) && W && dO && dW, "nnb_linear_backward: null X/W/dO/dW");
     NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_backward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_backward: bad prec");

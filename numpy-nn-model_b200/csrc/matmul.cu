@@ -212,6 +212,7 @@ int nnb_matmul_forward(const float* A, const int64_t a_strides[4], const float* 
                        int64_t K, int64_t N, float alpha, int prec, void* A_staged_out,
                        void* B_staged_out, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
+    NNB_RANGE("nnb_matmul_forward");
     NNB_REQUIRE(A && B && C && a_strides && b_strides, "nnb_matmul_forward: null pointer");
     NNB_REQUIRE(b0 > 0 && b1 > 0 && M > 0 && K > 0 && N > 0, "nnb_matmul_forward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_matmul_forward: bad prec");
@@ -236,6 +237,7 @@ int nnb_matmul_backward(const float* A, const int64_t a_strides[4], const float*
                         int64_t b0, int64_t b1, int64_t M, int64_t K, int64_t N, float alpha,
                         int prec, const void* A_staged, const void* B_staged, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_matmul_backward");
     NNB_REQUIRE(A && B && G && a_strides && b_strides, "nnb_matmul_backward: null pointer");
     NNB_REQUIRE(b0 > 0 && b1 > 0 && M > 0 && K > 0 && N > 0, "nnb_matmul_backward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_matmul_backward: bad prec");

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace nnb {
@@ -30,6 +32,11 @@ int fail(int code, const char* fmt, ...) {
 static std::atomic<int> g_pdl{[] { const char* e = getenv("NNB_PDL"); return e ? atoi(e) : 1; }()};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 int set_pdl(int on) { return g_pdl.exchange(on ? 1 : 0); }
+
+static const bool g_nvtx = [] { const char* e = getenv("NNB_NVTX"); return e ? atoi(e) != 0 : true; }();
+bool nvtx_enabled() { return g_nvtx; }
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

@@ -121,6 +121,10 @@ _SIGNATURES = {
     "nnb_comm_init": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int]),
     "nnb_comm_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "nnb_comm_destroy": (c_int, [c_void_p]),
+    "nnb_embedding_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "nnb_embedding_workspace_bytes": (c_size_t, [c_int64]),
+    "nnb_embedding_backward": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
     "nnb_swish_forward": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "nnb_swish_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "nnb_softmax_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
@@ -792,6 +796,41 @@ def dropout_apply(x, p, ticket, residual=None, want_planes=False):
     if want_planes:
         return y, ((planes_key(y.reshape(rows, cols), prec), buf) if buf is not None else None)
     return y
+
+
+# ---- nn.Embedding ---------------------------------------------------------------------------------------------------
+def _ids(ids):
+    if ids.dtype not in (torch.int32, torch.int64):
+        ids = ids.to(torch.int64)
+    return ids.contiguous()
+
+
+def embedding_forward(weight, ids):
+    """weight[ids] for an integer device tensor of any shape -> (*ids.shape, D)."""
+    require_device()
+    weight = _f32c(weight)
+    V, D = weight.shape
+    ids = _ids(ids)
+    out = torch.empty(tuple(ids.shape) + (D,), dtype=torch.float32, device="cuda")
+    if ids.numel():
+        _check(lib().nnb_embedding_forward(_ptr(weight), _ptr(ids), int(ids.dtype == torch.int64), ids.numel(), V, D, _ptr(out),
+                                           _stream()), "nnb_embedding_forward")
+    return out
+
+
+def embedding_backward(ids, grad, V, out=None):
+    """Gradient of weight[ids] with the reference's assignment semantics (the LAST duplicate wins). `out`: optional
+    caller-owned [V, D] destination (e.g. a slice of the data-parallel gradient bucket)."""
+    require_device()
+    L = lib()
+    grad = _f32c(grad)
+    D = grad.shape[-1]
+    ids = _ids(ids)
+    dw = out if _usable_out(out, (V, D)) else torch.empty((V, D), dtype=torch.float32, device="cuda")
+    ws = _workspace(L.nnb_embedding_workspace_bytes(V))
+    _check(L.nnb_embedding_backward(_ptr(ids), int(ids.dtype == torch.int64), _ptr(grad), ids.numel(), V, D, _ptr(dw), _ptr(ws),
+                                    ws.numel(), _stream()), "nnb_embedding_backward")
+    return dw
 
 
 # ---- gradient all-reduce inside the C-ABI (NCCL resolved at run time) -------------------------------------------------

@@ -25,10 +25,28 @@ class Embedding(Module):
         idx = X.data if isinstance(X, Tensor) else X
         if isinstance(idx, np.ndarray):
             idx = idx.astype(np.int32)
+        if self.weight.device == "cuda":
+            from ... import b200
+            from ...backend import is_device_array
+            ids = idx if is_device_array(idx) else self.weight.xp.array(np.asarray(idx), dtype=np.int64)
+            if ids.dtype in (b200.torch.int32, b200.torch.int64) and self.weight.data.ndim == 2:
+                # gather kernel forward; backward keeps the reference's assignment semantics of weight[idx]
+                # (autograd.py:909-910: the LAST duplicate id wins) with a deterministic two-pass scatter
+                out = _StaticTensor(b200.embedding_forward(self.weight.data, ids), (self.weight, ids), "embedding", "cuda",
+                                    _embedding_grad)
+                return out
         return self.weight[idx]
 
     def __call__(self, X):
         return self.forward(X)
+
+
+def _embedding_grad(weight: Tensor, ids, grad):
+    from ... import b200
+    if not weight.requires_grad:
+        return
+    buf = getattr(weight, "_grad_buffer", None) if weight.grad is None else None  # data-parallel bucket slice
+    weight.apply_grad(b200.embedding_backward(ids, grad, weight.data.shape[0], out=buf))
 
 
 class _StaticTensor(Tensor):

@@ -36,7 +36,7 @@ def install():
              "softmax_backward", "swish_forward", "swish_backward", "rmsnorm_forward", "rmsnorm_backward", "dropout_apply",
              "attention_supported", "attention_forward", "attention_backward", "cross_entropy_forward",
              "cross_entropy_backward", "dropout_ticket", "_cache_scope", "conv2d_forward", "conv2d_backward",
-             "conv_transpose2d_supported", "bn_forward", "bn_backward"]
+             "conv_transpose2d_supported", "bn_forward", "bn_backward", "embedding_forward", "embedding_backward"]
     for n in names:
         _saved[n] = getattr(b200, n, None)
     _saved["device_prop"] = be.TorchXP.device
@@ -248,6 +248,20 @@ def install():
         dx = torch.where(x <= 0, alpha, 1.0) * inv.reshape(1, -1, 1, 1) * (wg - s1 / n - xh * s2 / n)
         return dx, (grad * xh).sum((0, 2, 3)), grad.sum((0, 2, 3))
 
+    def embedding_forward(weight, ids):
+        calls.append("embedding_forward")
+        return weight[ids.to(torch.int64)]
+
+    def embedding_backward(ids, grad, V, out=None):
+        calls.append("embedding_backward")
+        flat = ids.reshape(-1).to(torch.int64)
+        g2 = grad.reshape(flat.numel(), -1)
+        dw = torch.zeros((V, g2.shape[1]), dtype=torch.float32)
+        for i in range(flat.numel()):  # assignment semantics: the last duplicate wins
+            dw[flat[i]] = g2[i]
+        return dw
+
+    b200.embedding_forward, b200.embedding_backward = embedding_forward, embedding_backward
     b200.conv2d_forward, b200.conv2d_backward = conv2d_forward, conv2d_backward
     b200.conv_transpose2d_supported = lambda *a: False
     b200.bn_forward, b200.bn_backward = bn_forward, bn_backward

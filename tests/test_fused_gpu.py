@@ -267,3 +267,22 @@ def test_conv_lrelu_bn_block_fused_equals_eager():
             autograd.set_fusion(prev)
     for a, b in zip(*res):
         assert (a - b).abs().max().item() <= 1e-4 * max(b.abs().max().item(), 1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64])
+def test_embedding_gather_and_last_write_wins_scatter(dtype):
+    """nn.Embedding kernels against NumPy's own semantics of `w[ids]` / `full[ids] = grad` (the reference's backward,
+    neunet/autograd.py:909-910): with duplicate ids the LAST occurrence wins -- bit-exact (index work)."""
+    b200 = _b200()
+    rng = np.random.RandomState(0)
+    V, D = 57, 36
+    w = rng.randn(V, D).astype(np.float32)
+    ids = rng.randint(0, V, (5, 23))
+    ids[0, :6] = [3, 3, 3, 9, 9, -1]      # duplicates and a negative (wrapping) index
+    g = rng.randn(5, 23, D).astype(np.float32)
+    out = b200.embedding_forward(torch.from_numpy(w).cuda(), torch.from_numpy(ids).to(dtype).cuda())
+    np.testing.assert_array_equal(out.cpu().numpy(), w[ids])
+    full = np.zeros_like(w)
+    full[ids] = g
+    dw = b200.embedding_backward(torch.from_numpy(ids).to(dtype).cuda(), torch.from_numpy(g).cuda(), V)
+    np.testing.assert_array_equal(dw.cpu().numpy(), full)
