@@ -400,10 +400,12 @@ __global__ void direct_wgrad_finish_kernel(const float* __restrict__ partial, in
 //   k = k0 + j*s  with  k0 = (-(py + pad - (kh-1))) mod s,   source row u + j + e,  e = (py + pad - (kh-1) + k0) / s
 // i.e. a stride-1 correlation of X with an (nk0 x nk1)-tap kernel -> one implicit GEMM per class.
 
-// Wc[o][(j0, j1, c)] = W[o][c][k0y + j0*s0][k0x + j1*s1]
+// Wc[o][(j0, j1, c)] = Wt[o][c][k0y + j0*s0][k0x + j1*s1], Wt = the (out, in, kh, kw) kernel of the TRANSPOSED conv.
+// swap = 0: Wt is W itself (nn.ConvTranspose2d forward); swap = 1: Wt[o][c][k][l] = W[c][o][kh-1-k][kw-1-l] with
+// W stored (Cin_t = c rows, ...) i.e. the flipped, in/out-swapped kernel of a strided nn.Conv2d whose dgrad this is.
 template <bool X3>
 __global__ void stage_weight_class_kernel(const float* __restrict__ W, int Cout, int Cin, int kh, int kw, int k0y, int k0x,
-                                          int s0, int s1, int nk0, int nk1, long long ld, __nv_bfloat16* hi,
+                                          int s0, int s1, int nk0, int nk1, int swap, long long ld, __nv_bfloat16* hi,
                                           __nv_bfloat16* lo) {
     const long long total = (long long)Cout * nk0 * nk1 * Cin;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -413,7 +415,9 @@ __global__ void stage_weight_class_kernel(const float* __restrict__ W, int Cout,
         const int j1 = (int)(t % nk1); t /= nk1;
         const int j0 = (int)(t % nk0);
         const int o = (int)(t / nk0);
-        const float v = W[(((long long)o * Cin + c) * kh + (k0y + j0 * s0)) * kw + (k0x + j1 * s1)];
+        const int k = k0y + j0 * s0, l = k0x + j1 * s1;
+        const float v = swap ? W[(((long long)c * Cout + o) * kh + (kh - 1 - k)) * kw + (kw - 1 - l)]
+                             : W[(((long long)o * Cin + c) * kh + k) * kw + l];
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const long long dst = (long long)o * ld + ((long long)j0 * nk1 + j1) * Cin + c;
         hi[dst] = h;
@@ -628,6 +632,67 @@ int run_stage_weight_klc(const float* W, const Geo& g, bool flip, const Planes& 
     return NNB_OK;
 }
 
+
+// Gather-form transposed convolution over ready channels-last planes `xh` of the input (B, Cin, H, W): s0*s1 parity-class
+// implicit GEMMs into T, then the interleave (+ bias) into O (B, Cout, Ho, Wo). Shared by nn.ConvTranspose2d forward
+// (swap = 0) and by the dgrad of a strided nn.Conv2d (swap = 1: "input" = dO, weights flipped and in/out swapped).
+int tconv_classes(const TGeo& t, const Planes& xh, const float* Wt, int swap, const float* bias, float* O, int prec, Bump ws,
+                  cudaStream_t stream) {
+    const Geo& g = t.g;
+    const bool x3 = prec == NNB_PREC_BF16X3;
+    const int64_t N = (int64_t)g.B * t.P * t.Q;
+    float* T = static_cast<float*>(ws.take((size_t)round_up((int64_t)g.s0 * g.s1 * g.Cout * N * 4, 256)));
+    if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "transposed conv: workspace too small (need >= %zu)", ws.off);
+    for (int py = 0; py < g.s0; ++py) {
+        for (int px = 0; px < g.s1; ++px) {
+            int k0y, nk0, ey, k0x, nk1, ex;
+            class_taps(py, g.pt, g.kh, g.s0, &k0y, &nk0, &ey);
+            class_taps(px, g.pl, g.kw, g.s1, &k0x, &nk1, &ex);
+            const int64_t Kc = (int64_t)nk0 * nk1 * g.Cin;
+            Bump cws = ws;  // per-class scratch is reused: the stream serialises the classes
+            Planes wc = take_planes(cws, g.Cout, Kc, prec);
+            if (!cws.ok()) return fail(NNB_ERR_WORKSPACE, "transposed conv: workspace too small (need >= %zu)", cws.off);
+            const long long total = (long long)g.Cout * Kc;
+            if (x3) stage_weight_class_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, k0y, k0x, g.s0, g.s1, nk0, nk1, swap, staged_ld(Kc), wc.hi, wc.lo);
+            else stage_weight_class_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, k0y, k0x, g.s0, g.s1, nk0, nk1, swap, staged_ld(Kc), wc.hi, wc.lo);
+            count_launch();
+            NNB_CUDA_OK(cudaGetLastError());
+            GemmProblem p;
+            p.M = g.Cout; p.N = N; p.K = Kc;
+            p.A.st = as_staged(wc, g.Cout, Kc);
+            p.conv = conv_operand(1, xh, g.B, g.Cin, g.H, g.W, t.P, t.Q, nk0, nk1, 1, 1, -ey, -ex, 1, 1);
+            p.D = T + ((int64_t)(py * g.s1 + px) * g.Cout) * N; p.ldd = N;
+            p.splitk_ws_bytes = cws.remaining();
+            p.splitk_ws = static_cast<float*>(cws.take(p.splitk_ws_bytes));
+            int rc = gemm(p, stream);
+            if (rc) return rc;
+        }
+    }
+    const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
+    NNB_CUDA_OK(launch_pdl(convT_interleave_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, (const float*)T, bias, g.B, g.Cout,
+                           t.P, t.Q, g.s0, g.s1, O));
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+// The dgrad of a strided nn.Conv2d IS a transposed convolution of dO (conv2d.py:35-96 builds it by zero-stuffing): same
+// stride and padding, kernel flipped with in/out swapped. Geometry of that transposed conv, or false when the class form
+// does not apply (then the zero-stuffed gather is used).
+bool strided_dgrad_as_tconv(const Geo& g, TGeo* t) {
+    if (!g_implicit || (g.s0 == 1 && g.s1 == 1) || g.d0 != 1 || g.d1 != 1) return false;
+    if ((g.Cout % 64) != 0 || g.kh < g.s0 || g.kw < g.s1) return false;
+    Geo& q = t->g;
+    q = g;
+    q.Cin = g.Cout; q.Cout = g.Cin; q.H = g.Ho; q.W = g.Wo;  // the "input" is dO, the "output" is dX
+    q.Ho = g.s0 * g.Ho - (g.s0 - 1) + (g.kh - 1) - 2 * g.pt;  // convtranspose2d.py:165-181 with output_padding 0
+    q.Wo = g.s1 * g.Wo - (g.s1 - 1) + (g.kw - 1) - 2 * g.pl;
+    if (q.Ho != g.H || q.Wo != g.W) return false;             // asymmetric padding / ragged sizes: not a plain transposed conv
+    if ((q.Ho % g.s0) != 0 || (q.Wo % g.s1) != 0) return false;
+    t->P = q.Ho / g.s0; t->Q = q.Wo / g.s1;
+    return gemm_conv_supported(1, q.Cin, t->P, t->Q, 1, 1);
+}
+
 }  // namespace
 }  // namespace nnb
 
@@ -826,7 +891,10 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
     Planes gp{nullptr, nullptr};
     if (!use_nhwc(g)) gp = take_planes(ws, g.Cout, M, prec);
     Planes colg{nullptr, nullptr}, wr{nullptr, nullptr};
-    if (dX) {
+    TGeo tg{};
+    // stride > 1: dX as a transposed convolution of dO in parity classes (real taps only) instead of the zero-stuffed gather
+    const bool cls_d = dX != nullptr && !imp_d && use_nhwc(g) && strided_dgrad_as_tconv(g, &tg);
+    if (dX && !cls_d) {
         if (!imp_d) colg = take_planes(ws, Mx, Kg, prec);
         wr = take_planes(ws, g.Cin, Kg, prec);
     }
@@ -874,7 +942,10 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
             count_launch();
             NNB_CUDA_OK(cudaGetLastError());
         }
-        if (dX) {
+        if (cls_d) {
+            rc = tconv_classes(tg, gh, Wt, 1, nullptr, dX, prec, Bump(skp, skb), stream);
+            if (rc) return rc;
+        } else if (dX) {
             if (!imp_d) {
                 GatherNhwcArgs ga{gh.hi, gh.lo, cop, g.Ho, g.Wo, g.H, g.W, g.kh, g.kw, 1, 1,
                                   g.d0 * (g.kh - 1) - g.pt, g.d1 * (g.kw - 1) - g.pl, g.d0, g.d1, g.s0, g.s1,
@@ -1007,7 +1078,7 @@ int nnb_conv_transpose2d_forward(const nnb_conv2d_desc* d, int out_pad0, int out
                                           "(needs Cin, Cout %% 64 == 0, dilation 1, no output padding, Ho %% stride == 0)");
     const Geo& g = t.g;
     const bool x3 = prec == NNB_PREC_BF16X3;
-    const int64_t xpos = (int64_t)g.B * g.H * g.W, N = (int64_t)g.B * t.P * t.Q;
+    const int64_t xpos = (int64_t)g.B * g.H * g.W;
     Bump ws(workspace, workspace_bytes);
     Planes xh;
     if (X_planes_out != nullptr) {
@@ -1016,41 +1087,10 @@ int nnb_conv_transpose2d_forward(const nnb_conv2d_desc* d, int out_pad0, int out
     } else {
         xh = take_nhwc(ws, xpos, g.Cin, prec);
     }
-    float* T = static_cast<float*>(ws.take((size_t)round_up((int64_t)g.s0 * g.s1 * g.Cout * N * 4, 256)));
     if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_forward: workspace too small (need >= %zu)", ws.off);
     rc = run_to_nhwc(X, g.B, g.Cin, g.H * g.W, xh, x3, stream);
     if (rc) return rc;
-    for (int py = 0; py < g.s0; ++py) {
-        for (int px = 0; px < g.s1; ++px) {
-            int k0y, nk0, ey, k0x, nk1, ex;
-            class_taps(py, g.pt, g.kh, g.s0, &k0y, &nk0, &ey);
-            class_taps(px, g.pl, g.kw, g.s1, &k0x, &nk1, &ex);
-            const int64_t Kc = (int64_t)nk0 * nk1 * g.Cin;
-            Bump cws = ws;  // per-class scratch is reused: the stream serialises the classes
-            Planes wc = take_planes(cws, g.Cout, Kc, prec);
-            if (!cws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv_transpose2d_forward: workspace too small (need >= %zu)", cws.off);
-            const long long total = (long long)g.Cout * Kc;
-            if (x3) stage_weight_class_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, k0y, k0x, g.s0, g.s1, nk0, nk1, staged_ld(Kc), wc.hi, wc.lo);
-            else stage_weight_class_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(Wt, g.Cout, g.Cin, g.kh, g.kw, k0y, k0x, g.s0, g.s1, nk0, nk1, staged_ld(Kc), wc.hi, wc.lo);
-            count_launch();
-            NNB_CUDA_OK(cudaGetLastError());
-            GemmProblem p;
-            p.M = g.Cout; p.N = N; p.K = Kc;
-            p.A.st = as_staged(wc, g.Cout, Kc);
-            p.conv = conv_operand(1, xh, g.B, g.Cin, g.H, g.W, t.P, t.Q, nk0, nk1, 1, 1, -ey, -ex, 1, 1);
-            p.D = T + ((int64_t)(py * g.s1 + px) * g.Cout) * N; p.ldd = N;
-            p.splitk_ws_bytes = cws.remaining();
-            p.splitk_ws = static_cast<float*>(cws.take(p.splitk_ws_bytes));
-            rc = gemm(p, stream);
-            if (rc) return rc;
-        }
-    }
-    const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
-    NNB_CUDA_OK(launch_pdl(convT_interleave_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, (const float*)T, bias, g.B, g.Cout,
-                           t.P, t.Q, g.s0, g.s1, O));
-    count_launch();
-    NNB_CUDA_OK(cudaGetLastError());
-    return NNB_OK;
+    return tconv_classes(t, xh, Wt, 0, bias, O, prec, ws, stream);
 }
 
 int nnb_conv_transpose2d_backward(const nnb_conv2d_desc* d, int out_pad0, int out_pad1, const float* X, const float* Wt,

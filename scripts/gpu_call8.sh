@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out/c8
+PT="python -m pytest -q --tb=short -p no:cacheprovider --timeout 60 --timeout-method=thread -m gpu"
+timeout 300 $PT tests > gpurun_out/c8/pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/c8/pytest.log
+timeout 200 python bench.py --steps 30 --warmup 3 --no-also --no-x3 --watchdog 180 > gpurun_out/c8/bench_gpt.json 2> gpurun_out/c8/bench_gpt.err; echo "bench rc=$?"; head -c 300 gpurun_out/c8/bench_gpt.json; echo
+timeout 240 python bench.py --workload ddpm --steps 20 --warmup 3 --no-x3 --watchdog 220 > gpurun_out/c8/bench_ddpm.json 2> gpurun_out/c8/bench_ddpm.err; echo "bench ddpm rc=$?"; head -c 300 gpurun_out/c8/bench_ddpm.json; echo
