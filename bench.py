@@ -532,11 +532,15 @@ class GptWorkload:
         """(K, N, launches per step) of every nn.Linear on the path (gpt cell 2-7)."""
         c = self.cfg
         d, ff, V, L = c["d_model"], c["d_ff"], c["vocab"], c["layers"]
+        from neunet import autograd
+        if autograd.fusion_enabled():  # the q/k/v projections of a block run as ONE GEMM over a shared weight buffer
+            return [(d, 3 * d, L, "wq|wk|wv (one GEMM)"), (d, d, L, "attn.fc"), (d, ff, L, "ffn.fc_1"), (ff, d, L, "ffn.fc_2"),
+                    (d, V, 1, "fc_out")]
         return [(d, d, 4 * L, "wq/wk/wv/fc"), (d, ff, L, "ffn.fc_1"), (ff, d, L, "ffn.fc_2"), (d, V, 1, "fc_out")]
 
     def roofline(self, pk, b200, with_ladder=True):
-        """Dominant kernel = gemm_tcgen05_kernel. One step launches it in 12 Linear shape x form classes
-        (4 layer shapes x fwd/dgrad/wgrad); every class is timed GPU-paced on rotating operand sets > L2 and
+        """Dominant kernel = gemm_tcgen05_kernel. One step launches it in 15 Linear shape x form classes
+        (5 layer shapes x fwd/dgrad/wgrad); every class is timed GPU-paced on rotating operand sets > L2 and
         `achieved` = (sum of algorithmic 2MKN over all Linear GEMM launches of a step) / (sum of their times)."""
         c = self.cfg
         M_ = c["batch"] * c["seq"]

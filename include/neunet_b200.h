@@ -311,7 +311,9 @@ int nnb_embedding_backward(const void* ids, int ids_are_int64, const float* grad
  * 2 = int32 tensor, masked where == mask_cmp; 3 = float tensor, masked where == mask_cmp; strides over
  * (B,H,Tq,Tk), 0 on broadcast axes. attn: (B,H,Tq,Tk) contiguous (post-dropout, what the example returns).
  * out / dQ: (B,Tq,H,D) contiguous; dK / dV: (B,Tk,H,D) contiguous -- the memory order of the example's
- * reshape/transpose views, so no copy is needed either side. out_staged (nullable): bf16 planes [B*Tq][H*D].
+ * reshape/transpose views, so no copy is needed either side. out_row_pitch (backward; 0 = H*D) is the distance in floats
+ * between consecutive (b, t) rows of dQ / dK / dV: 3*H*D lets the three be the column blocks dq | dk | dv of ONE
+ * [B*T, 3*H*D] matrix, which is the upstream gradient of a fused q/k/v projection as it stands. out_staged (nullable): bf16 planes [B*Tq][H*D].
  * Dropout: p in [0,1), mask = Philox(seed, call_id, epoch | *epoch_dev) over the flat attn index, regenerated in
  * backward (nothing O(T^2) is saved). Limits: Tq, Tk, D <= 64, Tk % 4 == D % 4 == 0 (nnb_attention_supported),
  * otherwise NNB_ERR_UNSUPPORTED and the caller runs the un-fused ops. */
@@ -326,8 +328,8 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
                            const float* V, const int64_t v_strides[4], const void* mask, int mask_kind, float mask_cmp,
                            const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
                            uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, const float* dO,
-                           const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t B, int64_t H,
-                           int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream);
+                           const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t out_row_pitch,
+                           int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream);
 
 /* ---- Dropout with a device RNG (row N4 of SURVEY.md 8f) ----------------------------------------
  * neunet/nn/layers/dropout.py:17-46: y = x * mask, mask ~ Bernoulli(1-p) / (1-p); backward is the

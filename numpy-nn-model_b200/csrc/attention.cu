@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a, float* 
 //   dV = (P * mask / (1 - p))^T . dO;  dQ = dS . K;  dK = dS^T . Q
 // Teams of 64 threads (8 x 8 outputs each) run the independent products side by side.
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const AttnView dO, float* __restrict__ dQ,
-                                                       float* __restrict__ dK, float* __restrict__ dV) {
+                                                       float* __restrict__ dK, float* __restrict__ dV, long long pitch) {
     extern __shared__ __align__(16) float sm[];
     float* Qt = sm;                  // [d][q]     A of S (k-major)
     float* Qn = Qt + T * LD;         // [q][d]     B of dK
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const A
             if (team == 0) { tile_fma<8, 8, true>(acc, P, dOn, a.Tq, tm * 8, tn * 8); dst = dV; rows = a.Tk; }
             else if (team == 1) { tile_fma<8, 8, false, 8>(acc, dS, Kn, a.Tk, tm, tn * 8); dst = dQ; rows = a.Tq; }
             else { tile_fma<8, 8, true>(acc, dS, Qn, a.Tq, tm * 8, tn * 8); dst = dK; rows = a.Tk; }
-            const long long hd = (long long)a.H * a.D;
+            const long long hd = pitch;  // floats between consecutive (b, t) rows: H*D, or 3*H*D for a packed dq|dk|dv buffer
             const int T_out = rows;  // (B, T_out, H, D) memory order
             if (dst != nullptr) {
 #pragma unroll
@@ -522,8 +522,8 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
                            const float* V, const int64_t v_strides[4], const void* mask, int mask_kind, float mask_cmp,
                            const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
                            uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, const float* dO,
-                           const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t B, int64_t H,
-                           int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream) {
+                           const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t out_row_pitch,
+                           int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream) {
     NNB_RANGE("nnb_attention_backward");
     AttnArgs a;
     int rc = fill_args(a, Q, q_strides, KT, kt_strides, V, v_strides, mask, mask_kind, mask_cmp, mask_strides, fill, scale, p,
@@ -541,7 +541,9 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    NNB_CUDA_OK(launch_pdl(attn_bwd_kernel, dim3((unsigned)(B * H)), dim3(256), smem, stream, a, g, dQ, dK, dV));
+    NNB_REQUIRE(out_row_pitch == 0 || (out_row_pitch >= H * D && out_row_pitch % 4 == 0), "nnb_attention_backward: bad out_row_pitch");
+    NNB_CUDA_OK(launch_pdl(attn_bwd_kernel, dim3((unsigned)(B * H)), dim3(256), smem, stream, a, g, dQ, dK, dV,
+                           (long long)(out_row_pitch ? out_row_pitch : H * D)));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;

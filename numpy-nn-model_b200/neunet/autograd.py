@@ -680,6 +680,18 @@ class Tensor:
                 tape.append(node)
         # leaves with a `_grad_ready` hook (neunet.distributed.GradBucket.overlap_backward): the hook
         # fires right after the LAST tape node that feeds the leaf has run, i.e. when its gradient is final
+        # fused sibling Linear layers (nn/layers/linear.py: _GroupCall) run ONE backward when the last member that takes
+        # part in this tape has received its gradient: count the members first
+        gcalls = {}
+        for v in tape:
+            gc = v.__dict__.get("_b200_gcall")
+            if gc is not None:
+                gcalls[id(gc)] = gc
+                gc.expected, gc.arrived = 0, 0
+        for v in tape:
+            gc = v.__dict__.get("_b200_gcall")
+            if gc is not None:
+                gc.expected += 1
         uses = {}
         for v in tape:
             for a in v.args:

@@ -163,7 +163,7 @@ _SIGNATURES = {
     "nnb_attention_backward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                        c_void_p, c_int, c_float, POINTER(c_int64), c_float, c_float, c_float, c_uint64,
                                        c_uint32, c_uint64, c_void_p, c_void_p, POINTER(c_int64), c_void_p, c_void_p,
-                                       c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+                                       c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "nnb_cross_entropy_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
     "nnb_cross_entropy_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
@@ -1010,14 +1010,22 @@ def attention_backward(q, kT, v, mask, fill, scale, p, ticket, grad):
     B, H, Tq, D = q.shape
     Tk = kT.shape[3]
     grad = grad if grad.dtype == torch.float32 else grad.to(torch.float32)
-    dq = torch.empty((B, Tq, H, D), dtype=torch.float32, device="cuda")
-    dk = torch.empty((B, Tk, H, D), dtype=torch.float32, device="cuda")
-    dv = torch.empty((B, Tk, H, D), dtype=torch.float32, device="cuda")
+    pitch = 0
+    if Tq == Tk:
+        # dq | dk | dv as the column blocks of ONE [B*T, 3*H*D] matrix: a fused q/k/v projection (nn/layers/linear.py:
+        # _SiblingGroup) takes it as its upstream gradient without a gather
+        packed = torch.empty((B, Tq, 3, H, D), dtype=torch.float32, device="cuda")
+        dq, dk, dv = packed[:, :, 0], packed[:, :, 1], packed[:, :, 2]
+        pitch = 3 * H * D
+    else:
+        dq = torch.empty((B, Tq, H, D), dtype=torch.float32, device="cuda")
+        dk = torch.empty((B, Tk, H, D), dtype=torch.float32, device="cuda")
+        dv = torch.empty((B, Tk, H, D), dtype=torch.float32, device="cuda")
     mt, kind, cmp, ms, _keep = _mask_args(mask, (B, H, Tq, Tk))
     seed, call_id, epoch, dev = ticket if ticket is not None else (0, 0, 0, None)
     _check(lib().nnb_attention_backward(_ptr(q), _strides4(q), _ptr(kT), _strides4(kT), _ptr(v), _strides4(v), _ptr(mt), kind,
                                         cmp, ms, float(fill), float(scale), float(p), seed, call_id, epoch, _ptr(dev),
-                                        _ptr(grad), _strides4(grad), _ptr(dq), _ptr(dk), _ptr(dv), B, H, Tq, Tk, D,
+                                        _ptr(grad), _strides4(grad), _ptr(dq), _ptr(dk), _ptr(dv), pitch, B, H, Tq, Tk, D,
                                         _stream()), "nnb_attention_backward")
     return dq.permute(0, 2, 1, 3), dk.permute(0, 2, 3, 1), dv.permute(0, 2, 1, 3)
 

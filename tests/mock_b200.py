@@ -66,6 +66,8 @@ def install():
     def linear_backward(x, w, grad, z=None, act=0, beta=1.0, need_dx=True, need_db=True, owner=None, x_staged=None,
                         dw_out=None, db_out=None):
         calls.append("linear_backward")
+        if grad._base is not None and grad.shape[-1] == w.shape[0] and w.shape[0] > 3 * 8 and grad.is_contiguous():
+            calls.append("linear_backward_zero_copy_candidate")
         g = grad
         if act:
             s = torch.sigmoid(beta * z)
@@ -180,6 +182,14 @@ def install():
         ds = ds / scale
         dq = torch.matmul(ds, kT.transpose(-1, -2))
         dkT = torch.matmul(q.transpose(-1, -2), ds)
+        B, H, Tq, D = q.shape
+        if Tq == kT.shape[3]:  # packed dq | dk | dv like the real binding
+            packed = torch.empty((B, Tq, 3, H, D), dtype=torch.float32)
+            packed[:, :, 0] = dq.permute(0, 2, 1, 3)
+            packed[:, :, 1] = dkT.permute(0, 3, 1, 2)
+            packed[:, :, 2] = dv.permute(0, 2, 1, 3)
+            calls.append("attention_backward_packed")
+            return packed[:, :, 0].permute(0, 2, 1, 3), packed[:, :, 1].permute(0, 2, 3, 1), packed[:, :, 2].permute(0, 2, 1, 3)
         return dq, dkT, dv
 
     def cross_entropy_forward(logits, targets, ignore_index=-100, reduction="mean"):

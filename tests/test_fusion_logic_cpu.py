@@ -82,6 +82,9 @@ def test_fused_equals_eager_with_dropout_masks():
     for g, r in zip(fused[3], eager[3]):
         _close(g, r, 2e-5)
     calls = fused[4]
+    from neunet.nn.layers import linear as _lin
+    assert _lin.fusion_stats["group_calls"] >= 2 and _lin.fusion_stats["backward_zero_copy"] >= 2  # q/k/v: ONE GEMM each way
+    assert calls.count("linear_forward") + calls.count("linear_forward_staged") == 9   # 2 x (qkv, fc, fc_1, fc_2) + fc_out
     assert "rmsnorm_forward_fused" in calls      # x + dropout(a) -> RMSNorm in one kernel
     assert "rmsnorm_backward_acc" in calls       # residual gradient accumulated by the norm's backward
     assert "linear_forward_staged" in calls      # Linear consumed ready-made operand planes
