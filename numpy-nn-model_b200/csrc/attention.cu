@@ -122,6 +122,7 @@ __device__ __forceinline__ void load_tile(float* dst, const float* p, long long 
 template <int TM, int TN, bool A_KM, int RS = 1>
 __device__ __forceinline__ void tile_fma(float (&acc)[TM][TN], const float* __restrict__ A, const float* __restrict__ B,
                                          int K, int m0, int n0) {
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
         float a[TM], b[TN];
         if (A_KM) {
@@ -218,7 +219,7 @@ __device__ __forceinline__ void scores_to_smem(const AttnArgs& a, const float* Q
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a, float* __restrict__ attn, float* __restrict__ out,
+__global__ void __launch_bounds__(256, 4) attn_fwd_kernel(const AttnArgs a, float* __restrict__ attn, float* __restrict__ out,
                                                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
     extern __shared__ __align__(16) float sm[];
     float* Qt = sm;                 // [d][q]
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a, float* 
 //   dPd = dO . V^T;  dP = dPd * mask / (1 - p);  dS = P * (dP - sum_key dP * P), 0 where masked, / scale
 //   dV = (P * mask / (1 - p))^T . dO;  dQ = dS . K;  dK = dS^T . Q
 // Teams of 64 threads (8 x 8 outputs each) run the independent products side by side.
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a, const AttnView dO, float* __restrict__ dQ,
+__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnArgs a, const AttnView dO, float* __restrict__ dQ,
                                                        float* __restrict__ dK, float* __restrict__ dV, long long pitch) {
     extern __shared__ __align__(16) float sm[];
     float* Qt = sm;                  // [d][q]     A of S (k-major)

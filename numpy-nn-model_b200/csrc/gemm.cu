@@ -376,13 +376,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                     if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); else ptx::mbar_arrive(&tmem_empty[acc]);
                 }
                 if (p.debug >= 1) continue;
-                if (p.tma_store && p.splits == 1) {
+                if (p.tma_store) {
                     // ---- fast path: registers -> swizzled smem tile -> TMA store (coalescing, tail
-                    // clipping and the fp32 writes are done by the copy engine, not by LSU traffic)
+                    // clipping and the fp32 writes are done by the copy engine, not by LSU traffic).
+                    // Split-K partials take the same path into the workspace ([split][batch][M][N], raw accumulators;
+                    // alpha / bias / activation are applied by the finishing kernel)
+                    const bool partial = p.splits > 1;
                     float x[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = p.alpha * __uint_as_float(v[j]);
-                    if (p.bias != nullptr) {
+                    for (int j = 0; j < 32; ++j) x[j] = partial ? __uint_as_float(v[j]) : p.alpha * __uint_as_float(v[j]);
+                    if (!partial && p.bias != nullptr) {
                         if (p.bias_per_row) {
                             const int row = row_base + lane;
                             const float rb = row < p.M ? p.bias[row] : 0.f;
@@ -393,7 +396,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                             for (int j = 0; j < 32; ++j) x[j] += __shfl_sync(0xffffffffu, bias_cur, j);  // 0 past N
                         }
                     }
-                    const bool has_z = p.Z != nullptr;
+                    const bool has_z = !partial && p.Z != nullptr;
                     // with a Z side-output each chunk uses both tiles (wait for all reads);
                     // otherwise the two tiles double-buffer the D stores
                     uint8_t* tile_d = has_z ? tile0 : tile0 + store_parity * 4096;
@@ -409,7 +412,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                             *reinterpret_cast<float4*>(tile_z + lane * 128 + ((j ^ sw) << 4)) =
                                 make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
                     }
-                    if (p.act != NNB_ACT_NONE) {
+                    if (!partial && p.act != NNB_ACT_NONE) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act, p.beta);
                     }
@@ -420,7 +423,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const KArgs p) {
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (ptx::elect_one()) {
-                        if (p.col_group > 0) {  // grouped columns: (column in group, row, group)
+                        if (partial) {
+                            ptx::tma_store_3d(&maps.d, tile_d, col0, row_base, split * p.out_batches + ob);
+                        } else if (p.col_group > 0) {  // grouped columns: (column in group, row, group)
                             const int grp = col0 / p.col_group;
                             ptx::tma_store_3d(&maps.d, tile_d, col0 - grp * p.col_group, row_base, grp);
                         } else {
@@ -752,7 +757,8 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
                     const double mma = iters * 4.0 * std::max(c / 2.0, 40.0);
                     // shared-memory traffic per k-block: TMA fill + UMMA operand reads of the local tiles
                     const double fill = iters * 2.0 * (16384.0 + (c / cgi) * 128.0) / 128.0;
-                    const double epi = (c / 32) * ((tma_ok_h && sp == 1) ? 160.0 : 1300.0) + 300.0;
+                    const bool fast_epi = sp == 1 ? tma_ok_h : ((g.N % 4) == 0);  // split-K partials also leave through TMA stores
+                    const double epi = (c / 32) * (fast_epi ? 160.0 : 1300.0) + 300.0;
                     double cyc = waves * std::max(std::max(mma, fill), epi) + 700.0 + 3000.0 + (cgi == 2 ? 2000.0 : 0.0);
                     if (sp > 1) {
                         const double out_bytes = (double)g.M * g.N * out_batches * 4.0;
@@ -889,7 +895,14 @@ int gemm(const GemmProblem& g, cudaStream_t stream) {
             int rc2 = encode_out_map(&maps.d, g.D, g.col_group, g.M, g.ldd, g.N / g.col_group, g.group_stride);
             if (rc2) return rc2;
         }
-        ka.tma_store = (tma || tma_grouped) ? 1 : 0;
+        bool tma_partial = false;
+        if (splits > 1 && (g.N % 4) == 0 && ok16(g.splitk_ws)) {
+            // split-K partials through the TMA-store epilogue too: the map covers the workspace as [split * batch][M][N]
+            int rc2 = encode_out_map(&maps.d, g.splitk_ws, g.N, g.M, g.N, splits * out_batches, g.M * g.N);
+            if (rc2) return rc2;
+            tma_partial = true;
+        }
+        ka.tma_store = (tma || tma_grouped || tma_partial) ? 1 : 0;
     }
 
     const int64_t work = tiles * splits;

@@ -81,7 +81,12 @@ def test_attention_forward_backward_vs_torch(B, H, Tq, Tk, D, mask_kind, p):
     for got, want in ((dq, ql.grad), (dkT, kl.grad), (dv, vl.grad)):
         assert got.shape == want.shape
         assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
-    assert dq.permute(0, 2, 1, 3).is_contiguous() and dkT.permute(0, 3, 1, 2).is_contiguous()
+    if Tq == Tk:  # dq | dk | dv are the column blocks of one [B*T, 3*H*D] matrix (the upstream gradient of a fused q/k/v GEMM)
+        want = (Tq * 3 * H * D, 3 * H * D, D, 1)
+        assert dq.permute(0, 2, 1, 3).stride() == want and dkT.permute(0, 3, 1, 2).stride() == want
+        assert dkT.data_ptr() - dq.data_ptr() == H * D * 4 and dv.data_ptr() - dq.data_ptr() == 2 * H * D * 4
+    else:
+        assert dq.permute(0, 2, 1, 3).is_contiguous() and dkT.permute(0, 3, 1, 2).is_contiguous()
 
 
 def test_attention_rejects_unsupported_sizes():
