@@ -221,6 +221,22 @@ int nnb_probe_linear_gemm(int64_t M, int64_t K, int64_t N, int form, int with_bi
                           int rounds, float* us_per_launch, int* launches_per_gemm,
                           cudaStream_t stream);
 
+/* ---- lm_head + CrossEntropy (row N3 of SURVEY.md 8f) ------------------------------------------------
+ * When the logits of a CrossEntropyLoss are the output of an nn.Linear (the GPT example's fc_out: 4096 x 15000 fp32 =
+ * 246 MB), the loss backward does not materialise dlogits in fp32: nnb_cross_entropy_backward_staged writes them
+ * straight as the bf16 operand planes (nnb_weight_staged_bytes(rows, C, prec) bytes) plus the bias gradient db (column
+ * sums, deterministic two-pass), and nnb_linear_backward_staged runs dgrad / wgrad on those planes -- no fp32 dlogits
+ * write + read and no staging pass (the reference's native kernel overwrites the logits in place instead,
+ * experimental/losses/cross_entropy_loss/cross_entropy.cu:195-212). Labels as in nnb_cross_entropy_forward. */
+size_t nnb_cross_entropy_staged_workspace_bytes(int64_t rows, int64_t C);
+int nnb_cross_entropy_backward_staged(const float* logits, const int32_t* targets, const float* lse,
+                                      const float* inv_denom, const float* upstream, int64_t rows, int64_t C,
+                                      int64_t ignore_index, void* dZ_staged_out, int prec, float* db, void* workspace,
+                                      size_t workspace_bytes, cudaStream_t stream);
+int nnb_linear_backward_staged(const float* X, const float* W, const void* dO_staged, float* dX, float* dW,
+                               int64_t M, int64_t K, int64_t N, int prec, const void* W_staged, const void* X_staged,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- gradient all-reduce over NCCL (the reference has no distributed code) -----
  * The ONE collective of the data-parallel step: an in-place sum all-reduce of the flat fp32 gradient bucket over
  * NVLink / NVSwitch. NCCL is resolved at run time from the libnccl.so.2 already in the process (or on the loader path):

@@ -156,6 +156,74 @@ ce_backward_kernel(const float* __restrict__ logits, const int* __restrict__ tar
     }
 }
 
+
+// lm_head + CrossEntropy (row N3 of SURVEY.md 8f): dlogits = (softmax - onehot) * keep / denom * upstream written
+// DIRECTLY as the bf16 operand planes (hi [+ lo]) that the Linear's dgrad / wgrad GEMMs read, plus per-block column partial
+// sums for the bias gradient -- the fp32 dlogits (246 MB at the GPT sizes) are never materialised and the Linear backward
+// needs no staging pass. Block = 64 rows x 256 columns; thread = two adjacent columns, walking the rows.
+constexpr int CE_ROWS = 64;
+template <bool X3>
+__global__ void __launch_bounds__(128)
+ce_backward_staged_kernel(const float* __restrict__ logits, const int* __restrict__ targets, const float* __restrict__ lse,
+                          const float* __restrict__ inv_denom, const float* __restrict__ upstream, long long rows, int C,
+                          int ignore_index, long long ld, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                          float* __restrict__ partial) {
+    __shared__ int s_t[CE_ROWS];
+    __shared__ float s_l[CE_ROWS];
+    pdl_trigger();
+    pdl_wait();
+    const long long r0 = (long long)blockIdx.y * CE_ROWS;
+    const int nr = (int)min((long long)CE_ROWS, rows - r0);
+    const float sc0 = (inv_denom ? *inv_denom : 1.0f) * upstream[0];
+    for (int i = threadIdx.x; i < CE_ROWS; i += 128) {
+        int t = -2;  // -2: ignored row (all zeros); -1: out-of-range label (NaN row)
+        if (i < nr) {
+            t = targets[r0 + i];
+            if (t == ignore_index) t = -2;
+            else { if (t < 0 && t >= -C) t += C; if (t < 0 || t >= C) t = -1; }
+            s_l[i] = lse[r0 + i];
+        }
+        s_t[i] = t;
+    }
+    __syncthreads();
+    const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+    if (c >= C) return;
+    const bool two = c + 1 < C;
+    float cs0 = 0.f, cs1 = 0.f;
+    for (int i = 0; i < nr; ++i) {
+        const int t = s_t[i];
+        float g0 = 0.f, g1 = 0.f;
+        if (t != -2) {
+            const float sc = t == -1 ? __int_as_float(0x7fc00000) : sc0;
+            const float* x = logits + (r0 + i) * C + c;
+            g0 = (expf(x[0] - s_l[i]) - (c == t ? 1.f : 0.f)) * sc;
+            if (two) g1 = (expf(x[1] - s_l[i]) - (c + 1 == t ? 1.f : 0.f)) * sc;
+        }
+        cs0 += g0;
+        cs1 += g1;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
+        const long long o = (r0 + i) * ld + c;  // ld and c are even: 4-byte aligned pair (pad column written as 0)
+        *reinterpret_cast<__nv_bfloat162*>(hi + o) = __nv_bfloat162(h0, h1);
+        if (X3)
+            *reinterpret_cast<__nv_bfloat162*>(lo + o) = __nv_bfloat162(__float2bfloat16_rn(g0 - __bfloat162float(h0)),
+                                                                         __float2bfloat16_rn(g1 - __bfloat162float(h1)));
+    }
+    float* prow = partial + (long long)blockIdx.y * C;
+    prow[c] = cs0;
+    if (two) prow[c + 1] = cs1;
+}
+
+// db[c] = sum over row blocks (fixed order)
+__global__ void ce_colsum_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * C + c];
+    db[c] = s;
+}
+
 }  // namespace
 }  // namespace nnb
 
@@ -205,6 +273,42 @@ int nnb_cross_entropy_backward(const float* logits, const int32_t* targets, cons
         NNB_CUDA_OK(launch_pdl(ce_backward_kernel, grid, dim3(256), 0, stream, logits + r0 * C, (const int*)(targets + r0),
                                lse + r0, inv_denom, upstream_per_row ? upstream + r0 : upstream, upstream_per_row,
                                (long long)nr, (int)C, (int)ignore_index, dlogits + r0 * C, vec));
+        count_launch();
+    }
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+size_t nnb_cross_entropy_staged_workspace_bytes(int64_t rows, int64_t C) {
+    if (rows <= 0 || C <= 0) return 0;
+    return (size_t)round_up(ceil_div(rows, CE_ROWS) * C * 4, 256) + 256;
+}
+
+int nnb_cross_entropy_backward_staged(const float* logits, const int32_t* targets, const float* lse,
+                                      const float* inv_denom, const float* upstream, int64_t rows, int64_t C,
+                                      int64_t ignore_index, void* dZ_staged_out, int prec, float* db, void* workspace,
+                                      size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_cross_entropy_backward_staged");
+    NNB_REQUIRE(logits && targets && lse && upstream && dZ_staged_out, "nnb_cross_entropy_backward_staged: null pointer");
+    NNB_REQUIRE(rows > 0 && C > 0 && C < (1ll << 31), "nnb_cross_entropy_backward_staged: bad shape");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_cross_entropy_backward_staged: bad prec");
+    NNB_REQUIRE((reinterpret_cast<uintptr_t>(dZ_staged_out) & 255) == 0, "nnb_cross_entropy_backward_staged: dZ_staged_out must be 256-byte aligned");
+    NNB_REQUIRE(workspace && workspace_bytes >= nnb_cross_entropy_staged_workspace_bytes(rows, C), "nnb_cross_entropy_backward_staged: workspace too small");
+    float* partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    auto* hi = static_cast<__nv_bfloat16*>(dZ_staged_out);
+    auto* lo = prec == NNB_PREC_BF16X3
+                   ? reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(dZ_staged_out) + staged_plane_bytes(1, rows, C))
+                   : nullptr;
+    const int nrb = (int)ceil_div(rows, CE_ROWS);
+    NNB_REQUIRE(nrb <= 65535, "nnb_cross_entropy_backward_staged: too many rows");
+    dim3 grid((unsigned)ceil_div(C, 256), (unsigned)nrb);
+    if (lo) NNB_CUDA_OK(launch_pdl(ce_backward_staged_kernel<true>, grid, dim3(128), 0, stream, logits, (const int*)targets, lse, inv_denom,
+                                   upstream, (long long)rows, (int)C, (int)ignore_index, (long long)staged_ld(C), hi, lo, partial));
+    else NNB_CUDA_OK(launch_pdl(ce_backward_staged_kernel<false>, grid, dim3(128), 0, stream, logits, (const int*)targets, lse, inv_denom,
+                                upstream, (long long)rows, (int)C, (int)ignore_index, (long long)staged_ld(C), hi, lo, partial));
+    count_launch();
+    if (db != nullptr) {
+        NNB_CUDA_OK(launch_pdl(ce_colsum_kernel, dim3((unsigned)ceil_div(C, 256)), dim3(256), 0, stream, (const float*)partial, nrb, (int)C, db));
         count_launch();
     }
     NNB_CUDA_OK(cudaGetLastError());

@@ -189,4 +189,49 @@ int nnb_linear_backward(const float* X, const float* W, const float* Z, const fl
     return NNB_OK;
 }
 
+int nnb_linear_backward_staged(const float* X, const float* W, const void* dO_staged, float* dX, float* dW,
+                               int64_t M, int64_t K, int64_t N, int prec, const void* W_staged, const void* X_staged,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_linear_backward_staged");
+    NNB_REQUIRE((X || X_staged) && (W || W_staged || !dX) && dO_staged && dW, "nnb_linear_backward_staged: null pointer");
+    NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_backward_staged: non-positive dimension");
+    NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_backward_staged: bad prec");
+    Bump ws(workspace, workspace_bytes);
+    Staged gs = weight_view(dO_staged, M, N, prec), xs, wsd;
+    int rc;
+    if (X_staged) {
+        xs = weight_view(X_staged, M, K, prec);
+    } else {
+        rc = stage_into(ws, view2d(X, M, K, K), prec, STAGE_COPY, nullptr, 0.f, nullptr, stream, &xs);
+        if (rc) return rc;
+    }
+    if (dX) {
+        if (W_staged) {
+            wsd = weight_view(W_staged, N, K, prec);
+        } else {
+            rc = stage_into(ws, view2d(W, N, K, K), prec, STAGE_COPY, nullptr, 0.f, nullptr, stream, &wsd);
+            if (rc) return rc;
+        }
+    }
+    const size_t sk_bytes = ws.remaining();
+    float* sk = static_cast<float*>(ws.take(sk_bytes));
+    if (dX) {
+        GemmProblem g;
+        g.M = M; g.N = K; g.K = N;
+        g.A.st = gs; g.A.mn_major = false;
+        g.B.st = wsd; g.B.mn_major = true;
+        g.D = dX; g.ldd = K;
+        g.splitk_ws = sk; g.splitk_ws_bytes = sk_bytes;
+        rc = gemm(g, stream);
+        if (rc) return rc;
+    }
+    GemmProblem g;
+    g.M = N; g.N = K; g.K = M;
+    g.A.st = gs; g.A.mn_major = true;
+    g.B.st = xs; g.B.mn_major = true;
+    g.D = dW; g.ldd = K;
+    g.splitk_ws = sk; g.splitk_ws_bytes = sk_bytes;
+    return gemm(g, stream);
+}
+
 }  // extern "C"

@@ -168,6 +168,11 @@ _SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p]),
     "nnb_cross_entropy_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                            c_int64, c_void_p, c_void_p]),
+    "nnb_cross_entropy_staged_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "nnb_cross_entropy_backward_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                                  c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nnb_linear_backward_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nnb_adamw_create": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(c_void_p),
                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_void_p]),
     "nnb_adamw_set_grads": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
@@ -1071,6 +1076,42 @@ def _force(obj):
             _force(o)
     elif hasattr(obj, "grad_fn") and hasattr(obj, "data"):
         obj.data  # noqa: B018
+
+
+def cross_entropy_linear_backward(saved, upstream, x, w, need_dx=True, need_db=True, owner=None, x_staged=None,
+                                  dw_out=None, db_out=None):
+    """Backward of CrossEntropy(Linear(x)) in one go (row N3): dlogits leave the loss kernel as the bf16 operand planes of the
+    Linear's dgrad / wgrad (never as a fp32 tensor), db as their column sums. Returns (dX like x, dW (N, K), db (1, N))."""
+    require_device()
+    L = lib()
+    logits, tgt, lse, inv, ignore_index = saved
+    rows, C = logits.shape
+    N, K = w.shape
+    assert C == N
+    x2 = _f32c(x).reshape(-1, K)
+    M = x2.shape[0]
+    assert M == rows
+    w = _f32c(w)
+    prec = _state["prec"]
+    up = _f32c(upstream).reshape(-1)
+    dz = torch.empty(L.nnb_weight_staged_bytes(rows, C, prec), dtype=torch.uint8, device="cuda")
+    db = None
+    if need_db:
+        db = db_out if _usable_out(db_out, (1, N)) else torch.empty((1, N), dtype=torch.float32, device="cuda")
+    ws = _workspace(max(L.nnb_cross_entropy_staged_workspace_bytes(rows, C), L.nnb_linear_workspace_bytes(M, K, N, prec, 1)))
+    _check(L.nnb_cross_entropy_backward_staged(_ptr(logits), _ptr(tgt), _ptr(lse), _ptr(inv), _ptr(up), rows, C, ignore_index,
+                                               _ptr(dz), prec, _ptr(db), _ptr(ws), ws.numel(), _stream()),
+           "nnb_cross_entropy_backward_staged")
+    dx = torch.empty((M, K), dtype=torch.float32, device="cuda") if need_dx else None
+    dw = dw_out if _usable_out(dw_out, (N, K)) else torch.empty((N, K), dtype=torch.float32, device="cuda")
+    wst = _staged_weight(owner, w, N, K) if need_dx else None
+    if x_staged is not None and getattr(x_staged, "_b200_prec", None) != prec:
+        x_staged = None
+    _check(L.nnb_linear_backward_staged(_ptr(x2), _ptr(w), _ptr(dz), _ptr(dx), _ptr(dw), M, K, N, prec, _ptr(wst), _ptr(x_staged),
+                                        _ptr(ws), ws.numel(), _stream()), "nnb_linear_backward_staged")
+    if dx is not None:
+        dx = dx.reshape(x.shape)
+    return dx, dw, db
 
 
 # ---- whole-step CUDA graphs ---------------------------------------------------------------------------------

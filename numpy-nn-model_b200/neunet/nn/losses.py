@@ -105,7 +105,15 @@ class CrossEntropyLoss(Module):
             if y_true.dtype not in (np.int16, np.int32, np.int64):
                 raise TypeError("Target must be of int dtype")
             from .. import b200
+            lin = _pending_linear_source(y_pred) if self.reduction in ("mean", "sum") else None
             loss, saved = b200.cross_entropy_forward(y_pred.data, y_true.data, self.ignore_index, self.reduction)
+            if lin is not None and lin.args[3] is None and not lin.args[4] and lin.__dict__.get("_b200_gcall") is None:
+                # the logits are the output of an nn.Linear nobody else has read (lm_head): the backward goes from the
+                # loss straight to the Linear's inputs -- dlogits only ever exist as bf16 operand planes (row N3)
+                X, W, b, _z, _act, _beta, xst = lin.args
+                out = _FusedCETensor(loss, (X, W, b, saved, xst), "cross_entropy_linear", y_pred.device)
+                out.grad_fn = _fused_ce_linear_grad
+                return out
             return _FusedCETensor(loss, (y_pred, saved), "cross_entropy", y_pred.device)
         return self.nll_loss(self.log_softmax(y_pred), y_true)
 
@@ -115,6 +123,34 @@ class _FusedCETensor(Tensor):
         t = Tensor._wrap(data, args, op, True, device)
         self.__dict__.update(t.__dict__)
         self.grad_fn = _fused_ce_grad
+
+
+def _pending_linear_source(t):
+    """The still-pending nn.Linear result that `t` is a (reshape) view of, or None. Pending = nobody has read the logits
+    yet, so routing the gradient around them cannot starve another consumer."""
+    from ..autograd import _pending
+    if not _pending(t):
+        return None
+    node, hops = t, 0
+    while _pending(node, "view") and node.op == "reshape" and hops < 4:
+        node, hops = node._f_src, hops + 1
+    if _pending(node, "linear") and node.__dict__.get("_b200_gcall") is None and len(node.shape) >= 2 \
+            and int(np.prod(node.shape[:-1])) == t.shape[0] and node.shape[-1] == t.shape[1]:
+        return node
+    return None
+
+
+def _fused_ce_linear_grad(X: Tensor, W: Tensor, b, saved, xst, grad):
+    from .. import b200
+    dw_out = getattr(W, "_grad_buffer", None) if W.grad is None else None
+    db_out = getattr(b, "_grad_buffer", None) if (b is not None and b.grad is None) else None
+    dx, dw, db = b200.cross_entropy_linear_backward(saved, grad, X.data, W.data, need_dx=X.requires_grad, need_db=b is not None,
+                                                    owner=W, x_staged=xst, dw_out=dw_out, db_out=db_out)
+    if dx is not None:
+        X.apply_grad(dx)
+    W.apply_grad(dw)
+    if b is not None:
+        b.apply_grad(db)
 
 
 def _fused_ce_grad(y_pred: Tensor, saved, grad):

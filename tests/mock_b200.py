@@ -36,7 +36,8 @@ def install():
              "softmax_backward", "swish_forward", "swish_backward", "rmsnorm_forward", "rmsnorm_backward", "dropout_apply",
              "attention_supported", "attention_forward", "attention_backward", "cross_entropy_forward",
              "cross_entropy_backward", "dropout_ticket", "_cache_scope", "conv2d_forward", "conv2d_backward",
-             "conv_transpose2d_supported", "bn_forward", "bn_backward", "embedding_forward", "embedding_backward"]
+             "conv_transpose2d_supported", "bn_forward", "bn_backward", "embedding_forward", "embedding_backward",
+             "cross_entropy_linear_backward"]
     for n in names:
         _saved[n] = getattr(b200, n, None)
     _saved["device_prop"] = be.TorchXP.device
@@ -257,6 +258,16 @@ def install():
         s1, s2 = wg.sum((0, 2, 3), keepdim=True), (wg * xh).sum((0, 2, 3), keepdim=True)
         dx = torch.where(x <= 0, alpha, 1.0) * inv.reshape(1, -1, 1, 1) * (wg - s1 / n - xh * s2 / n)
         return dx, (grad * xh).sum((0, 2, 3)), grad.sum((0, 2, 3))
+
+    def cross_entropy_linear_backward(saved, upstream, x, w, need_dx=True, need_db=True, owner=None, x_staged=None,
+                                      dw_out=None, db_out=None):
+        calls.append("cross_entropy_linear_backward")
+        d = cross_entropy_backward(saved, upstream)
+        calls.pop()
+        out = linear_backward(x, w, d, need_dx=need_dx, need_db=need_db)
+        calls.pop()
+        return out
+    b200.cross_entropy_linear_backward = cross_entropy_linear_backward
 
     def embedding_forward(weight, ids):
         calls.append("embedding_forward")

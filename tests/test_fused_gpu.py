@@ -291,3 +291,34 @@ def test_embedding_gather_and_last_write_wins_scatter(dtype):
     full[ids] = g
     dw = b200.embedding_backward(torch.from_numpy(ids).to(dtype).cuda(), torch.from_numpy(g).cuda(), V)
     np.testing.assert_array_equal(dw.cpu().numpy(), full)
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 6e-3)])
+@pytest.mark.parametrize("rows,C,K", [(256, 1500, 64), (130, 1001, 40), (4096, 15000, 512)])
+def test_lm_head_cross_entropy_staged_backward(prec, tol, rows, C, K):
+    """Row N3: CrossEntropy(Linear(x)) backward with dlogits emitted as bf16 operand planes (never as fp32) against the
+    composition of the two stand-alone backward passes AND against torch fp32 autograd (F.cross_entropy(F.linear))."""
+    b200 = _b200()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    x = torch.randn(rows, K, generator=g, device="cuda")
+    w = torch.randn(C, K, generator=g, device="cuda") / K ** 0.5
+    b = torch.randn(1, C, generator=g, device="cuda") * 0.1
+    tgt = torch.randint(0, C, (rows,), generator=g, device="cuda", dtype=torch.int32)
+    tgt[::7] = 0  # ignore_index rows
+    with b200.precision(prec):
+        logits, _, xst = b200.linear_forward(x, w, b, keep_x_staged=True)
+        loss, saved = b200.cross_entropy_forward(logits, tgt, ignore_index=0, reduction="mean")
+        up = torch.ones((), device="cuda") * 1.7
+        dx, dw, db = b200.cross_entropy_linear_backward(saved, up, x, w, x_staged=xst)
+        d = b200.cross_entropy_backward(saved, up)
+        dx0, dw0, db0 = b200.linear_backward(x, w, d, x_staged=xst)
+    for got, want in ((dx, dx0), (dw, dw0), (db, db0)):
+        # same math, but the staged form rounds dlogits to bf16(x3) BEFORE the column sums / contractions
+        assert (got - want).abs().max().item() <= tol * max(want.abs().max().item(), 1e-6)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    ref = torch.nn.functional.cross_entropy(torch.nn.functional.linear(xr, wr, br.reshape(-1)), tgt.long(), ignore_index=0) * 1.7
+    ref.backward()
+    assert abs(float(loss.item()) * 1.7 - float(ref.item())) <= tol * abs(float(ref.item()))
+    for got, want in ((dx, xr.grad), (dw, wr.grad), (db, br.grad)):
+        assert (got - want).abs().max().item() <= tol * max(want.abs().max().item(), 1e-6)
