@@ -504,6 +504,154 @@ void class_taps(int par, int pad, int k, int s, int* k0, int* nk, int* e) {
     *e = (par + pad - (k - 1) + *k0) / s;  // exact
 }
 
+// ---------------------------------------------------------------- tiny-channel layers, one image per block in shared memory
+// The direct kernels above read every operand from global memory per multiply; for the MNIST-classifier layers
+// (1 -> 8 and 8 -> 16 channels, 28 x 28 / 14 x 14) a whole zero-padded image (all input channels), its output (or output
+// gradient) and the kernel fit in shared memory, so a block stages them once and every multiply reads shared memory.
+// wgrad keeps a thread's weight elements in registers ACROSS the images the block walks, so the partial-sum volume is
+// (blocks x weights), not (images x weights). Deterministic: fixed image order per block, fixed-order finish.
+struct TileGeo {
+    int Hp, Wp;       // padded image extent held in shared memory (top/left pad + what the taps reach)
+    int imgs_per_block;
+};
+
+__device__ __forceinline__ void load_padded_image(float* Xs, const float* __restrict__ X, const Geo& g, int Hp, int Wp, int b) {
+    for (int e = threadIdx.x; e < g.Cin * Hp * Wp; e += blockDim.x) {
+        const int x = e % Wp, y = (e / Wp) % Hp, i = e / (Wp * Hp);
+        const int yy = y - g.pt, xx = x - g.pl;
+        Xs[e] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? X[(((long long)b * g.Cin + i) * g.H + yy) * g.W + xx] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_fwd_kernel(const Geo g, const TileGeo t, const float* __restrict__ X, const float* __restrict__ Wt,
+                const float* __restrict__ bias, float* __restrict__ O) {
+    extern __shared__ __align__(16) float smf[];
+    float* Ws = smf;                                   // [Cout][Cin][kh][kw]
+    float* Xs = Ws + g.Cout * g.Cin * g.kh * g.kw;     // [Cin][Hp][Wp]
+    const int nw = g.Cout * g.Cin * g.kh * g.kw, HWo = g.Ho * g.Wo, khw = g.kh * g.kw;
+    for (int e = threadIdx.x; e < nw; e += blockDim.x) Ws[e] = Wt[e];
+    for (int b = blockIdx.x; b < g.B; b += gridDim.x) {
+        __syncthreads();
+        load_padded_image(Xs, X, g, t.Hp, t.Wp, b);
+        __syncthreads();
+        for (int e = threadIdx.x; e < g.Cout * HWo; e += blockDim.x) {
+            const int pos = e % HWo, o = e / HWo;
+            const int ho = pos / g.Wo, wo = pos - ho * g.Wo;
+            float acc = bias ? bias[o] : 0.f;
+            const float* wp = Ws + o * g.Cin * khw;
+            for (int i = 0; i < g.Cin; ++i) {
+                const float* xp = Xs + (i * t.Hp + ho * g.s0) * t.Wp + wo * g.s1;
+                for (int k = 0; k < g.kh; ++k)
+                    for (int l = 0; l < g.kw; ++l) acc = fmaf(xp[k * g.d0 * t.Wp + l * g.d1], wp[(i * g.kh + k) * g.kw + l], acc);
+            }
+            O[((long long)b * g.Cout + o) * HWo + pos] = acc;
+        }
+    }
+}
+
+// partial[block][w] = sum over the block's images and all positions of X[.., ho*s + k*d, wo*s + l*d] * dO[.., o, ho, wo]
+__global__ void __launch_bounds__(256)
+tile_wgrad_kernel(const Geo g, const TileGeo t, const float* __restrict__ X, const float* __restrict__ dO,
+                  float* __restrict__ partial) {
+    extern __shared__ __align__(16) float smf[];
+    float* Gs = smf;                     // [Cout][Ho*Wo]
+    float* Xs = Gs + g.Cout * g.Ho * g.Wo;  // [Cin][Hp][Wp]
+    const int nw = g.Cout * g.Cin * g.kh * g.kw, HWo = g.Ho * g.Wo;
+    // a thread owns weights w = tid, tid + 256, ... (<= 4 of them: nw <= 31 * 256 / ... checked on the host)
+    constexpr int MAXW = 32;
+    float acc[MAXW];
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) acc[j] = 0.f;
+    // when there are fewer weights than threads, L threads share a weight and split the positions
+    const int L = nw < 256 ? 256 / nw : 1;
+    const int lanes = nw < 256 ? nw * L : 256;
+    for (int b = blockIdx.x; b < g.B; b += gridDim.x) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < g.Cout * HWo; e += blockDim.x) Gs[e] = dO[(long long)b * g.Cout * HWo + e];
+        load_padded_image(Xs, X, g, t.Hp, t.Wp, b);
+        __syncthreads();
+        if ((int)threadIdx.x < lanes) {
+            const int sub = nw < 256 ? (int)threadIdx.x / nw : 0;
+            int j = 0;
+            for (int w = nw < 256 ? (int)threadIdx.x % nw : (int)threadIdx.x; w < nw; w += 256, ++j) {
+                const int l = w % g.kw, k = (w / g.kw) % g.kh, i = (w / (g.kw * g.kh)) % g.Cin, o = w / (g.kw * g.kh * g.Cin);
+                const float* gp = Gs + o * HWo;
+                const float* xp = Xs + (i * t.Hp + k * g.d0) * t.Wp + l * g.d1;
+                float s = 0.f;
+                for (int pos = sub; pos < HWo; pos += L) {
+                    const int ho = pos / g.Wo, wo = pos - ho * g.Wo;
+                    s = fmaf(xp[ho * g.s0 * t.Wp + wo * g.s1], gp[pos], s);
+                }
+                acc[j] += s;
+            }
+        }
+    }
+    // partial row of this block: [L sub-lanes][nw] (the finish kernel adds blocks and sub-lanes in a fixed order)
+    float* prow = partial + (long long)blockIdx.x * L * nw;
+    if ((int)threadIdx.x < lanes) {
+        const int sub = nw < 256 ? (int)threadIdx.x / nw : 0;
+        int j = 0;
+        for (int w = nw < 256 ? (int)threadIdx.x % nw : (int)threadIdx.x; w < nw; w += 256, ++j) prow[(long long)sub * nw + w] = acc[j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_dgrad_kernel(const Geo g, const float* __restrict__ dO, const float* __restrict__ Wt, float* __restrict__ dX) {
+    extern __shared__ __align__(16) float smf[];
+    float* Ws = smf;                                   // [Cout][Cin][kh][kw]
+    float* Gs = Ws + g.Cout * g.Cin * g.kh * g.kw;     // [Cout][Ho*Wo]
+    const int nw = g.Cout * g.Cin * g.kh * g.kw, HWo = g.Ho * g.Wo, HW = g.H * g.W, khw = g.kh * g.kw;
+    for (int e = threadIdx.x; e < nw; e += blockDim.x) Ws[e] = Wt[e];
+    for (int b = blockIdx.x; b < g.B; b += gridDim.x) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < g.Cout * HWo; e += blockDim.x) Gs[e] = dO[(long long)b * g.Cout * HWo + e];
+        __syncthreads();
+        for (int e = threadIdx.x; e < g.Cin * HW; e += blockDim.x) {
+            const int x = e % g.W, y = (e / g.W) % g.H, i = e / HW;
+            float acc = 0.f;
+            for (int k = 0; k < g.kh; ++k) {
+                const int ny = y + g.pt - k * g.d0;
+                if (ny < 0 || ny % g.s0) continue;
+                const int ho = ny / g.s0;
+                if (ho >= g.Ho) continue;
+                for (int l = 0; l < g.kw; ++l) {
+                    const int nx = x + g.pl - l * g.d1;
+                    if (nx < 0 || nx % g.s1) continue;
+                    const int wo = nx / g.s1;
+                    if (wo >= g.Wo) continue;
+                    const float* gp = Gs + ho * g.Wo + wo;
+                    const float* wp = Ws + (i * g.kh + k) * g.kw + l;
+                    for (int o = 0; o < g.Cout; ++o) acc = fmaf(gp[o * HWo], wp[o * g.Cin * khw], acc);
+                }
+            }
+            dX[(long long)b * g.Cin * HW + e] = acc;
+        }
+    }
+}
+
+constexpr size_t TILE_SMEM_LIMIT = 160 * 1024;
+constexpr int TILE_MAX_BLOCKS = 296;  // two per SM: each block walks B / blocks images
+
+bool tile_geo(const Geo& g, TileGeo* t) {
+    t->Hp = g.pt + std::max(g.H, (g.Ho - 1) * g.s0 + (g.kh - 1) * g.d0 + 1);
+    t->Wp = g.pl + std::max(g.W, (g.Wo - 1) * g.s1 + (g.kw - 1) * g.d1 + 1);
+    const size_t nw = (size_t)g.Cout * g.Cin * g.kh * g.kw;
+    const size_t img = (size_t)g.Cin * t->Hp * t->Wp, out = (size_t)g.Cout * g.Ho * g.Wo;
+    t->imgs_per_block = 1;
+    return nw <= 32 * 256 && (std::max(nw, out) + std::max(img, out)) * 4 <= TILE_SMEM_LIMIT;
+}
+
+int tile_blocks(const Geo& g) { return std::min(g.B, TILE_MAX_BLOCKS); }
+int tile_wgrad_lanes(const Geo& g) { const int nw = g.Cout * g.Cin * g.kh * g.kw; return nw < 256 ? 256 / nw : 1; }
+
+template <typename K>
+int tile_smem_attr(K kernel, size_t bytes) {
+    NNB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_LIMIT));
+    (void)bytes;
+    return NNB_OK;
+}
+
 int grid_for(long long n, int threads) {
     return (int)std::max<long long>(1, std::min<long long>(ceil_div(n, threads), (long long)num_sms() * 32));
 }
@@ -713,7 +861,8 @@ size_t nnb_conv2d_workspace_bytes(const nnb_conv2d_desc* d, int prec, int backwa
     Geo g{};
     if (make_geo(d, &g)) return 0;
     const size_t dbp = (size_t)round_up((int64_t)CHANNEL_SUM_CHUNKS * g.Cout * 4, 256) + 256;  // db partial sums
-    if (use_direct(g)) return 512 + dbp + (size_t)DIRECT_WGRAD_CHUNKS * g.Cout * g.Cin * g.kh * g.kw * 4;
+    if (use_direct(g))
+        return 512 + dbp + (size_t)std::max(DIRECT_WGRAD_CHUNKS, TILE_MAX_BLOCKS * tile_wgrad_lanes(g)) * g.Cout * g.Cin * g.kh * g.kw * 4;
     const size_t p = planes(prec);
     const int cip = use_nhwc(g) ? cpad(g.Cin) : g.Cin, cop = use_nhwc(g) ? cpad(g.Cout) : g.Cout;
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo, Kc = (int64_t)cip * g.kh * g.kw;
@@ -761,8 +910,16 @@ int nnb_conv2d_forward_ex(const nnb_conv2d_desc* d, const float* X, const float*
     int rc = make_geo(d, &g);
     if (rc) return rc;
     if (use_direct(g)) {
-        const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
-        direct_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(g, X, Wt, bias, O);
+        TileGeo tg{};
+        if (tile_geo(g, &tg)) {
+            static bool cfg = false;
+            if (!cfg) { int rc2 = tile_smem_attr(tile_fwd_kernel, 0); if (rc2) return rc2; cfg = true; }
+            const size_t smem = ((size_t)g.Cout * g.Cin * g.kh * g.kw + (size_t)g.Cin * tg.Hp * tg.Wp) * 4;
+            tile_fwd_kernel<<<tile_blocks(g), 256, smem, stream>>>(g, tg, X, Wt, bias, O);
+        } else {
+            const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
+            direct_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(g, X, Wt, bias, O);
+        }
         count_launch();
         NNB_CUDA_OK(cudaGetLastError());
         return NNB_OK;
@@ -866,8 +1023,33 @@ int nnb_conv2d_backward_ex(const nnb_conv2d_desc* d, const float* X, const float
     }
     if (use_direct(g)) {
         const int nw = g.Cout * g.Cin * g.kh * g.kw;
-        const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DIRECT_WGRAD_CHUNKS, (g.B * HWo + 4095) / 4096));
+        TileGeo tg{};
+        const bool tiled = tile_geo(g, &tg);
         Bump& dws = ws;
+        if (tiled) {
+            static bool cfg = false;
+            if (!cfg) {
+                int rc2 = tile_smem_attr(tile_wgrad_kernel, 0);
+                if (!rc2) rc2 = tile_smem_attr(tile_dgrad_kernel, 0);
+                if (rc2) return rc2;
+                cfg = true;
+            }
+            const int blocks = tile_blocks(g), rows = blocks * tile_wgrad_lanes(g);
+            float* partial = static_cast<float*>(dws.take((size_t)rows * nw * 4));
+            if (!dws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", dws.off);
+            const size_t smem = ((size_t)g.Cout * HWo + (size_t)g.Cin * tg.Hp * tg.Wp) * 4;
+            tile_wgrad_kernel<<<blocks, 256, smem, stream>>>(g, tg, X, dO, partial);
+            direct_wgrad_finish_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, stream>>>(partial, nw, rows, dW);
+            count_launch(2);
+            if (dX) {
+                const size_t smem2 = ((size_t)nw + (size_t)g.Cout * HWo) * 4;
+                tile_dgrad_kernel<<<blocks, 256, smem2, stream>>>(g, dO, Wt, dX);
+                count_launch();
+            }
+            NNB_CUDA_OK(cudaGetLastError());
+            return NNB_OK;
+        }
+        const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DIRECT_WGRAD_CHUNKS, (g.B * HWo + 4095) / 4096));
         float* partial = static_cast<float*>(dws.take((size_t)chunks * nw * 4));
         if (!dws.ok()) return fail(NNB_ERR_WORKSPACE, "nnb_conv2d_backward: workspace too small (need >= %zu)", dws.off);
         direct_wgrad_kernel<<<dim3((unsigned)nw, (unsigned)chunks), 256, 0, stream>>>(g, X, dO, partial);

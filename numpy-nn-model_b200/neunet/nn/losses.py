@@ -134,8 +134,9 @@ def _pending_linear_source(t):
     node, hops = t, 0
     while _pending(node, "view") and node.op == "reshape" and hops < 4:
         node, hops = node._f_src, hops + 1
+    # only wide heads: the staged loss backward walks 256 classes per block, a 10-class head would idle 98 % of it
     if _pending(node, "linear") and node.__dict__.get("_b200_gcall") is None and len(node.shape) >= 2 \
-            and int(np.prod(node.shape[:-1])) == t.shape[0] and node.shape[-1] == t.shape[1]:
+            and int(np.prod(node.shape[:-1])) == t.shape[0] and node.shape[-1] == t.shape[1] and t.shape[1] >= 512:
         return node
     return None
 
