@@ -95,6 +95,16 @@ int nnb_linear_backward(const float* X, const float* W, const float* Z, const fl
                         float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
                         float beta, int prec, const void* W_staged, const void* X_staged,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* nnb_linear_backward on an upstream gradient that still has to pass an nn.Dropout (neunet/nn/layers/dropout.py:39-46:
+ * dx = grad * mask): dO is multiplied by the dropout mask of the Philox ticket (drop_p, seed, call_id, epoch | *epoch_dev;
+ * flat index over the contiguous [M, N] matrix, same bits as nnb_dropout) inside the staging pass that converts dO to
+ * bf16 planes, before swish' and the bias column sums -- the stand-alone mask pass over dO (one read + one write of
+ * M*N floats) disappears. N % 4 == 0, otherwise NNB_ERR_UNSUPPORTED (run nnb_dropout, then nnb_linear_backward). */
+int nnb_linear_backward_dropped(const float* X, const float* W, const float* Z, const float* dO,
+                                float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
+                                float beta, int prec, const void* W_staged, const void* X_staged,
+                                void* workspace, size_t workspace_bytes, float drop_p, uint64_t seed, uint32_t call_id,
+                                uint64_t epoch, const uint64_t* epoch_dev, cudaStream_t stream);
 size_t nnb_weight_staged_bytes(int64_t rows, int64_t cols, int prec);
 int nnb_stage_weight(const float* W, int64_t rows, int64_t cols, int prec, void* dst,
                      cudaStream_t stream);
@@ -320,8 +330,10 @@ int nnb_embedding_backward(const void* ids, int ids_are_int64, const float* grad
  *   scores = q . kT / scale; scores = where(mask, fill, scores); p = softmax(scores, -1);
  *   attn = dropout(p); out = attn . v
  * replacing two Tensor.matmul (neunet/autograd.py:192-230), a division, where (autograd.py:658-684),
- * nn.Softmax (activations.py:437-459) and nn.Dropout (layers/dropout.py:17-46). fp32 arithmetic on the CUDA
- * cores (exact like the reference; per head the products are <= 64 x 64 x 64).
+ * nn.Softmax (activations.py:437-459) and nn.Dropout (layers/dropout.py:17-46). The per-head products (<= 64 x 64 x 64)
+ * run on the tensor cores as warp-level TF32 MMAs with fp32 accumulation, straight from fp32 shared-memory tiles:
+ * prec = NNB_PREC_BF16 -> one TF32 product (~5e-4 rel. per contraction), NNB_PREC_BF16X3 -> hi/lo split, three
+ * products (~1e-6 rel., fp32-grade; parity mode). Softmax, masking, dropout and all sums are fp32.
  * q: logical (B,H,Tq,D), kT: logical (B,H,D,Tk), v: logical (B,H,Tk,D), dO: logical (B,H,Tq,D), each with four
  * element strides (any layout). mask (nullable) is described by mask_kind: 1 = float tensor, masked where != 0;
  * 2 = int32 tensor, masked where == mask_cmp; 3 = float tensor, masked where == mask_cmp; strides over
@@ -345,7 +357,7 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
                            const int64_t mask_strides[4], float fill, float scale, float p, uint64_t seed,
                            uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, const float* dO,
                            const int64_t do_strides[4], float* dQ, float* dK, float* dV, int64_t out_row_pitch,
-                           int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream);
+                           int prec, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, cudaStream_t stream);
 
 /* ---- Dropout with a device RNG (row N4 of SURVEY.md 8f) ----------------------------------------
  * neunet/nn/layers/dropout.py:17-46: y = x * mask, mask ~ Bernoulli(1-p) / (1-p); backward is the
@@ -365,6 +377,13 @@ int nnb_rng_advance(uint64_t* epoch_dev, cudaStream_t stream);
 int nnb_dropout_fused(const float* x, const float* residual, float* y, int64_t rows, int64_t cols, float p,
                       uint64_t seed, uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev,
                       void* Y_staged_out, int prec, cudaStream_t stream);
+/* y = dropout(swish(z, beta)) over a [rows, cols] matrix, same mask / planes contract as nnb_dropout_fused: the
+ * feed-forward block of examples/gpt.ipynb cell 4 l.9-13 (fc_2(dropout(swish(fc_1(x))))) = nn.Swish
+ * (neunet/nn/activations.py:208-233) + nn.Dropout (layers/dropout.py:17-46) in one pass over the pre-activation z that
+ * the fc_1 GEMM wrote; the Swish output itself is never materialised (backward needs z and the Philox ticket only). */
+int nnb_swish_dropout_fused(const float* z, float beta, float* y, int64_t rows, int64_t cols, float p, uint64_t seed,
+                            uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, void* Y_staged_out, int prec,
+                            cudaStream_t stream);
 
 /* ---- fused CrossEntropyLoss (row N3 of SURVEY.md 8f, first half) --------------------------------
  * LogSoftmax(axis=1) + NLLLoss with unit class weights (neunet/nn/losses.py:59-126); native analogue

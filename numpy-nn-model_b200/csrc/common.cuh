@@ -123,9 +123,13 @@ size_t stage_colsum_scratch_bytes(int64_t cols);
 
 // dst planes must hold staged_plane_bytes() each. If `colsum` is non-null it receives
 // sum over (batch, rows) of the *transformed fp32* values per column (bias gradient), length cols.
+// `drop` (nullable): the source is first multiplied by the dropout mask of that Philox ticket (x * keep / (1 - p), flat
+// index = row * cols + col, so the view must be one contiguous [rows, cols] matrix with cols % 4 == 0): the backward of
+// nn.Dropout folded into the staging of the upstream gradient of the nn.Linear below it.
+struct DropArgs;
 int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst_hi,
                   __nv_bfloat16* dst_lo, int op, const float* aux, float beta, float* colsum,
-                  float* colsum_scratch, cudaStream_t stream, Staged* out);
+                  float* colsum_scratch, cudaStream_t stream, Staged* out, const DropArgs* drop = nullptr);
 
 // ---- GEMM ---------------------------------------------------------------------------------------
 // D[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )

@@ -19,13 +19,17 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// y = (residual +) dropout(x); optionally also the bf16 planes of y (hi [+ lo]) for the next Linear, so the
-// consumer needs no staging pass. keep iff word >= p * 2^32  (P[keep] = 1 - p to within 2^-32).
-template <bool PLANES>
+// the stand-alone Swish of elementwise.cu (neunet/nn/activations.py:208-211), same expression -> same bits
+__device__ __forceinline__ float swish_of(float z, float beta) { return z * (1.0f / (1.0f + expf(-beta * z))); }
+
+// y = (residual +) dropout(x) -- x = swish(z) when SWISH (the FFN of examples/gpt.ipynb cell 4: fc_2(dropout(swish(fc_1 x)))
+// reads the pre-activation once and never materialises the activation); optionally also the bf16 planes of y (hi [+ lo])
+// for the next Linear, so the consumer needs no staging pass. keep iff word >= p * 2^32  (P[keep] = 1 - p to within 2^-32).
+template <bool PLANES, bool SWISH = false>
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                       float* __restrict__ y, long long n, const DropArgs d,
                                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                      int vec) {
+                                                      int vec, float beta = 1.0f) {
     pdl_trigger();
     pdl_wait();
     const uint64_t epoch = drop_epoch(d);
@@ -37,6 +41,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
         const long long e = i << 2;
         if (vec && e + 3 < n) {
             float4 v = *reinterpret_cast<const float4*>(x + e);
+            if (SWISH) { v.x = swish_of(v.x, beta); v.y = swish_of(v.y, beta); v.z = swish_of(v.z, beta); v.w = swish_of(v.w, beta); }
             v.x = c[0] >= d.thresh ? v.x * d.scale : 0.f;
             v.y = c[1] >= d.thresh ? v.y * d.scale : 0.f;
             v.z = c[2] >= d.thresh ? v.z * d.scale : 0.f;
@@ -58,7 +63,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (e + j < n) {
-                    float v = c[j] >= d.thresh ? x[e + j] * d.scale : 0.f;
+                    const float xv = SWISH ? swish_of(x[e + j], beta) : x[e + j];
+                    float v = c[j] >= d.thresh ? xv * d.scale : 0.f;
                     if (res != nullptr) v += res[e + j];
                     y[e + j] = v;
                     if (PLANES) {
@@ -103,9 +109,39 @@ int nnb_dropout_fused(const float* x, const float* residual, float* y, int64_t r
         hi = static_cast<__nv_bfloat16*>(Y_staged_out);
         if (prec == NNB_PREC_BF16X3)
             lo = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(Y_staged_out) + staged_plane_bytes(1, rows, cols));
-        NNB_CUDA_OK(launch_pdl(dropout_kernel<true>, dim3(blocks), dim3(256), 0, stream, x, residual, y, (long long)n, d, hi, lo, vec));
+        NNB_CUDA_OK(launch_pdl(dropout_kernel<true, false>, dim3(blocks), dim3(256), 0, stream, x, residual, y, (long long)n, d, hi, lo, vec, 1.0f));
     } else {
-        NNB_CUDA_OK(launch_pdl(dropout_kernel<false>, dim3(blocks), dim3(256), 0, stream, x, residual, y, (long long)n, d, hi, lo, vec));
+        NNB_CUDA_OK(launch_pdl(dropout_kernel<false, false>, dim3(blocks), dim3(256), 0, stream, x, residual, y, (long long)n, d, hi, lo, vec, 1.0f));
+    }
+    count_launch();
+    NNB_CUDA_OK(cudaGetLastError());
+    return NNB_OK;
+}
+
+int nnb_swish_dropout_fused(const float* z, float beta, float* y, int64_t rows, int64_t cols, float p, uint64_t seed,
+                            uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev, void* Y_staged_out, int prec,
+                            cudaStream_t stream) {
+    NNB_RANGE("nnb_swish_dropout_fused");
+    NNB_REQUIRE(z && y, "nnb_swish_dropout: null pointer");
+    NNB_REQUIRE(rows > 0 && cols > 0, "nnb_swish_dropout: bad size");
+    NNB_REQUIRE(p >= 0.f && p < 1.f, "nnb_swish_dropout: p must be in [0, 1)");
+    const int64_t n = rows * cols;
+    const DropArgs d = make_drop_args(p, seed, call_id, epoch, epoch_dev);
+    const int vec = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const long long nvec = (n + 3) / 4;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div(nvec, 256), (long long)num_sms() * 16));
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    const float* none = nullptr;
+    if (Y_staged_out != nullptr) {
+        NNB_REQUIRE(cols % 8 == 0, "nnb_swish_dropout: staged output needs cols % 8 == 0");
+        NNB_REQUIRE((reinterpret_cast<uintptr_t>(Y_staged_out) & 255) == 0, "nnb_swish_dropout: Y_staged_out must be 256-byte aligned");
+        NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_swish_dropout: bad prec");
+        hi = static_cast<__nv_bfloat16*>(Y_staged_out);
+        if (prec == NNB_PREC_BF16X3)
+            lo = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(Y_staged_out) + staged_plane_bytes(1, rows, cols));
+        NNB_CUDA_OK(launch_pdl(dropout_kernel<true, true>, dim3(blocks), dim3(256), 0, stream, z, none, y, (long long)n, d, hi, lo, vec, beta));
+    } else {
+        NNB_CUDA_OK(launch_pdl(dropout_kernel<false, true>, dim3(blocks), dim3(256), 0, stream, z, none, y, (long long)n, d, hi, lo, vec, beta));
     }
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());

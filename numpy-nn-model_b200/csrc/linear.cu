@@ -2,6 +2,7 @@
 // Reference semantics: neunet/nn/layers/linear.py:17-24 (backward), 48-58 (forward);
 // fused Swish: neunet/nn/experimental/linear_swish/linear_swish_cutlass_evt_full.cu:558-818.
 #include "common.cuh"
+#include "philox.cuh"
 #include "workspace.cuh"
 
 namespace nnb {
@@ -24,7 +25,7 @@ static Staged weight_view(const void* blob, int64_t rows, int64_t cols, int prec
 }
 
 static int stage_into(Bump& ws, const View4& v, int prec, int op, const float* aux, float beta,
-                      float* colsum, cudaStream_t stream, Staged* out) {
+                      float* colsum, cudaStream_t stream, Staged* out, const DropArgs* drop = nullptr) {
     const int64_t batch = v.b0 * v.b1;
     auto* hi = static_cast<__nv_bfloat16*>(ws.take(staged_plane_bytes(batch, v.rows, v.cols)));
     __nv_bfloat16* lo = nullptr;
@@ -33,7 +34,7 @@ static int stage_into(Bump& ws, const View4& v, int prec, int op, const float* a
     float* scratch = nullptr;
     if (colsum) scratch = static_cast<float*>(ws.take(stage_colsum_scratch_bytes(v.cols)));
     if (!ws.ok()) return fail(NNB_ERR_WORKSPACE, "workspace too small (need >= %zu bytes)", ws.off);
-    return stage_operand(v, false, prec, hi, lo, op, aux, beta, colsum, scratch, stream, out);
+    return stage_operand(v, false, prec, hi, lo, op, aux, beta, colsum, scratch, stream, out, drop);
 }
 
 }  // namespace nnb
@@ -133,11 +134,10 @@ int nnb_linear_forward_staged(const void* X_staged, const void* W_staged, const 
     return gemm(g, stream);
 }
 
-int nnb_linear_backward(const float* X, const float* W, const float* Z, const float* dO,
-                        float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
-                        float beta, int prec, const void* W_staged, const void* X_staged,
-                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    NNB_RANGE("nnb_linear_backward");
+static int linear_backward_impl(const float* X, const float* W, const float* Z, const float* dO,
+                                float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
+                                float beta, int prec, const void* W_staged, const void* X_staged,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream, const nnb::DropArgs* drop) {
     NNB_REQUIRE((X || X_staged) && W && dO && dW, "nnb_linear_backward: null X/W/dO/dW");
     NNB_REQUIRE(M > 0 && K > 0 && N > 0, "nnb_linear_backward: non-positive dimension");
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_linear_backward: bad prec");
@@ -146,7 +146,7 @@ int nnb_linear_backward(const float* X, const float* W, const float* Z, const fl
     Staged gs, xs, wsd;
     // dZ = dO (* swish'(Z)); db = column sums of dZ, fused into the same pass over dO
     int rc = stage_into(ws, view2d(dO, M, N, N), prec, act == NNB_ACT_SWISH ? STAGE_SWISH_BWD : STAGE_COPY,
-                        Z, beta, db, stream, &gs);
+                        Z, beta, db, stream, &gs, drop);
     if (rc) return rc;
     if (X_staged) {
         xs = weight_view(X_staged, M, K, prec);
@@ -187,6 +187,28 @@ int nnb_linear_backward(const float* X, const float* W, const float* Z, const fl
         if (rc) return rc;
     }
     return NNB_OK;
+}
+
+int nnb_linear_backward(const float* X, const float* W, const float* Z, const float* dO,
+                        float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
+                        float beta, int prec, const void* W_staged, const void* X_staged,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NNB_RANGE("nnb_linear_backward");
+    return linear_backward_impl(X, W, Z, dO, dX, dW, db, M, K, N, act, beta, prec, W_staged, X_staged, workspace,
+                                workspace_bytes, stream, nullptr);
+}
+
+int nnb_linear_backward_dropped(const float* X, const float* W, const float* Z, const float* dO,
+                                float* dX, float* dW, float* db, int64_t M, int64_t K, int64_t N, int act,
+                                float beta, int prec, const void* W_staged, const void* X_staged,
+                                void* workspace, size_t workspace_bytes, float drop_p, uint64_t seed, uint32_t call_id,
+                                uint64_t epoch, const uint64_t* epoch_dev, cudaStream_t stream) {
+    NNB_RANGE("nnb_linear_backward_dropped");
+    NNB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "nnb_linear_backward_dropped: p must be in [0, 1)");
+    if (N % 4 != 0) return fail(NNB_ERR_UNSUPPORTED, "nnb_linear_backward_dropped: needs N %% 4 == 0");
+    const nnb::DropArgs d = nnb::make_drop_args(drop_p, seed, call_id, epoch, epoch_dev);
+    return linear_backward_impl(X, W, Z, dO, dX, dW, db, M, K, N, act, beta, prec, W_staged, X_staged, workspace,
+                                workspace_bytes, stream, &d);
 }
 
 int nnb_linear_backward_staged(const float* X, const float* W, const void* dO_staged, float* dX, float* dW,

@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nnb {
 namespace {
@@ -32,16 +33,18 @@ struct StageArgs {
     int rows_per_block;
     int vec_ok;
     int tx;  // threads along columns (power of two <= 128)
+    DropArgs drop;  // DROP: dropout mask applied to the source first (flat index row * cols + col)
 };
 
 // Block = 128 threads arranged as TX (columns, 4 elements each) x TY (rows): wide matrices use
 // TX = 128, narrow ones (e.g. the 4096 x 10 logits gradient) fold rows into the block so no lane
 // idles. blockIdx.y owns a chunk of rows, blockIdx.z = batch. Column partial sums (bias gradient)
 // are reduced over TY in shared memory and written once per block.
-template <bool X3, int OP>
+template <bool X3, int OP, bool DROP = false>
 __global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
     pdl_trigger();
     pdl_wait();  // launched with the PDL attribute: nothing above touches global memory
+    const uint64_t epoch = DROP ? drop_epoch(a.drop) : 0;
     const int TX = a.tx, TY = (int)blockDim.x / a.tx;
     const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x / TX;
     const long long c = ((long long)blockIdx.x * TX + tx) * 4;
@@ -66,7 +69,13 @@ __global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
             for (int u = 0; u < 4; ++u) {
                 const long long rr = r + (long long)u * TY;
                 if (rr >= r1) break;
-                const float x[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+                float x[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+                if (DROP) {
+                    uint32_t w[4];
+                    drop_words(a.drop, epoch, (rr * a.v.cols + c) >> 2, w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = w[j] >= a.drop.thresh ? x[j] * a.drop.scale : 0.f;
+                }
                 __nv_bfloat16 h[4], l[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -85,17 +94,26 @@ __global__ void __launch_bounds__(512) stage_rows_kernel(const StageArgs a) {
             if (full && a.vec_ok) {
                 const float4 t = *reinterpret_cast<const float4*>(src + r * a.v.s_r + c);
                 x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+                if (DROP) {
+                    uint32_t w[4];
+                    drop_words(a.drop, epoch, (r * a.v.cols + c) >> 2, w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = w[j] >= a.drop.thresh ? x[j] * a.drop.scale : 0.f;
+                }
                 if (OP == STAGE_SWISH_BWD) {
                     const float4 z = *reinterpret_cast<const float4*>(aux + r * a.v.s_r + c);
                     x[0] *= swish_grad(z.x, a.beta); x[1] *= swish_grad(z.y, a.beta);
                     x[2] *= swish_grad(z.z, a.beta); x[3] *= swish_grad(z.w, a.beta);
                 }
             } else {
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                if (DROP) drop_words(a.drop, epoch, (r * a.v.cols + c) >> 2, w);  // cols % 4 == 0: c .. c + 3 share a group
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (c + j < a.v.cols) {
                         const long long off = r * a.v.s_r + (c + j) * a.v.s_c;
                         x[j] = src[off];
+                        if (DROP) x[j] = w[j] >= a.drop.thresh ? x[j] * a.drop.scale : 0.f;
                         if (OP == STAGE_SWISH_BWD) x[j] *= swish_grad(aux[off], a.beta);
                     }
                 }
@@ -172,8 +190,10 @@ size_t stage_colsum_scratch_bytes(int64_t cols) {
 
 int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst_hi,
                   __nv_bfloat16* dst_lo, int op, const float* aux, float beta, float* colsum,
-                  float* colsum_scratch, cudaStream_t stream, Staged* out) {
+                  float* colsum_scratch, cudaStream_t stream, Staged* out, const DropArgs* drop) {
     NNB_REQUIRE(!transpose, "stage_operand: transposing stage not implemented (use MN-major operand)");
+    NNB_REQUIRE(!drop || (src.b0 * src.b1 == 1 && src.s_c == 1 && src.s_r == src.cols && src.cols % 4 == 0),
+                "stage_operand: a dropout mask needs one contiguous [rows, cols] matrix with cols % 4 == 0");
     NNB_REQUIRE(src.ptr && dst_hi, "stage_operand: null pointer");
     NNB_REQUIRE(src.rows > 0 && src.cols > 0 && src.b0 > 0 && src.b1 > 0, "stage_operand: empty view");
     const bool x3 = prec == NNB_PREC_BF16X3;
@@ -192,6 +212,7 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     a.ld = ld;
     a.plane_stride = src.rows * ld;
     a.partial = nullptr;
+    if (drop) a.drop = *drop; else a.drop = DropArgs{};
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     a.vec_ok = src.s_c == 1 && (src.s_r % 4) == 0 && (src.s_b0 % 4) == 0 && (src.s_b1 % 4) == 0 &&
                al16(src.ptr) && (aux == nullptr || al16(aux));
@@ -218,13 +239,17 @@ int stage_operand(const View4& src, bool transpose, int prec, __nv_bfloat16* dst
     a.rows_per_block = (int)rpb;
     if (colsum) a.partial = colsum_scratch;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
-    if (x3) {
-        if (op == STAGE_SWISH_BWD) NNB_CUDA_OK(launch_pdl(stage_rows_kernel<true, STAGE_SWISH_BWD>, grid, dim3(threads), 0, stream, a));
-        else NNB_CUDA_OK(launch_pdl(stage_rows_kernel<true, STAGE_COPY>, grid, dim3(threads), 0, stream, a));
+    const dim3 block(threads);
+#define NNB_STAGE_LAUNCH(X3_, OP_, DROP_) NNB_CUDA_OK(launch_pdl(stage_rows_kernel<X3_, OP_, DROP_>, grid, block, 0, stream, a))
+    const bool swish = op == STAGE_SWISH_BWD;
+    if (drop) {
+        if (x3) { if (swish) NNB_STAGE_LAUNCH(true, STAGE_SWISH_BWD, true); else NNB_STAGE_LAUNCH(true, STAGE_COPY, true); }
+        else    { if (swish) NNB_STAGE_LAUNCH(false, STAGE_SWISH_BWD, true); else NNB_STAGE_LAUNCH(false, STAGE_COPY, true); }
     } else {
-        if (op == STAGE_SWISH_BWD) NNB_CUDA_OK(launch_pdl(stage_rows_kernel<false, STAGE_SWISH_BWD>, grid, dim3(threads), 0, stream, a));
-        else NNB_CUDA_OK(launch_pdl(stage_rows_kernel<false, STAGE_COPY>, grid, dim3(threads), 0, stream, a));
+        if (x3) { if (swish) NNB_STAGE_LAUNCH(true, STAGE_SWISH_BWD, false); else NNB_STAGE_LAUNCH(true, STAGE_COPY, false); }
+        else    { if (swish) NNB_STAGE_LAUNCH(false, STAGE_SWISH_BWD, false); else NNB_STAGE_LAUNCH(false, STAGE_COPY, false); }
     }
+#undef NNB_STAGE_LAUNCH
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     if (colsum) {

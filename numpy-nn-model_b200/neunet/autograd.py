@@ -144,7 +144,7 @@ class Tensor:
 
     def _reverse_broadcast(self, grad):
         """Sum a broadcast gradient back to this tensor's shape (autograd.py:948-962)."""
-        gshape, sshape = tuple(grad.shape), tuple(self.data.shape)
+        gshape, sshape = tuple(grad.shape), tuple(self.shape)  # .shape: a pending result is not forced for its shape
         if gshape == sshape:
             return grad
         xp = self.xp
@@ -648,6 +648,7 @@ class Tensor:
         if not self.requires_grad:
             return
         xp = self.xp
+        self.data  # noqa: B018 -- a pending root (deferred evaluation) is produced now: its producer fills in what backward needs
         if grad is None:
             grad = xp.ones_like(self.data)
         elif isinstance(grad, Tensor):
@@ -702,7 +703,8 @@ class Tensor:
                     else:
                         ent[1] += 1
         for v in reversed(tape):
-            v.grad_fn(*v.args, grad=v.grad)
+            g = v.__dict__.get("_grad") if isinstance(v, _Deferred) else v.grad  # raw: a parked _MaskedGrad goes to its consumer as is
+            v.grad_fn(*v.args, grad=g)
             if uses:
                 for a in v.args:
                     ent = uses.get(id(a)) if isinstance(a, Tensor) else None
@@ -711,6 +713,35 @@ class Tensor:
                         if ent[1] == 0:
                             del uses[id(a)]
                             a._grad_ready(a)
+
+
+class _MaskedGrad:
+    """An upstream gradient that still has to pass the backward of an nn.Dropout (``raw * mask(ticket) / (1 - p)``), parked
+    as the ``.grad`` of an nn.Linear result: the Linear's backward applies the mask inside the pass that converts its
+    upstream gradient to bf16 planes (neunet.b200.linear_backward: grad_drop), so the stand-alone mask kernel and its
+    read + write of the whole gradient disappear. Anything else that reads ``.grad`` gets the masked array
+    (``_Deferred.grad`` resolves it)."""
+    __slots__ = ("raw", "p", "ticket")
+
+    def __init__(self, raw, p, ticket):
+        self.raw, self.p, self.ticket = raw, p, ticket
+
+    def resolve(self):
+        from . import b200
+        return b200.dropout_apply(self.raw, self.p, self.ticket)
+
+
+_MASKED_GRAD_CONSUMERS = set()  # grad_fns that accept a _MaskedGrad (nn/layers/linear.py registers _linear_grad_fn)
+
+
+def _apply_dropped_grad(a, grad, p, ticket):
+    """``a.grad += grad * dropout_mask`` -- parked unmasked when ``a`` is an nn.Linear result with no gradient yet."""
+    if (_FUSION["on"] and isinstance(a, _Deferred) and a.requires_grad and a.__dict__.get("_grad") is None
+            and a.grad_fn in _MASKED_GRAD_CONSUMERS and tuple(grad.shape) == tuple(a.shape) and grad.shape[-1] % 4 == 0):
+        a.__dict__["_grad"] = _MaskedGrad(grad, p, ticket)
+        return
+    from . import b200
+    a.apply_grad(b200.dropout_apply(grad, p, ticket))
 
 
 class _Deferred(Tensor):
@@ -726,7 +757,7 @@ class _Deferred(Tensor):
         d["_thunk"] = thunk
         d["_shape"] = tuple(int(v) for v in shape)
         d["xp"] = get_xp("cuda")
-        d["grad"] = None
+        d["_grad"] = None
         d["op"] = op
         d["args"] = args
         d["requires_grad"] = requires_grad
@@ -762,6 +793,17 @@ class _Deferred(Tensor):
     @property
     def pending(self):
         return self._data is None
+
+    @property
+    def grad(self):
+        g = self.__dict__.get("_grad")
+        if type(g) is _MaskedGrad:
+            g = self.__dict__["_grad"] = g.resolve()
+        return g
+
+    @grad.setter
+    def grad(self, value):
+        self.__dict__["_grad"] = value
 
     @property
     def shape(self):
@@ -830,7 +872,7 @@ def _defer_add_dropout(x, t):
         if xr.requires_grad:
             xr.apply_grad(grad)
         if a.requires_grad:
-            a.apply_grad(b200.dropout_apply(grad, mask.p, mask.ticket))
+            _apply_dropped_grad(a, grad, mask.p, mask.ticket)
     out.grad_fn = grad_fn
     return out
 

@@ -84,6 +84,9 @@ _SIGNATURES = {
     "nnb_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
+    "nnb_linear_backward_dropped": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_int64, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_float, c_uint64, c_uint32, c_uint64, c_void_p, c_void_p]),
     "nnb_weight_staged_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "nnb_stage_weight": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "nnb_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
@@ -140,6 +143,8 @@ _SIGNATURES = {
     "nnb_rng_advance": (c_int, [c_void_p, c_void_p]),
     "nnb_dropout_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_uint64, c_uint32, c_uint64,
                                   c_void_p, c_void_p, c_int, c_void_p]),
+    "nnb_swish_dropout_fused": (c_int, [c_void_p, c_float, c_void_p, c_int64, c_int64, c_float, c_uint64, c_uint32, c_uint64,
+                                        c_void_p, c_void_p, c_int, c_void_p]),
     "nnb_rmsnorm_forward_fused": (c_int, [c_void_p, c_void_p, c_float, c_uint64, c_uint32, c_uint64, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                           c_float, c_void_p]),
@@ -163,7 +168,7 @@ _SIGNATURES = {
     "nnb_attention_backward": (c_int, [c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                        c_void_p, c_int, c_float, POINTER(c_int64), c_float, c_float, c_float, c_uint64,
                                        c_uint32, c_uint64, c_void_p, c_void_p, POINTER(c_int64), c_void_p, c_void_p,
-                                       c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+                                       c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "nnb_cross_entropy_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
     "nnb_cross_entropy_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
@@ -370,10 +375,11 @@ def _usable_out(buf, shape):
 
 
 def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, need_db=True, owner=None,
-                    x_staged=None, dw_out=None, db_out=None):
+                    x_staged=None, dw_out=None, db_out=None, grad_drop=None):
     """Returns (dX like x, dW (N,K), db (1,N)) -- dX / db None when not requested. dw_out / db_out: optional
     caller-owned destinations (e.g. slices of the data-parallel gradient bucket) the GEMM / column sums write
-    into directly instead of fresh tensors."""
+    into directly instead of fresh tensors. grad_drop = (p, ticket): `grad` still has to pass the backward of an
+    nn.Dropout -- the mask is applied inside the staging pass over grad (nnb_linear_backward_dropped)."""
     require_device()
     L = lib()
     N, K = w.shape
@@ -393,9 +399,19 @@ def linear_backward(x, w, grad, z=None, act=ACT_NONE, beta=1.0, need_dx=True, ne
         x_staged = None  # precision changed between forward and backward: convert again
     wsb = L.nnb_linear_workspace_bytes(M, K, N, prec, 1)
     ws = _workspace(wsb)
-    _check(L.nnb_linear_backward(_ptr(x2), _ptr(w), _ptr(z2), _ptr(g2), _ptr(dx), _ptr(dw), _ptr(db), M, K, N, act,
-                                 float(beta), prec, _ptr(wst), _ptr(x_staged), _ptr(ws), ws.numel(), _stream()),
-           "nnb_linear_backward")
+    if grad_drop is not None and N % 4 != 0:
+        g2 = dropout_apply(g2, grad_drop[0], grad_drop[1])
+        grad_drop = None
+    if grad_drop is not None:
+        p_drop, (seed, call_id, epoch, dev) = grad_drop
+        _check(L.nnb_linear_backward_dropped(_ptr(x2), _ptr(w), _ptr(z2), _ptr(g2), _ptr(dx), _ptr(dw), _ptr(db), M, K, N, act,
+                                             float(beta), prec, _ptr(wst), _ptr(x_staged), _ptr(ws), ws.numel(),
+                                             float(p_drop), seed, call_id, epoch, _ptr(dev), _stream()),
+               "nnb_linear_backward_dropped")
+    else:
+        _check(L.nnb_linear_backward(_ptr(x2), _ptr(w), _ptr(z2), _ptr(g2), _ptr(dx), _ptr(dw), _ptr(db), M, K, N, act,
+                                     float(beta), prec, _ptr(wst), _ptr(x_staged), _ptr(ws), ws.numel(), _stream()),
+               "nnb_linear_backward")
     if dx is not None:
         dx = dx.reshape(x.shape)
     return dx, dw, db
@@ -803,6 +819,22 @@ def dropout_apply(x, p, ticket, residual=None, want_planes=False):
     return y
 
 
+def swish_dropout_apply(z, beta, p, ticket, want_planes=True):
+    """dropout(swish(z)) in one pass over the pre-activation (+ the bf16 planes of the result for the next nn.Linear).
+    Bit-identical to dropout_apply(swish_forward(z, beta), p, ticket)."""
+    require_device()
+    z = _f32c(z)
+    y = torch.empty_like(z)
+    seed, call_id, epoch, dev = ticket
+    cols = z.shape[-1]
+    rows = z.numel() // max(cols, 1)
+    buf, prec = _new_planes(rows, cols) if want_planes else (None, _state["prec"])
+    if z.numel():
+        _check(lib().nnb_swish_dropout_fused(_ptr(z), float(beta), _ptr(y), rows, cols, float(p), seed, call_id, epoch,
+                                             _ptr(dev), _ptr(buf), prec, _stream()), "nnb_swish_dropout_fused")
+    return y, ((planes_key(y.reshape(rows, cols), prec), buf) if buf is not None else None)
+
+
 # ---- nn.Embedding ---------------------------------------------------------------------------------------------------
 def _ids(ids):
     if ids.dtype not in (torch.int32, torch.int64):
@@ -1030,7 +1062,8 @@ def attention_backward(q, kT, v, mask, fill, scale, p, ticket, grad):
     seed, call_id, epoch, dev = ticket if ticket is not None else (0, 0, 0, None)
     _check(lib().nnb_attention_backward(_ptr(q), _strides4(q), _ptr(kT), _strides4(kT), _ptr(v), _strides4(v), _ptr(mt), kind,
                                         cmp, ms, float(fill), float(scale), float(p), seed, call_id, epoch, _ptr(dev),
-                                        _ptr(grad), _strides4(grad), _ptr(dq), _ptr(dk), _ptr(dv), pitch, B, H, Tq, Tk, D,
+                                        _ptr(grad), _strides4(grad), _ptr(dq), _ptr(dk), _ptr(dv), pitch, _state["prec"], B, H, Tq,
+                                        Tk, D,
                                         _stream()), "nnb_attention_backward")
     return dq.permute(0, 2, 1, 3), dk.permute(0, 2, 3, 1), dv.permute(0, 2, 1, 3)
 

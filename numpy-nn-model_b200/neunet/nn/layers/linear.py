@@ -28,13 +28,17 @@ class _LinearTensor(Tensor):
 def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, x_staged, grad):
     if X.device == "cuda":
         from ... import b200
+        from ...autograd import _MaskedGrad
+        grad_drop = None
+        if type(grad) is _MaskedGrad:  # the upstream nn.Dropout left its mask to this layer's staging pass
+            grad, grad_drop = grad.raw, (grad.p, grad.ticket)
         # data-parallel training: the first (normally only) gradient contribution of a parameter is written
         # straight into its slice of the all-reduce bucket (neunet.distributed.GradBucket.overlap_backward)
         dw_out = getattr(weight, "_grad_buffer", None) if weight.grad is None else None
         db_out = getattr(bias, "_grad_buffer", None) if (bias is not None and bias.grad is None) else None
         dx, dw, db = b200.linear_backward(X.data, weight.data, grad, z=Z, act=act, beta=beta,
                                           need_dx=X.requires_grad, need_db=bias is not None, owner=weight,
-                                          x_staged=x_staged, dw_out=dw_out, db_out=db_out)
+                                          x_staged=x_staged, dw_out=dw_out, db_out=db_out, grad_drop=grad_drop)
         if dx is not None:
             X.apply_grad(dx)
         weight.apply_grad(dw)
@@ -49,6 +53,11 @@ def _linear_grad_fn(X: Tensor, weight: Tensor, bias, Z, act, beta, x_staged, gra
     weight.apply_grad(np.swapaxes(np.matmul(np.swapaxes(X.data, -1, -2), grad), -1, -2))
     if bias is not None:
         bias.apply_grad(np.sum(grad, axis=0, keepdims=True))
+
+
+from ... import autograd as _autograd  # noqa: E402
+
+_autograd._MASKED_GRAD_CONSUMERS.add(_linear_grad_fn)
 
 
 class _SiblingGroup:
@@ -232,13 +241,35 @@ def _deferred_linear(layer, X: Tensor) -> Tensor:
         return O
 
     def fuse_swish(beta):
+        """``nn.Swish`` on this pending Linear: the result stays pending. Read as it is, Swish is the GEMM's epilogue;
+        consumed by ``nn.Dropout`` first (the feed-forward block fc_2(dropout(swish(fc_1(x))))), the GEMM writes the
+        pre-activation only and ONE pass turns it into the dropped activations + their bf16 planes for fc_2
+        (``nnb_swish_dropout_fused``): the Swish output is never written unless somebody reads it."""
         lst = X.__dict__.get("_b200_pending_lin")
         if lst and out in lst:
             lst.remove(out)
-        O, Z, xst = run(1, beta)
-        out.args = (X, W, b, None, 0, 1.0, xst)
-        out.data = Z  # the pre-activation is the GEMM's side output: the Linear result itself is delivered for free
-        return _LinearTensor(O, (X, W, b, Z, 1, beta, xst), "linear_swish", "cuda")
+
+        def deliver(Z, xst):
+            out.args = (X, W, b, None, 0, 1.0, xst)
+            out.data = Z  # the pre-activation is the GEMM's side output: the Linear result itself is delivered for free
+            sw.args = (X, W, b, Z, 1, beta, xst)
+
+        def launch():
+            O, Z, xst = run(1, beta)
+            deliver(Z, xst)
+            return O
+
+        def fuse_dropout(p, ticket):
+            Z, _, xst = run(0, 1.0)
+            deliver(Z, xst)
+            sw.__dict__["_f_kind"] = "swish_lazy"
+            sw.__dict__["_thunk"] = lambda: b200.swish_forward(Z, beta)
+            return b200.swish_dropout_apply(Z, beta, p, ticket, want_planes=True)
+
+        sw = _Deferred.make(launch, out.shape, (X, W, b, None, 1, beta, None), "linear_swish", True, _f_kind="linear_swish",
+                            _f_fuse_dropout=fuse_dropout)
+        sw.grad_fn = _linear_grad_fn
+        return sw
 
     out = _Deferred.make(thunk, tuple(X.shape[:-1]) + (layer.out_features,), (X, W, b, None, act0, beta0, None), "linear", True,
                          _f_kind="linear", _f_act=act0, _f_fuse_swish=fuse_swish, _f_layer=layer)

@@ -60,8 +60,8 @@ class _StaticTensor(Tensor):
 
 def _dropout_grad(X: Tensor, mask, grad):
     if isinstance(mask, _DeviceMask):
-        from ... import b200
-        X.apply_grad(b200.dropout_apply(grad, mask.p, mask.ticket))
+        from ...autograd import _apply_dropped_grad
+        _apply_dropped_grad(X, grad, mask.p, mask.ticket)
         return
     X.apply_grad(grad * mask)
 
@@ -86,7 +86,7 @@ class Dropout(Module):
             raise TypeError("Input must be a tensor")
         if self.training and X.device == "cuda" and 0 <= self.p < 1:
             from ... import b200
-            from ...autograd import _Deferred, fusion_enabled
+            from ...autograd import _Deferred, _pending, fusion_enabled
             mask = _DeviceMask(self.p, b200.dropout_ticket())  # the ticket is taken NOW: call order fixes the masks
             if fusion_enabled():
                 # pending: `x + dropout(a)`, `norm(x + dropout(a))` and attention absorb it into their kernel
@@ -95,7 +95,11 @@ class Dropout(Module):
                 def thunk():
                     if not planes_ok:
                         return b200.dropout_apply(X.data, p, ticket)
-                    y, planes = b200.dropout_apply(X.data, p, ticket, want_planes=True)
+                    if _pending(X, "linear_swish"):
+                        # dropout(swish(linear(x))): one pass over the GEMM's pre-activation (nn/layers/linear.py: fuse_swish)
+                        y, planes = X._f_fuse_dropout(p, ticket)
+                    else:
+                        y, planes = b200.dropout_apply(X.data, p, ticket, want_planes=True)
                     out._b200_xst = planes  # bf16 operand planes for a following nn.Linear
                     return y
                 out = _Deferred.make(thunk, X.shape, (X, mask), "dropout", True, _f_kind="dropout", _f_src=X, _f_p=p,

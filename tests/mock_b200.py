@@ -37,7 +37,7 @@ def install():
              "attention_supported", "attention_forward", "attention_backward", "cross_entropy_forward",
              "cross_entropy_backward", "dropout_ticket", "_cache_scope", "conv2d_forward", "conv2d_backward",
              "conv_transpose2d_supported", "bn_forward", "bn_backward", "embedding_forward", "embedding_backward",
-             "cross_entropy_linear_backward"]
+             "cross_entropy_linear_backward", "swish_dropout_apply"]
     for n in names:
         _saved[n] = getattr(b200, n, None)
     _saved["device_prop"] = be.TorchXP.device
@@ -65,11 +65,13 @@ def install():
         return o, (z if save_z else None), None
 
     def linear_backward(x, w, grad, z=None, act=0, beta=1.0, need_dx=True, need_db=True, owner=None, x_staged=None,
-                        dw_out=None, db_out=None):
-        calls.append("linear_backward")
+                        dw_out=None, db_out=None, grad_drop=None):
+        calls.append("linear_backward_dropped" if grad_drop is not None else "linear_backward")
         if grad._base is not None and grad.shape[-1] == w.shape[0] and w.shape[0] > 3 * 8 and grad.is_contiguous():
             calls.append("linear_backward_zero_copy_candidate")
         g = grad
+        if grad_drop is not None:
+            g = g * _mask(g.shape, grad_drop[0], grad_drop[1])
         if act:
             s = torch.sigmoid(beta * z)
             f = z * s
@@ -117,6 +119,11 @@ def install():
         if want_planes:
             return y, (_planes(y.reshape(-1, y.shape[-1])) if y.shape[-1] % 8 == 0 else None)
         return y
+
+    def swish_dropout_apply(z, beta, p, ticket, want_planes=True):
+        calls.append("swish_dropout")
+        y = z * torch.sigmoid(beta * z) * _mask(z.shape, p, ticket)
+        return y, (_planes(y.reshape(-1, y.shape[-1])) if (want_planes and y.shape[-1] % 8 == 0) else None)
 
     def rmsnorm_forward(x, w, b=None, eps=1e-6, add_dropout=None, want_planes=False):
         calls.append("rmsnorm_forward_fused" if add_dropout is not None else "rmsnorm_forward")
@@ -290,6 +297,7 @@ def install():
     for n, f in dict(linear_forward=linear_forward, linear_backward=linear_backward, matmul=matmul,
                      matmul_backward=matmul_backward, softmax_forward=softmax_forward, softmax_backward=softmax_backward,
                      swish_forward=swish_forward, swish_backward=swish_backward, dropout_apply=dropout_apply,
+                     swish_dropout_apply=swish_dropout_apply,
                      rmsnorm_forward=rmsnorm_forward, rmsnorm_backward=rmsnorm_backward,
                      attention_supported=attention_supported, attention_forward=attention_forward,
                      attention_backward=attention_backward, cross_entropy_forward=cross_entropy_forward,

@@ -89,6 +89,42 @@ def test_fused_equals_eager_with_dropout_masks():
     assert "rmsnorm_backward_acc" in calls       # residual gradient accumulated by the norm's backward
     assert "linear_forward_staged" in calls      # Linear consumed ready-made operand planes
     assert "softmax_forward" not in calls and "matmul" not in calls
+    # fc_2(dropout(swish(fc_1 x))): one pass over the pre-activation, the Swish output is never materialised
+    assert calls.count("swish_dropout") == 2 and "swish_forward" not in calls
+    # the backward of every nn.Dropout that sits on an nn.Linear result is applied by that Linear's staging pass:
+    # 2 layers x (attention fc, fc_1 via swish, fc_2); only the embedding dropout keeps a stand-alone mask pass
+    assert calls.count("linear_backward_dropped") == 6 and calls.count("dropout") == 2  # embedding dropout: forward + backward
+
+
+def test_swish_output_absorbed_by_dropout_still_materialises_when_read():
+    with mock_b200.mocked():
+        import neunet
+        import neunet.nn as nn
+        from neunet import autograd, b200
+        np.random.seed(0)
+        lin, act, drop = nn.Linear(8, 16).to("cuda"), nn.Swish(), nn.Dropout(0.25)
+        x = neunet.tensor(np.random.randn(4, 8), device="cuda", requires_grad=True)
+        out = {}
+        for fuse in (True, False):
+            prev = autograd.set_fusion(fuse)
+            try:
+                b200.manual_seed(5)
+                b200._mock_reset_rng()
+                mock_b200.calls.clear()
+                x.grad = None
+                lin.weight.grad = None
+                s = act(lin(x))
+                d = drop(s)
+                dv = mock_b200.to_np(d.data).copy()
+                if fuse:
+                    assert "swish_dropout" in mock_b200.calls and "swish_forward" not in mock_b200.calls and s.pending
+                sv = mock_b200.to_np(s.data).copy()  # read AFTER the dropout absorbed it
+                (d * 2.0).sum().backward()
+                out[fuse] = (dv, sv, mock_b200.to_np(x.grad).copy(), mock_b200.to_np(lin.weight.grad).copy())
+            finally:
+                autograd.set_fusion(prev)
+        for a, b in zip(out[True], out[False]):
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6)
 
 
 def test_pending_results_materialise_when_read():
