@@ -747,8 +747,11 @@ def measure(wl, args, world, rank, local, K, W, dist, torch, b200, GradBucket, s
         loss = wl.forward_loss(*inputs)
         loss.backward()  # with overlap on, each ~32 MB gradient chunk is all-reduced as soon as it is final
         if bucket is not None:
-            bucket.all_reduce()  # the one collective: sum of gradients over NVLink (NCCL); waits for the chunks
-        opt.step()
+            # the one collective: sum of gradients over NVLink (NCCL). Each chunk's AdamW launch waits for that chunk only,
+            # so the optimizer of the early chunks runs underneath the all-reduce of the last one
+            bucket.all_reduce_and_step(opt)
+        else:
+            opt.step()
         return loss
 
     overlap = bucket is not None and not args.no_overlap

@@ -423,6 +423,13 @@ int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stre
 int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, int mode, float grad_scale,
                    cudaStream_t stream);
+/* The same update for tensors [first_tensor, first_tensor + n_tensors) only: data-parallel training steps each gradient
+ * chunk as soon as its all-reduce has landed, so the optimizer of the early chunks runs underneath the collective of
+ * the last ones (neunet/distributed.py: GradBucket.all_reduce_and_step). One optimizer step = ranges that cover every
+ * tensor once, all with the same `step`; with step = 0 exactly one of them passes advance_counter = 1 (the first). */
+int nnb_adamw_step_range(nnb_adamw* opt, int first_tensor, int n_tensors, double lr, double beta1, double beta2, double eps,
+                         double weight_decay, int64_t step, int mode, float grad_scale, int advance_counter,
+                         cudaStream_t stream);
 /* CUDA-graph support: pass step = 0 to nnb_adamw_step to use (and first advance) a step counter
  * kept in device memory, so replaying a captured step keeps the bias corrections moving;
  * nnb_adamw_set_step() seeds that counter (number of steps already taken). */

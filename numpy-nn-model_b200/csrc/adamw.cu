@@ -29,6 +29,7 @@ struct nnb_adamw {
     bool staging = false;
     long long* d_t = nullptr;     // device-resident step counter (CUDA-graph replays advance it)
     std::vector<const float**> snapshots;  // pinned pointer tables owned by captured graphs
+    std::vector<int> blk_start;   // [n + 1]: first block of every tensor (nnb_adamw_step_range)
 };
 
 namespace nnb {
@@ -178,6 +179,8 @@ int nnb_adamw_create(nnb_adamw** out, int n, float* const* p, const float* const
     nnb_adamw* o = new nnb_adamw();
     o->n = n;
     o->nblocks = (int)bt.size();
+    o->blk_start.assign(n + 1, (int)bt.size());
+    for (int b = (int)bt.size() - 1; b >= 0; --b) o->blk_start[bt[b]] = b;
     o->h_g.assign(n, nullptr);
     if (g) for (int i = 0; i < n; ++i) o->h_g[i] = g[i];
     NNB_CUDA_OK(cudaMalloc(&o->d_p, n * sizeof(float*)));
@@ -231,13 +234,12 @@ int nnb_adamw_set_grads(nnb_adamw* opt, const float* const* g, cudaStream_t stre
     return NNB_OK;
 }
 
-int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double eps,
-                   double weight_decay, int64_t step, int mode, float grad_scale,
-                   cudaStream_t stream) {
-    NNB_RANGE("nnb_adamw_step");
+static int adamw_launch(nnb_adamw* opt, int first, int count, double lr, double beta1, double beta2, double eps,
+                        double weight_decay, int64_t step, int mode, float grad_scale, bool advance, cudaStream_t stream) {
     NNB_REQUIRE(opt, "nnb_adamw_step: null handle");
     NNB_REQUIRE(step >= 0, "nnb_adamw_step: step must be >= 1, or 0 to use the device-resident counter");
     NNB_REQUIRE(mode == NNB_OPT_ADAM_L2 || mode == NNB_OPT_ADAMW, "nnb_adamw_step: bad mode");
+    NNB_REQUIRE(first >= 0 && count > 0 && first + count <= opt->n, "nnb_adamw_step_range: bad tensor range");
     AdamScalars s;
     // Scalars are formed in double exactly where the reference forms them in Python floats, then
     // rounded once to fp32 (NumPy casts a Python float operand to the array dtype).
@@ -255,19 +257,37 @@ int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double
     s.wd = (float)weight_decay;
     s.gscale = grad_scale;
     s.mode = mode;
-    if (step == 0) {
+    if (step == 0 && advance) {
         adam_advance_step_kernel<<<1, 1, 0, stream>>>(opt->d_t);
         count_launch();
     }
-    adamw_multi_kernel<<<opt->nblocks, ADAM_THREADS, 0, stream>>>(opt->d_p, opt->d_g, opt->d_m, opt->d_v,
-                                                                  opt->d_sizes, opt->d_blk_tensor,
-                                                                  opt->d_blk_chunk, s,
-                                                                  step == 0 ? opt->d_t : nullptr,
-                                                                  opt->staging ? opt->d_stage : nullptr,
-                                                                  opt->d_stage_cols, opt->d_stage_lo);
-    count_launch();
+    const int b0 = opt->blk_start[first], b1 = opt->blk_start[first + count];
+    if (b1 > b0) {
+        adamw_multi_kernel<<<b1 - b0, ADAM_THREADS, 0, stream>>>(opt->d_p, opt->d_g, opt->d_m, opt->d_v, opt->d_sizes,
+                                                                 opt->d_blk_tensor + b0, opt->d_blk_chunk + b0, s,
+                                                                 step == 0 ? opt->d_t : nullptr,
+                                                                 opt->staging ? opt->d_stage : nullptr,
+                                                                 opt->d_stage_cols, opt->d_stage_lo);
+        count_launch();
+    }
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
+}
+
+int nnb_adamw_step(nnb_adamw* opt, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, int mode, float grad_scale,
+                   cudaStream_t stream) {
+    NNB_RANGE("nnb_adamw_step");
+    NNB_REQUIRE(opt, "nnb_adamw_step: null handle");
+    return adamw_launch(opt, 0, opt->n, lr, beta1, beta2, eps, weight_decay, step, mode, grad_scale, true, stream);
+}
+
+int nnb_adamw_step_range(nnb_adamw* opt, int first_tensor, int n_tensors, double lr, double beta1, double beta2, double eps,
+                         double weight_decay, int64_t step, int mode, float grad_scale, int advance_counter,
+                         cudaStream_t stream) {
+    NNB_RANGE("nnb_adamw_step_range");
+    return adamw_launch(opt, first_tensor, n_tensors, lr, beta1, beta2, eps, weight_decay, step, mode, grad_scale,
+                        advance_counter != 0, stream);
 }
 
 int nnb_adamw_set_staging(nnb_adamw* opt, void* const* staged, const int64_t* cols, int prec,

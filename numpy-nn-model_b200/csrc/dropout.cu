@@ -19,8 +19,9 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// the stand-alone Swish of elementwise.cu (neunet/nn/activations.py:208-211), same expression -> same bits
-__device__ __forceinline__ float swish_of(float z, float beta) { return z * (1.0f / (1.0f + expf(-beta * z))); }
+// Swish (neunet/nn/activations.py:208-211) with the fast exponential / reciprocal (~2 ulp): with four sigmoids and one
+// Philox block per 16 bytes this pass is issue-bound, not HBM-bound
+__device__ __forceinline__ float swish_of(float z, float beta) { return z * __fdividef(1.0f, 1.0f + __expf(-beta * z)); }
 
 // y = (residual +) dropout(x) -- x = swish(z) when SWISH (the FFN of examples/gpt.ipynb cell 4: fc_2(dropout(swish(fc_1 x)))
 // reads the pre-activation once and never materialises the activation); optionally also the bf16 planes of y (hi [+ lo])

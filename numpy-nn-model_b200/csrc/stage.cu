@@ -12,7 +12,7 @@ namespace {
 
 __device__ __forceinline__ float swish_grad(float z, float beta) {
     // d/dz [z * sigmoid(beta z)] = beta*f + sigmoid(beta z) * (1 - beta*f)
-    const float s = 1.0f / (1.0f + __expf(-beta * z));
+    const float s = __fdividef(1.0f, 1.0f + __expf(-beta * z));  // MUFU.EX2 + MUFU.RCP: this pass is issue-bound, not HBM-bound
     const float f = z * s;
     return beta * f + s * (1.0f - beta * f);
 }

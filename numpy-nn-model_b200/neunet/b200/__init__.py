@@ -183,6 +183,8 @@ _SIGNATURES = {
     "nnb_adamw_set_grads": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
     "nnb_adamw_step": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_int64, c_int,
                                c_float, c_void_p]),
+    "nnb_adamw_step_range": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_int64, c_int,
+                                     c_float, c_int, c_void_p]),
     "nnb_adamw_set_step": (c_int, [c_void_p, c_int64, c_void_p]),
     "nnb_adamw_set_staging": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p]),
     "nnb_adamw_destroy": (c_int, [c_void_p]),
@@ -821,7 +823,7 @@ def dropout_apply(x, p, ticket, residual=None, want_planes=False):
 
 def swish_dropout_apply(z, beta, p, ticket, want_planes=True):
     """dropout(swish(z)) in one pass over the pre-activation (+ the bf16 planes of the result for the next nn.Linear).
-    Bit-identical to dropout_apply(swish_forward(z, beta), p, ticket)."""
+    Same mask and (to ~2 ulp) the same values as dropout_apply(swish_forward(z, beta), p, ticket)."""
     require_device()
     z = _f32c(z)
     y = torch.empty_like(z)
@@ -1266,6 +1268,20 @@ class FusedAdam:
         _check(L.nnb_adamw_step(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                 int(t), mode, float(grad_scale), _stream()), "nnb_adamw_step")
         weights_changed()
+
+    def set_grads(self, grads):
+        """Upload the gradient pointer table (None = skipped) for the range steps that follow."""
+        self._grads_keep = grads
+        arr = (c_void_p * self.n)(*[(g.data_ptr() if g is not None else None) for g in grads])
+        _check(lib().nnb_adamw_set_grads(self._h, arr, _stream()), "nnb_adamw_set_grads")
+
+    def step_range(self, first, count, lr, betas, eps, weight_decay, t, mode, grad_scale=1.0, advance=False):
+        """The update for parameters [first, first + count) only (after set_grads); see nnb_adamw_step_range."""
+        if torch.cuda.is_current_stream_capturing():
+            t = 0
+        _check(lib().nnb_adamw_step_range(self._h, int(first), int(count), float(lr), float(betas[0]), float(betas[1]),
+                                          float(eps), float(weight_decay), int(t), mode, float(grad_scale), int(bool(advance)),
+                                          _stream()), "nnb_adamw_step_range")
 
     def sync_staging(self, owners):
         """Fused weight staging: for every parameter that a Linear layer has asked bf16 planes for

@@ -213,3 +213,41 @@ class GradBucket:
             self._reduce(live)
             self._adopt(live)
         self._reset_step()
+
+    def all_reduce_and_step(self, optimizer):
+        """``all_reduce()`` followed by ``optimizer.step()``, with the optimizer of every gradient chunk launched as soon as
+        THAT chunk's all-reduce has landed: chunks are reduced in the order backward produced them, so the Adam(W) update of
+        the early chunks (the last layers) runs underneath the collective of the late ones (the embedding, final only when
+        backward ends) instead of behind it. Same arithmetic as the two separate calls. Falls back to them whenever the
+        overlapped path does not apply (no chunks yet, CPU, an optimizer over a different parameter list, stray gradients)."""
+        ok = (self._chunks is not None and self.device == "cuda" and hasattr(optimizer, "step_ranges")
+              and len(optimizer.params) == len(self.params) and all(a is b for a, b in zip(optimizer.params, self.params)))
+        if ok:
+            covered = set(self._chunk_of)
+            ok = not any(p.grad is not None and i not in covered for i, p in enumerate(self.params))
+        if not ok:
+            self.all_reduce()
+            optimizer.step()
+            return
+        states = []
+        for c, st in enumerate(self._launched):
+            if st is None:  # chunk never completed during backward: launch it now, in chunk order on every rank
+                members = self._chunks[c]
+                live = self._pack(members[0], members[-1] + 1)
+                st = (live, self._reduce(live, async_op=True))
+            states.append(st)
+            self._adopt(st[0])  # pointers only: the optimizer's gradient table is the bucket slices
+
+        def waiter(work):
+            return (lambda: work.wait()) if work is not None else None
+
+        ranges, lo_prev = [], len(self.params)
+        for c, (live, work) in enumerate(states):  # launch order = reverse parameter order
+            members = self._chunks[c]
+            lo = members[0]
+            ranges.append((lo, lo_prev - lo, waiter(work)))  # up to the previous chunk: dead parameters in between are skipped
+            lo_prev = lo
+        if lo_prev > 0:
+            ranges.append((0, lo_prev, None))
+        optimizer.step_ranges(ranges)
+        self._reset_step()

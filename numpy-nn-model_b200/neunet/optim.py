@@ -29,7 +29,9 @@ class _AdamBase:
             p.grad = None
 
     # -- device path ---------------------------------------------------------------------------
-    def _device_step(self):
+    def _device_step(self, ranges=None):
+        """ranges: None = one launch over every parameter; else an iterable of (first, count, before) -- the update is
+        issued range by range, `before()` (e.g. the wait for that gradient chunk's all-reduce) called ahead of each."""
         from . import b200
         key = tuple(p.data.data_ptr() for p in self.params)
         if self._fused is None or self._fused_key != key:
@@ -49,8 +51,25 @@ class _AdamBase:
                     g = g.contiguous().to(p.data.dtype)
             grads.append(g)
         self._fused.sync_staging(self.params)  # the kernel also writes the bf16 planes Linear layers read
-        self._fused.step(grads, self.lr, self.betas, self.eps, self.weight_decay, self.t, self._mode, self.grad_scale)
+        if ranges is None:
+            self._fused.step(grads, self.lr, self.betas, self.eps, self.weight_decay, self.t, self._mode, self.grad_scale)
+        else:
+            self._fused.set_grads(grads)
+            first_launch = True
+            for first, count, before in ranges:
+                if before is not None:
+                    before()
+                self._fused.step_range(first, count, self.lr, self.betas, self.eps, self.weight_decay, self.t, self._mode,
+                                       self.grad_scale, advance=first_launch)
+                first_launch = False
+            b200.weights_changed()
         self._fused.stamp_staging(self.params, grads)
+
+    def step_ranges(self, ranges):
+        """One optimizer step issued as several launches over disjoint parameter ranges that together cover every
+        parameter (``neunet.distributed.GradBucket.all_reduce_and_step``); same result as ``step()``."""
+        self.t += 1
+        return self._device_step(ranges)
 
     def step(self):
         self.t += 1

@@ -43,7 +43,7 @@ def _params(layers):
     return ps
 
 
-def _step(layers, opt, x, y, bucket=None, device="cuda"):
+def _step(layers, opt, x, y, bucket=None, device="cuda", chunked_step=False):
     import neunet
     import neunet.nn as nn
     opt.zero_grad()
@@ -52,6 +52,9 @@ def _step(layers, opt, x, y, bucket=None, device="cuda"):
         h = l(h)
     loss = nn.CrossEntropyLoss()(h, neunet.tensor(y, dtype=np.int32, device=device))
     loss.backward()
+    if bucket is not None and chunked_step:
+        bucket.all_reduce_and_step(opt)  # the optimizer of each chunk right behind that chunk's all-reduce
+        return loss
     if bucket is not None:
         bucket.all_reduce()
     opt.step()
@@ -80,7 +83,7 @@ def _worker(rank, world, port, xs, ys, ret, native=False):
     opt = Adam(params, lr=1e-2, eps=1e-3)  # large eps: near-zero gradients must not turn round-off into sign flips
     opt.grad_scale = 1.0 / world
     for t in range(4):
-        _step(layers, opt, xs[t][rank], ys[t][rank], bucket)
+        _step(layers, opt, xs[t][rank], ys[t][rank], bucket, chunked_step=(t == 3))
         if t == 1:
             bucket.overlap_backward()  # steps 2, 3: chunked all-reduce launched from the ready-hooks
     torch.cuda.synchronize()
