@@ -21,7 +21,11 @@ __device__ __forceinline__ float lrelu(float x, float alpha) { return x <= 0.f ?
 
 constexpr int BN_CHUNKS = 32;  // partial-sum rows per channel (fixed order -> deterministic)
 
-// grid = (C, chunks): block (c, j) reduces images b = j, j + chunks, ... of channel c.
+// grid = (C, chunks): block (c, j) reduces images b = j, j + chunks, ... of channel c. The block's threads walk the
+// (image, pixel) pairs of those planes as ONE flat index, so a 4 x 4 plane of a deep UNet level keeps four lanes busy per
+// image and 64 images fill the block -- a block per plane left 252 of 256 threads idle there (ncu launch list, round 2:
+// 91 us for the 4 MB of a C = 1024 level against 15 us for the 33 MB of the C = 128 level). `chunks` shrinks with the
+// plane so every block still has ~2 K elements (chunks_for).
 // MODE 0: {sum a, sum a^2};  MODE 1: {sum g, sum g * xhat}
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g,
@@ -33,45 +37,52 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     const float mu = MODE == 1 ? mean[c] : 0.f, is = MODE == 1 ? inv[c] : 0.f;
     double s0 = 0.0, s1 = 0.0;
     const bool vec = (HW % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
-    for (int b = blockIdx.y; b < B; b += gridDim.y) {
-        const float* xp = x + ((long long)b * C + c) * HW;
-        const float* gp = MODE == 1 ? g + ((long long)b * C + c) * HW : nullptr;
-        float t0 = 0.f, t1 = 0.f;  // fp32 within one image plane per thread (<= HW / 256 terms), fp64 across
-        if (vec) {
-            for (int i = threadIdx.x * 4; i < HW; i += 1024) {
-                const float4 v = *reinterpret_cast<const float4*>(xp + i);
-                const float a[4] = {lrelu(v.x, alpha), lrelu(v.y, alpha), lrelu(v.z, alpha), lrelu(v.w, alpha)};
-                if (MODE == 0) {
+    const int nimg = (B - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;  // images of this block
+    const long long total = (long long)nimg * HW;
+    const long long img_stride = (long long)gridDim.y * C * HW, base = ((long long)blockIdx.y * C + c) * HW;
+    if (vec) {
+        for (long long e = (long long)threadIdx.x * 4; e < total; e += 1024) {
+            const long long k = e / HW;
+            const long long off = base + k * img_stride + (e - k * HW);
+            const float4 v = *reinterpret_cast<const float4*>(x + off);
+            const float a[4] = {lrelu(v.x, alpha), lrelu(v.y, alpha), lrelu(v.z, alpha), lrelu(v.w, alpha)};
+            float t0 = 0.f, t1 = 0.f;  // fp32 over the four elements, fp64 across
+            if (MODE == 0) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { t0 += a[j]; t1 += a[j] * a[j]; }
-                } else {
-                    const float4 gv = *reinterpret_cast<const float4*>(gp + i);
-                    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+                for (int j = 0; j < 4; ++j) { t0 += a[j]; t1 += a[j] * a[j]; }
+            } else {
+                const float4 gv = *reinterpret_cast<const float4*>(g + off);
+                const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { t0 += gg[j]; t1 += gg[j] * ((a[j] - mu) * is); }
-                }
+                for (int j = 0; j < 4; ++j) { t0 += gg[j]; t1 += gg[j] * ((a[j] - mu) * is); }
             }
-        } else {
-            for (int i = threadIdx.x; i < HW; i += 256) {
-                const float a = lrelu(xp[i], alpha);
-                if (MODE == 0) { t0 += a; t1 += a * a; }
-                else { t0 += gp[i]; t1 += gp[i] * ((a - mu) * is); }
-            }
+            s0 += (double)t0;
+            s1 += (double)t1;
         }
-        s0 += (double)t0;
-        s1 += (double)t1;
+    } else {
+        for (long long e = threadIdx.x; e < total; e += 256) {
+            const long long k = e / HW;
+            const long long off = base + k * img_stride + (e - k * HW);
+            const float a = lrelu(x[off], alpha);
+            if (MODE == 0) { s0 += (double)a; s1 += (double)(a * a); }
+            else { s0 += (double)g[off]; s1 += (double)(g[off] * ((a - mu) * is)); }
+        }
     }
-    __shared__ double r0[256], r1[256];
-    r0[threadIdx.x] = s0;
-    r1[threadIdx.x] = s1;
+    // fixed-order block reduction: shuffles inside the warp, then the eight warp totals in warp order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    }
+    __shared__ double r0[8], r1[8];
+    if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = s0; r1[threadIdx.x >> 5] = s1; }
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
-        partial[((long long)blockIdx.y * C + c) * 2] = r0[0];
-        partial[((long long)blockIdx.y * C + c) * 2 + 1] = r1[0];
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a0 += r0[w]; a1 += r1[w]; }
+        partial[((long long)blockIdx.y * C + c) * 2] = a0;
+        partial[((long long)blockIdx.y * C + c) * 2 + 1] = a1;
     }
 }
 
@@ -112,24 +123,28 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ mean, const float* __restrict__ inv,
                                                        const float* __restrict__ w, const float* __restrict__ b,
                                                        const double* __restrict__ sums, double count, int C, int HW,
-                                                       long long planes, float alpha, float* __restrict__ out) {
+                                                       long long planes, float alpha, float* __restrict__ out, int lpp) {
     pdl_trigger();
     pdl_wait();
     const bool vec = (HW % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                                         reinterpret_cast<uintptr_t>(g)) & 15) == 0;
-    for (long long pl = blockIdx.x; pl < planes; pl += gridDim.x) {  // one (b, c) image plane at a time
+    // `lpp` lanes (a power of two chosen by the host: ~ HW / 4, at most the block) share one (b, c) image plane, so a block
+    // works on blockDim / lpp planes at a time: the 4 x 4 and 8 x 8 planes of the deep UNet levels fill the block too
+    const int sub = threadIdx.x / lpp, lane = threadIdx.x - sub * lpp, ppb = blockDim.x / lpp;
+    const double inv_count = 1.0 / count;
+    for (long long pl = (long long)blockIdx.x * ppb + sub; pl < planes; pl += (long long)gridDim.x * ppb) {
         const int c = (int)(pl % C);
         const float mu = mean[c], is = inv[c], wc = w ? w[c] : 1.f, bc = b ? b[c] : 0.f;
         float k1 = 0.f, k2 = 0.f;
         if (MODE == 1) {
-            k1 = (float)(sums[2 * c] / count) * wc;       // mean(w * g)
-            k2 = (float)(sums[2 * c + 1] / count) * wc;   // mean(w * g * xhat)
+            k1 = (float)(sums[2 * c] * inv_count) * wc;       // mean(w * g)
+            k2 = (float)(sums[2 * c + 1] * inv_count) * wc;   // mean(w * g * xhat)
         }
         const float* xp = x + pl * HW;
         const float* gp = MODE == 1 ? g + pl * HW : nullptr;
         float* op = out + pl * HW;
         if (vec) {
-            for (int i = threadIdx.x * 4; i < HW; i += blockDim.x * 4) {
+            for (int i = lane * 4; i < HW; i += lpp * 4) {
                 const float4 v = *reinterpret_cast<const float4*>(xp + i);
                 const float xv[4] = {v.x, v.y, v.z, v.w};
                 float r[4];
@@ -148,7 +163,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                 *reinterpret_cast<float4*>(op + i) = make_float4(r[0], r[1], r[2], r[3]);
             }
         } else {
-            for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+            for (int i = lane; i < HW; i += lpp) {
                 if (MODE == 0) {
                     op[i] = (lrelu(xp[i], alpha) - mu) * is * wc + bc;
                 } else {
@@ -175,12 +190,27 @@ int check_shape(int64_t B, int64_t C, int64_t HW, const char* who) {
     return NNB_OK;
 }
 
-int chunks_for(int64_t B) { return (int)std::min<int64_t>(BN_CHUNKS, B); }
+// partial rows per channel: every block gets >= ~2 K elements, at most BN_CHUNKS (and at most B) rows
+int chunks_for(int64_t B, int64_t HW) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(BN_CHUNKS, B), B * HW / 2048));
+}
+
+// lanes that share one image plane in bn_apply_kernel (power of two, <= 256) and the grid that goes with them
+int apply_lanes(int64_t HW) {
+    const int64_t want = (HW % 4 == 0) ? HW / 4 : HW;
+    int lpp = 1;
+    while (lpp < 256 && lpp < want) lpp <<= 1;
+    return lpp;
+}
+int apply_blocks(long long planes, int lpp) {
+    const long long ppb = 256 / lpp;
+    return (int)std::max<long long>(1, std::min<long long>((planes + ppb - 1) / ppb, (long long)num_sms() * 8));
+}
 
 template <int MODE>
 int run_reduce(const float* x, const float* g, const float* mean, const float* inv, int64_t B, int64_t C, int64_t HW,
                float alpha, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    const int chunks = chunks_for(B);
+    const int chunks = chunks_for(B, HW);
     NNB_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)chunks * C * 2 * sizeof(double) + 256,
                 "nnb_bn: workspace too small (nnb_bn_workspace_bytes)");
     double* partial = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
@@ -234,10 +264,9 @@ int nnb_bn_apply(const float* x, const float* mean, const float* inv_std, const 
     int rc = check_shape(B, C, HW, "nnb_bn_apply");
     if (rc) return rc;
     const long long planes = (long long)B * C;
-    const int blocks = (int)std::min<long long>(planes, (long long)num_sms() * 16);
-    const int threads = HW >= 1024 ? 256 : (HW >= 256 ? 64 : 32);
-    NNB_CUDA_OK(launch_pdl(bn_apply_kernel<0>, dim3(blocks), dim3(threads), 0, stream, x, (const float*)nullptr, mean, inv_std, w, b,
-                           (const double*)nullptr, 1.0, (int)C, (int)HW, planes, alpha, y));
+    const int lpp = apply_lanes(HW);
+    NNB_CUDA_OK(launch_pdl(bn_apply_kernel<0>, dim3(apply_blocks(planes, lpp)), dim3(256), 0, stream, x, (const float*)nullptr, mean,
+                           inv_std, w, b, (const double*)nullptr, 1.0, (int)C, (int)HW, planes, alpha, y, lpp));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;
@@ -263,10 +292,9 @@ int nnb_bn_backward_apply(const float* x, const float* grad, const float* mean, 
     if (rc) return rc;
     if (dx != nullptr) {
         const long long planes = (long long)B * C;
-        const int blocks = (int)std::min<long long>(planes, (long long)num_sms() * 16);
-        const int threads = HW >= 1024 ? 256 : (HW >= 256 ? 64 : 32);
-        NNB_CUDA_OK(launch_pdl(bn_apply_kernel<1>, dim3(blocks), dim3(threads), 0, stream, x, grad, mean, inv_std, w,
-                               (const float*)nullptr, sums, count, (int)C, (int)HW, planes, alpha, dx));
+        const int lpp = apply_lanes(HW);
+        NNB_CUDA_OK(launch_pdl(bn_apply_kernel<1>, dim3(apply_blocks(planes, lpp)), dim3(256), 0, stream, x, grad, mean, inv_std, w,
+                               (const float*)nullptr, sums, count, (int)C, (int)HW, planes, alpha, dx, lpp));
         count_launch();
     }
     if (dw != nullptr || db != nullptr) {

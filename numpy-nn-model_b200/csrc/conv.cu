@@ -448,6 +448,33 @@ __global__ void __launch_bounds__(256) convT_interleave_kernel(const float* __re
     }
 }
 
+// The same for stride (s0, 2) with Wo % 4 == 0 and < 2^31 elements (every transposed conv of the DDPM UNet): one thread
+// per FOUR adjacent output pixels = two adjacent class positions of the px = 0 and px = 1 planes -> two 8-byte loads, one
+// 16-byte store, 32-bit index arithmetic (the generic kernel spends its time in six 64-bit divisions per element).
+__global__ void __launch_bounds__(256) convT_interleave_s2_kernel(const float* __restrict__ T, const float* __restrict__ bias,
+                                                                  unsigned B, unsigned Cout, unsigned P, unsigned Q, unsigned s0,
+                                                                  float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const unsigned Ho = P * s0, W4 = Q / 2;  // Wo / 4 quads per output row
+    const unsigned N = B * P * Q;
+    const unsigned total4 = B * Cout * Ho * W4;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += gridDim.x * blockDim.x) {
+        const unsigned xq = idx % W4;
+        unsigned t = idx / W4;
+        const unsigned y = t % Ho; t /= Ho;
+        const unsigned o = t % Cout;
+        const unsigned b = t / Cout;
+        const unsigned py = y % s0, u = y / s0;
+        const size_t n = (size_t)(b * P + u) * Q + 2 * xq;                     // class position of the quad's first pixel
+        const size_t plane0 = ((size_t)(py * 2) * Cout + o) * N + n;           // px = 0 plane; px = 1 is Cout * N further
+        const float2 c0 = *reinterpret_cast<const float2*>(T + plane0);
+        const float2 c1 = *reinterpret_cast<const float2*>(T + plane0 + (size_t)Cout * N);
+        const float bo = bias != nullptr ? bias[o] : 0.f;
+        *reinterpret_cast<float4*>(out + (size_t)idx * 4) = make_float4(c0.x + bo, c1.x + bo, c0.y + bo, c1.y + bo);
+    }
+}
+
 // dW[o][c][kh-1-k'][kw-1-l'] = T[c][((k'*kw + l')*Cout + o)]: one thread per (c, o), reads coalesced over o
 __global__ void permute_dw_convT_kernel(const float* __restrict__ T, int Cout, int Cin, int kh, int kw, float* __restrict__ dW) {
     const int khw = kh * kw;
@@ -817,8 +844,15 @@ int tconv_classes(const TGeo& t, const Planes& xh, const float* Wt, int swap, co
         }
     }
     const long long total = (long long)g.B * g.Cout * g.Ho * g.Wo;
-    NNB_CUDA_OK(launch_pdl(convT_interleave_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, (const float*)T, bias, g.B, g.Cout,
-                           t.P, t.Q, g.s0, g.s1, O));
+    const long long npos = (long long)g.B * t.P * t.Q;
+    if (g.s1 == 2 && (t.Q % 2) == 0 && total < (1ll << 31) && (long long)g.s0 * 2 * g.Cout * npos < (1ll << 40) &&
+        ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(O)) & 15) == 0) {
+        NNB_CUDA_OK(launch_pdl(convT_interleave_s2_kernel, dim3(grid_for(total / 4, 256)), dim3(256), 0, stream, (const float*)T, bias,
+                               (unsigned)g.B, (unsigned)g.Cout, (unsigned)t.P, (unsigned)t.Q, (unsigned)g.s0, O));
+    } else {
+        NNB_CUDA_OK(launch_pdl(convT_interleave_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, (const float*)T, bias, g.B,
+                               g.Cout, t.P, t.Q, g.s0, g.s1, O));
+    }
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
     return NNB_OK;

@@ -1,11 +1,11 @@
 #!/bin/bash
+# two-GPU check: NCCL parity tests (torch.distributed and nnb_comm, chunked optimizer step) + the data-parallel bench lines
 mkdir -p gpurun_out/n2
-export BENCH_HB_DIR=gpurun_out/n2 NCCL_DEBUG=WARN
-run() { name=$1; np=$2; shift 2
-  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port 29511 \
-     bench.py --gpus $np --steps 30 --warmup 3 --watchdog 170 --no-x3 "$@" > gpurun_out/n2/$name.json 2> gpurun_out/n2/$name.err
-  rc=$?; echo "$name rc=$rc"; head -c 330 gpurun_out/n2/$name.json; echo; [ $rc -ne 0 ] && tail -5 gpurun_out/n2/$name.err; return 0
-}
-run gpt2 2
-run ddpm2 2 --workload ddpm
-timeout 150 python -m pytest tests/test_multigpu.py -x -q -m gpu -p no:cacheprovider --timeout 100 --timeout-method=thread 2>&1 | tail -3
+export BENCH_HB_DIR=gpurun_out/n2
+timeout 200 python -m pytest -q --tb=short -p no:cacheprovider --timeout 150 --timeout-method=thread -m gpu tests/test_multigpu.py > gpurun_out/n2/pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/n2/pytest.log
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+   bench.py --gpus 2 --steps 30 --warmup 3 --watchdog 170 --no-x3 > gpurun_out/n2/gpt2.json 2> gpurun_out/n2/gpt2.err
+echo "gpt2 rc=$?"; grep '^{' gpurun_out/n2/gpt2.json | head -c 330; echo
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
+   bench.py --gpus 2 --steps 30 --warmup 3 --watchdog 170 --no-x3 --workload ddpm > gpurun_out/n2/ddpm2.json 2> gpurun_out/n2/ddpm2.err
+echo "ddpm2 rc=$?"; grep '^{' gpurun_out/n2/ddpm2.json | head -c 330; echo

@@ -229,7 +229,8 @@ def test_fused_step_captures_into_a_cuda_graph():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
 
 
-@pytest.mark.parametrize("B,C,H,W,alpha,affine", [(8, 128, 16, 16, 0.01, True), (5, 16, 7, 7, 1.0, True), (64, 256, 4, 4, 0.01, False)])
+@pytest.mark.parametrize("B,C,H,W,alpha,affine", [(8, 128, 16, 16, 0.01, True), (5, 16, 7, 7, 1.0, True), (64, 256, 4, 4, 0.01, False),
+                                                  (64, 32, 32, 32, 0.01, True), (3, 520, 2, 2, 0.2, True), (40, 64, 8, 8, 0.01, True)])
 def test_leaky_relu_batchnorm_fused_vs_torch(B, C, H, W, alpha, affine):
     """Fused LeakyReLU + BatchNorm2d kernels vs torch fp32 (F.leaky_relu + F.batch_norm in training mode, the semantics of
     neunet/nn/layers/batchnorm2d.py:57-115 with ddof = 0 batch statistics), forward, running stats, dx / dw / db."""
