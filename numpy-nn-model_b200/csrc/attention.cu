@@ -8,9 +8,9 @@
 //
 // One CTA owns one (batch, head): Tq, Tk, D <= 64, so Q, K, V, the score tile and the gradients of one head
 // live in shared memory and the O(T^2) intermediates never travel to HBM (only `attn`, which the API
-// returns, is written). All arithmetic is fp32 FMA on the CUDA cores: per head the products are
-// 64 x 64 x 64 -- a 128-row tensor-core tile would be half padding and every operand would need its own
-// bf16 staging launch -- and the result is fp32-exact like the reference. The dropout mask is regenerated
+// returns, is written). The per-head products (64 x 64 x 64) are warp-level TF32 tensor-core MMAs with fp32
+// accumulation (see "tensor-core products" below: one product in bf16 mode, the hi/lo three-product split in
+// bf16x3 mode); masking, softmax, dropout and every sum are fp32. The dropout mask is regenerated
 // from its Philox ticket in backward (philox.cuh), indexed like the stand-alone kernel over the contiguous
 // (B, H, Tq, Tk) `attn` tensor. Outputs are written in (B, T, H, D) memory order -- the layout the
 // surrounding reshape/transpose views of the example expect, so no `.contiguous()` copy is ever made --
@@ -115,47 +115,6 @@ __device__ __forceinline__ void load_tile(float* dst, const float* p, long long 
     }
 }
 
-// acc[TM][TN] += sum_k A(m0 + i, k) * B(k, n0 + j); B is stored [k][n] (n contiguous, float4 reads);
-// A is stored [k][m] when A_KM (float4 reads) or [m][k] (scalar reads; a warp touches <= 4 distinct rows,
-// the rest is broadcast).
-// With the row-major A (scalar reads) a thread's TM rows are m0, m0 + RS, m0 + 2 RS, ...: RS = 8 makes the rows a warp
-// reads together ADJACENT (pitch 68 floats = 4 banks apart) instead of 8 rows apart (8 * 68 = 0 mod 32 banks: conflicts).
-template <int TM, int TN, bool A_KM, int RS = 1>
-__device__ __forceinline__ void tile_fma(float (&acc)[TM][TN], const float* __restrict__ A, const float* __restrict__ B,
-                                         int K, int m0, int n0) {
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        float a[TM], b[TN];
-        if (A_KM) {
-#pragma unroll
-            for (int i = 0; i < TM; i += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(A + k * LD + m0 + i);
-                a[i] = t4.x; a[i + 1] = t4.y; a[i + 2] = t4.z; a[i + 3] = t4.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = A[(m0 + i * RS) * LD + k];
-        }
-#pragma unroll
-        for (int j = 0; j < TN; j += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(B + k * LD + n0 + j);
-            b[j] = t4.x; b[j + 1] = t4.y; b[j + 2] = t4.z; b[j + 3] = t4.w;
-        }
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-}
-
-template <int TM, int TN>
-__device__ __forceinline__ void zero_acc(float (&acc)[TM][TN]) {
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-}
-
 // Reductions over the 16 lanes that own one row. The two half-warps of a warp own DIFFERENT rows and may diverge
 // (ragged Tq: one row live, the other padding), so each names only its own 16 lanes in the shuffle mask.
 __device__ __forceinline__ unsigned half_mask() { return (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu; }
@@ -195,272 +154,14 @@ __device__ __forceinline__ void softmax_row(float* Srow, int Tk, int l, float (&
     for (int j = 0; j < 4; ++j) p[j] *= inv;
 }
 
-// S[q][key] = (Q . K^T)[q][key] / scale, masked -> smem. 256 threads, 4 x 4 outputs each.
-__device__ __forceinline__ void scores_to_smem(const AttnArgs& a, const float* Qt, const float* Kt, float* S, int b, int h,
-                                               int tid) {
-    const int ty = tid >> 4, tx = tid & 15;
-    float acc[4][4];
-    zero_acc(acc);
-    tile_fma<4, 4, true>(acc, Qt, Kt, a.D, ty * 4, tx * 4);
-    __syncthreads();  // S re-uses Qt's storage: every thread must be done reading Q^T / K^T
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = ty * 4 + i;
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int key = tx * 4 + j;
-            float s = acc[i][j] / a.scale;
-            if (a.m.p != nullptr && q < a.Tq && key < a.Tk &&
-                masked(a.m, b * a.m.s[0] + h * a.m.s[1] + q * a.m.s[2] + key * a.m.s[3]))
-                s = a.m.fill;
-            o[j] = s;
-        }
-        *reinterpret_cast<float4*>(S + q * LD + tx * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256, 4) attn_fwd_kernel(const AttnArgs a, float* __restrict__ attn, float* __restrict__ out,
-                                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-    extern __shared__ __align__(16) float sm[];
-    float* Qt = sm;                 // [d][q]
-    float* Kt = Qt + T * LD;        // [d][key]
-    float* Vn = Kt + T * LD;        // [key][d]
-    float* S = Qt;                  // [q][key]  re-uses Q^T once the scores are in registers (3 tiles = 52 KB: 4 CTAs per SM)
-    float* Pt = Kt;                 // [key][q]  (post-dropout probabilities, A operand of P.V) re-uses K^T
-    pdl_trigger();
-    pdl_wait();
-    const int tid = threadIdx.x;
-    const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
-    {
-        const float* qp = a.q.p + b * a.q.s[0] + h * a.q.s[1];
-        const float* kp = a.kt.p + b * a.kt.s[0] + h * a.kt.s[1];
-        const float* vp = a.v.p + b * a.v.s[0] + h * a.v.s[1];
-        if (tile_vec_ok(qp, a.q.s[2], a.q.s[3], a.Tq, a.D) && tile_vec_ok(kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk) &&
-            tile_vec_ok(vp, a.v.s[2], a.v.s[3], a.Tk, a.D)) {
-            TileRegs rq, rk, rv;  // all twelve 16-byte loads of the thread are in flight together
-            tile_load(rq, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, tid);
-            tile_load(rk, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, tid);
-            tile_load(rv, vp, a.v.s[2], a.v.s[3], a.Tk, a.D, tid);
-            tile_store(rq, Qt, a.q.s[3], true, tid);
-            tile_store(rk, Kt, a.kt.s[3], false, tid);
-            tile_store(rv, Vn, a.v.s[3], false, tid);
-        } else {
-            load_tile(Qt, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, true, tid, 256);
-            load_tile(Kt, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, false, tid, 256);
-            load_tile(Vn, vp, a.v.s[2], a.v.s[3], a.Tk, a.D, false, tid, 256);
-        }
-    }
-    __syncthreads();
-    scores_to_smem(a, Qt, Kt, S, b, h, tid);
-    __syncthreads();
-    {
-        const uint64_t epoch = a.drop ? drop_epoch(a.d) : 0;
-        const int l = tid & 15;
-        for (int q = tid >> 4; q < T; q += 16) {
-            float p[4] = {0.f, 0.f, 0.f, 0.f};
-            if (q < a.Tq) {
-                softmax_row(S + q * LD, a.Tk, l, p);
-                if (4 * l < a.Tk) {
-                    const long long e = ((long long)bh * a.Tq + q) * a.Tk + 4 * l;
-                    if (a.drop) {
-                        uint32_t r[4];
-                        drop_words(a.d, epoch, e >> 2, r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) p[j] = r[j] >= a.d.thresh ? p[j] * a.d.scale : 0.f;
-                    }
-                    *reinterpret_cast<float4*>(attn + e) = make_float4(p[0], p[1], p[2], p[3]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) Pt[(4 * l + j) * LD + q] = p[j];
-        }
-    }
-    __syncthreads();
-    {
-        const int ty = tid >> 4, tx = tid & 15;
-        float acc[4][4];
-        zero_acc(acc);
-        tile_fma<4, 4, true>(acc, Pt, Vn, a.Tk, ty * 4, tx * 4);
-        const int dd = tx * 4;
-        if (dd < a.D) {
-            const long long hd = (long long)a.H * a.D;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int q = ty * 4 + i;
-                if (q >= a.Tq) continue;
-                const long long off = ((long long)b * a.Tq + q) * hd + (long long)h * a.D + dd;  // (B, Tq, H, D)
-                *reinterpret_cast<float4*>(out + off) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                if (out_hi != nullptr) {
-                    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        hi[j] = __float2bfloat16_rn(acc[i][j]);
-                        lo[j] = __float2bfloat16_rn(acc[i][j] - __bfloat162float(hi[j]));
-                    }
-                    *reinterpret_cast<uint2*>(out_hi + off) = *reinterpret_cast<const uint2*>(hi);
-                    if (out_lo != nullptr) *reinterpret_cast<uint2*>(out_lo + off) = *reinterpret_cast<const uint2*>(lo);
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------ backward
-// Recomputes S and P from q, k (no O(T^2) tensor is read back), then
-//   dPd = dO . V^T;  dP = dPd * mask / (1 - p);  dS = P * (dP - sum_key dP * P), 0 where masked, / scale
-//   dV = (P * mask / (1 - p))^T . dO;  dQ = dS . K;  dK = dS^T . Q
-// Teams of 64 threads (8 x 8 outputs each) run the independent products side by side.
-__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnArgs a, const AttnView dO, float* __restrict__ dQ,
-                                                       float* __restrict__ dK, float* __restrict__ dV, long long pitch) {
-    extern __shared__ __align__(16) float sm[];
-    float* Qt = sm;                  // [d][q]     A of S (k-major)
-    float* Qn = Qt + T * LD;         // [q][d]     B of dK
-    float* Kt = Qn + T * LD;         // [d][key]   B of S
-    float* Kn = Kt + T * LD;         // [key][d]   B of dQ
-    float* Vt = Kn + T * LD;         // [d][key]   B of dPd
-    float* dOn = Vt + T * LD;        // [q][d]     A of dPd (row-major), B of dV
-    float* P = Qt;                   // [q][key]   S -> P -> P*mask/(1-p); re-uses Q^T after phase 1 (6 tiles = 104 KB: 2 CTAs per SM)
-    float* dS = Kt;                  // [q][key]   dPd -> dS; re-uses K^T after phase 1
-    pdl_trigger();
-    pdl_wait();
-    const int tid = threadIdx.x;
-    const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
-    const float* qp = a.q.p + b * a.q.s[0] + h * a.q.s[1];
-    const float* kp = a.kt.p + b * a.kt.s[0] + h * a.kt.s[1];
-    {
-        const float* vp = a.v.p + b * a.v.s[0] + h * a.v.s[1];
-        const float* gp = dO.p + b * dO.s[0] + h * dO.s[1];
-        if (tile_vec_ok(qp, a.q.s[2], a.q.s[3], a.Tq, a.D) && tile_vec_ok(kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk) &&
-            tile_vec_ok(vp, a.v.s[2], a.v.s[3], a.Tk, a.D) && tile_vec_ok(gp, dO.s[2], dO.s[3], a.Tq, a.D)) {
-            TileRegs rq, rk, rv, rg;  // sixteen 16-byte loads per thread in flight, each matrix read from HBM once
-            tile_load(rq, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, tid);
-            tile_load(rk, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, tid);
-            tile_load(rv, vp, a.v.s[2], a.v.s[3], a.Tk, a.D, tid);
-            tile_load(rg, gp, dO.s[2], dO.s[3], a.Tq, a.D, tid);
-            tile_store(rq, Qt, a.q.s[3], true, tid);
-            tile_store(rq, Qn, a.q.s[3], false, tid);
-            tile_store(rk, Kt, a.kt.s[3], false, tid);
-            tile_store(rk, Kn, a.kt.s[3], true, tid);
-            tile_store(rv, Vt, a.v.s[3], true, tid);
-            tile_store(rg, dOn, dO.s[3], false, tid);
-        } else {
-            load_tile(Qt, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, true, tid, 256);
-            load_tile(Qn, qp, a.q.s[2], a.q.s[3], a.Tq, a.D, false, tid, 256);
-            load_tile(Kt, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, false, tid, 256);
-            load_tile(Kn, kp, a.kt.s[2], a.kt.s[3], a.D, a.Tk, true, tid, 256);
-            load_tile(Vt, vp, a.v.s[2], a.v.s[3], a.Tk, a.D, true, tid, 256);
-            load_tile(dOn, gp, dO.s[2], dO.s[3], a.Tq, a.D, false, tid, 256);
-        }
-    }
-    __syncthreads();
-    // phase 1: threads 0..127 -> S, threads 128..255 -> dPd  (8 x 4 outputs each)
-    {
-        const int t = tid & 127, tm = t >> 4, tn = t & 15;
-        float acc[8][4];
-        zero_acc(acc);
-        if (tid < 128) tile_fma<8, 4, true>(acc, Qt, Kt, a.D, tm * 8, tn * 4);
-        else tile_fma<8, 4, false, 8>(acc, dOn, Vt, a.D, tm, tn * 4);  // rows tm, tm + 8, ...
-        __syncthreads();  // P / dS re-use the Q^T / K^T tiles: all reads of phase 1 are done
-        if (tid < 128) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int q = tm * 8 + i;
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int key = tn * 4 + j;
-                    float s = acc[i][j] / a.scale;
-                    if (a.m.p != nullptr && q < a.Tq && key < a.Tk &&
-                        masked(a.m, b * a.m.s[0] + h * a.m.s[1] + q * a.m.s[2] + key * a.m.s[3]))
-                        s = a.m.fill;
-                    o[j] = s;
-                }
-                *reinterpret_cast<float4*>(P + q * LD + tn * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(dS + (tm + 8 * i) * LD + tn * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        }
-    }
-    __syncthreads();
-    // phase 2: rows
-    {
-        const uint64_t epoch = a.drop ? drop_epoch(a.d) : 0;
-        const int l = tid & 15;
-        for (int q = tid >> 4; q < T; q += 16) {
-            float p[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f}, pd[4] = {0.f, 0.f, 0.f, 0.f};
-            if (q < a.Tq) {
-                softmax_row(P + q * LD, a.Tk, l, p);
-                const float4 g4 = *reinterpret_cast<const float4*>(dS + q * LD + 4 * l);
-                float dp[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pd[j] = p[j];
-                if (a.drop && 4 * l < a.Tk) {
-                    uint32_t r[4];
-                    drop_words(a.d, epoch, (((long long)bh * a.Tq + q) * a.Tk + 4 * l) >> 2, r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool keep = r[j] >= a.d.thresh;
-                        dp[j] = keep ? dp[j] * a.d.scale : 0.f;
-                        pd[j] = keep ? p[j] * a.d.scale : 0.f;
-                    }
-                }
-                float t = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) t += (4 * l + j < a.Tk) ? dp[j] * p[j] : 0.f;
-                t = half_warp_sum(t);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int key = 4 * l + j;
-                    float v = (key < a.Tk) ? (dp[j] - t) * p[j] : 0.f;
-                    if (a.m.p != nullptr && key < a.Tk &&
-                        masked(a.m, b * a.m.s[0] + h * a.m.s[1] + q * a.m.s[2] + key * a.m.s[3]))
-                        v = 0.f;  // where(): masked scores receive no gradient
-                    ds[j] = v / a.scale;
-                }
-            }
-            *reinterpret_cast<float4*>(P + q * LD + 4 * l) = make_float4(pd[0], pd[1], pd[2], pd[3]);
-            *reinterpret_cast<float4*>(dS + q * LD + 4 * l) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-        }
-    }
-    __syncthreads();
-    // phase 3: team 0 -> dV = Pd^T . dO, team 1 -> dQ = dS . K, team 2 -> dK = dS^T . Q   (8 x 8 outputs each)
-    {
-        const int team = tid >> 6, t = tid & 63, tm = t >> 3, tn = t & 7;
-        if (team < 3) {
-            float acc[8][8];
-            zero_acc(acc);
-            float* dst;
-            int rows;
-            if (team == 0) { tile_fma<8, 8, true>(acc, P, dOn, a.Tq, tm * 8, tn * 8); dst = dV; rows = a.Tk; }
-            else if (team == 1) { tile_fma<8, 8, false, 8>(acc, dS, Kn, a.Tk, tm, tn * 8); dst = dQ; rows = a.Tq; }
-            else { tile_fma<8, 8, true>(acc, dS, Qn, a.Tq, tm * 8, tn * 8); dst = dK; rows = a.Tk; }
-            const long long hd = pitch;  // floats between consecutive (b, t) rows: H*D, or 3*H*D for a packed dq|dk|dv buffer
-            const int T_out = rows;  // (B, T_out, H, D) memory order
-            if (dst != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = team == 1 ? tm + 8 * i : tm * 8 + i;  // dQ's rows are interleaved (see tile_fma)
-                    if (r >= rows) continue;
-                    float* o = dst + ((long long)b * T_out + r) * hd + (long long)h * a.D + tn * 8;
-                    if (tn * 8 + 3 < a.D) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                    if (tn * 8 + 7 < a.D) *reinterpret_cast<float4*>(o + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------ tensor-core variant
-// The same two kernels with every 64 x 64 x 64 product on the tensor cores: warp-level mma.sync m16n8k8 (TF32 operands,
-// fp32 accumulate) straight from the fp32 shared-memory tiles. tcgen05 is the wrong tool at this size -- its M = 128
-// tile is half padding for one head and its operands must be staged in the UMMA shared-memory layout by TMA, i.e.
-// from bf16 planes no producer has -- while the warp-level path takes fragments from the tiles as they lie and
-// cuts the instruction stream ~9x against the FFMA micro-kernel above, which was issue-bound (ncu: 46 % issue slots busy,
-// 21.6 M warp instructions per forward launch). Precision follows the library's two modes: NNB_PREC_BF16 -> one TF32
+// ------------------------------------------------------------------------------------------ tensor-core products
+// Every 64 x 64 x 64 product runs on the tensor cores: warp-level mma.sync m16n8k8 (TF32 operands, fp32 accumulate)
+// straight from the fp32 shared-memory tiles. tcgen05 is the wrong tool at this size -- its M = 128 tile is half padding
+// for one head and its operands must be staged in the UMMA shared-memory layout by TMA, i.e. from bf16 planes no
+// producer has -- while the warp-level path takes fragments from the tiles as they lie. The first version of these
+// kernels did the products as fp32 FMAs on the CUDA cores and was issue-bound (ncu, profiles/r2_attention_ncu.md: 46 % issue
+// slots busy, 21.6 M warp instructions per forward launch, 92 us per backward launch); the MMA form halves the
+// instruction stream (10.8 M) and runs the backward in 36 us. Precision follows the library's two modes: NNB_PREC_BF16 -> one TF32
 // product (10-bit mantissa, tighter than the bf16 GEMMs around it), NNB_PREC_BF16X3 -> the same hi/lo split as the
 // GEMMs, x = hi + lo with hi = tf32(x), lo = tf32(x - hi), three products (lo*hi + hi*lo + hi*hi, ~1e-6 relative: fp32-grade).
 //
@@ -820,12 +521,6 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_mma_kernel(const AttnArgs a, 
     }
 }
 
-// NEUNET_B200_ATTN_SIMT=1 selects the fp32 CUDA-core kernels (diagnostics / A-B timing); read once.
-bool use_simt() {
-    static const bool on = [] { const char* e = getenv("NEUNET_B200_ATTN_SIMT"); return e && e[0] == '1'; }();
-    return on;
-}
-
 int fill_args(AttnArgs& a, const float* Q, const int64_t* qs, const float* KT, const int64_t* ks, const float* V,
               const int64_t* vs, const void* mask, int mask_kind, float mask_cmp, const int64_t* ms, float fill,
               float scale, float p, uint64_t seed, uint32_t call_id, uint64_t epoch, const uint64_t* epoch_dev,
@@ -883,16 +578,14 @@ int nnb_attention_forward(const float* Q, const int64_t q_strides[4], const floa
     }
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_attention_forward: bad prec");
     static bool configured = false;
-    const size_t smem_simt = (size_t)3 * T * LD * sizeof(float), smem_mma = (size_t)(2 * T * LD + T * LP) * sizeof(float) + T * 4 * sizeof(uint16_t);
+    const size_t smem_mma = (size_t)(2 * T * LD + T * LP) * sizeof(float) + T * 4 * sizeof(uint16_t);
     if (!configured) {
-        NNB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_simt));
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
         configured = true;
     }
     const dim3 grid((unsigned)(B * H));
-    if (use_simt()) NNB_CUDA_OK(launch_pdl(attn_fwd_kernel, grid, dim3(256), smem_simt, stream, a, attn, out, hi, lo));
-    else if (prec == NNB_PREC_BF16X3) NNB_CUDA_OK(launch_pdl(attn_fwd_mma_kernel<true>, grid, dim3(256), smem_mma, stream, a, attn, out, hi, lo));
+    if (prec == NNB_PREC_BF16X3) NNB_CUDA_OK(launch_pdl(attn_fwd_mma_kernel<true>, grid, dim3(256), smem_mma, stream, a, attn, out, hi, lo));
     else NNB_CUDA_OK(launch_pdl(attn_fwd_mma_kernel<false>, grid, dim3(256), smem_mma, stream, a, attn, out, hi, lo));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());
@@ -919,17 +612,15 @@ int nnb_attention_backward(const float* Q, const int64_t q_strides[4], const flo
     NNB_REQUIRE(prec == NNB_PREC_BF16 || prec == NNB_PREC_BF16X3, "nnb_attention_backward: bad prec");
     NNB_REQUIRE(out_row_pitch == 0 || (out_row_pitch >= H * D && out_row_pitch % 4 == 0), "nnb_attention_backward: bad out_row_pitch");
     static bool configured = false;
-    const size_t smem_simt = (size_t)6 * T * LD * sizeof(float), smem_mma = (size_t)(4 * T * LD + T * LP) * sizeof(float) + T * 4 * sizeof(uint16_t);
+    const size_t smem_mma = (size_t)(4 * T * LD + T * LP) * sizeof(float) + T * 4 * sizeof(uint16_t);
     if (!configured) {
-        NNB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_simt));
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
         NNB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
         configured = true;
     }
     const dim3 grid((unsigned)(B * H));
     const long long pitch = (long long)(out_row_pitch ? out_row_pitch : H * D);
-    if (use_simt()) NNB_CUDA_OK(launch_pdl(attn_bwd_kernel, grid, dim3(256), smem_simt, stream, a, g, dQ, dK, dV, pitch));
-    else if (prec == NNB_PREC_BF16X3) NNB_CUDA_OK(launch_pdl(attn_bwd_mma_kernel<true>, grid, dim3(256), smem_mma, stream, a, g, dQ, dK, dV, pitch));
+    if (prec == NNB_PREC_BF16X3) NNB_CUDA_OK(launch_pdl(attn_bwd_mma_kernel<true>, grid, dim3(256), smem_mma, stream, a, g, dQ, dK, dV, pitch));
     else NNB_CUDA_OK(launch_pdl(attn_bwd_mma_kernel<false>, grid, dim3(256), smem_mma, stream, a, g, dQ, dK, dV, pitch));
     count_launch();
     NNB_CUDA_OK(cudaGetLastError());

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time nnb_attention_forward / backward at the GPT-small shape (B=64, H=8, T=64, D=64: 512 heads per launch) with CUDA
-events over rotating operand sets larger than L2, in both precision modes. NEUNET_B200_ATTN_SIMT=1 in the environment
-times the fp32 CUDA-core kernels instead (A/B)."""
+events over rotating operand sets larger than L2, in both precision modes (host-paced: the number includes the
+allocations of the Python binding; the in-step figure is the ncu launch list under profiles/)."""
 import os
 import sys
 
@@ -43,7 +43,7 @@ def timed(fn, reps=5):
     return best
 
 
-kind = "simt" if os.environ.get("NEUNET_B200_ATTN_SIMT") == "1" else "mma"
+kind = "mma"
 for prec in ("bf16", "bf16x3"):
     with b200.precision(prec):
         f = timed(lambda i: b200.attention_forward(*views(i), mask, -1e9, scale, 0.1, ticket, want_planes=True))

@@ -33,6 +33,8 @@ def _setup():
     (64, 128, 128, 4, 3, 1, 1),    # 4 x 4 images: eight images per box
     (4, 128, 128, 32, 4, 2, 1),    # DDPM down-sample: strided boxes forward, zero-stuffed dgrad
     (3, 64, 64, 16, 3, 1, 1),      # ragged last box (B not a multiple of the images per box)
+    (2, 40, 48, 8, 3, 1, 1),       # channel counts that are not multiples of 64: ragged 64-channel layout tiles
+    (2, 72, 80, 12, 3, 1, 1),      # ... spanning two tiles; 12 x 12 maps (144 pixels: ragged 32-pixel tiles)
 ])
 def test_conv2d_implicit_gemm_vs_torch(prec, B, Cin, Cout, HW, k, s, p):
     b200 = _setup()
