@@ -68,6 +68,42 @@ def main():
         rm, rv = torch.zeros(1, 64, device="cuda"), torch.ones(1, 64, device="cuda")
         y, mean, inv = b200.bn_forward(x, torch.ones(64, device="cuda"), torch.zeros(64, device="cuda"), 0.01, 1e-5, 0.1, rm, rv)
         b200.bn_backward(x, torch.randn_like(x), mean, inv, torch.ones(64, device="cuda"), 0.01)
+        for shp in ((3, 16, 2, 2), (4, 8, 32, 32), (5, 6, 3, 3)):  # planes smaller / larger than a block, odd plane size
+            xb = torch.randn(*shp, device="cuda")
+            C = shp[1]
+            y, mean, inv = b200.bn_forward(xb, torch.ones(C, device="cuda"), torch.zeros(C, device="cuda"), 0.01, 1e-5, 0.1,
+                                           torch.zeros(1, C, device="cuda"), torch.ones(1, C, device="cuda"))
+            ref = torch.nn.functional.batch_norm(torch.nn.functional.leaky_relu(xb, 0.01), None, None, training=True, eps=1e-5)
+            assert (y - ref).abs().max().item() < 1e-4
+            b200.bn_backward(xb, torch.randn_like(xb), mean, inv, torch.ones(C, device="cuda"), 0.01)
+    # bf16 mode: the one-product instantiations of the attention kernels; swish + dropout pass; masked dO staging
+    with b200.precision("bf16"):
+        q = torch.randn(2, 33, 2, 32, device="cuda").permute(0, 2, 1, 3)
+        kv = torch.randn(2, 40, 2, 32, device="cuda").permute(0, 2, 1, 3)
+        cond = (torch.rand(2, 1, 33, 40, device="cuda") < 0.3).float()
+        out, attn, _ = b200.attention_forward(q, kv.permute(0, 1, 3, 2), kv, (cond, 1, 0.0), -1e9, 5.0, 0.2, (1, 2, 3, None))
+        b200.attention_backward(q, kv.permute(0, 1, 3, 2), kv, (cond, 1, 0.0), -1e9, 5.0, 0.2, (1, 2, 3, None), torch.randn_like(out))
+        z = torch.randn(3, 10, 24, device="cuda")
+        y, planes = b200.swish_dropout_apply(z, 1.0, 0.25, (4, 5, 6, None))
+        want = b200.dropout_apply(b200.swish_forward(z, 1.0), 0.25, (4, 5, 6, None))
+        assert (y - want).abs().max().item() < 1e-5
+        xl, wl, gl = torch.randn(30, 40, device="cuda"), torch.randn(24, 40, device="cuda"), torch.randn(30, 24, device="cuda")
+        b200.linear_backward(xl, wl, gl, z=z.reshape(30, 24), act=1, beta=1.0, grad_drop=(0.25, (4, 5, 6, None)))
+    # optimizer issued as ranges
+    from neunet.distributed import GradBucket
+    from neunet.optim import AdamW
+    lins = [nn.Linear(16, 24).to("cuda"), nn.Linear(24, 8).to("cuda")]
+    params = lins[0].parameters() + lins[1].parameters()
+    opt2, bucket = AdamW(params, lr=1e-2), GradBucket(params, chunk_bytes=1 << 10)
+    for t in range(3):
+        opt2.zero_grad()
+        h = neunet.tensor(np.random.randn(4, 16).astype(np.float32), device="cuda")
+        for l in lins:
+            h = l(h)
+        (h * h).sum().backward()
+        bucket.all_reduce_and_step(opt2)
+        if t == 0:
+            bucket.overlap_backward()
     torch.cuda.synchronize()
     print("sanitize_small ok")
 
