@@ -42,7 +42,7 @@ def main():
     print("Instruction counts per kernel from `cuobjdump -sass`. UTCHMMA = tcgen05.mma (`.2CTA` = cta_group::2 pairs), LDTM = "
           "tcgen05.ld (TMEM -> registers), UTMALDG / UTMASTG = TMA tensor loads / stores (cp.async.bulk.tensor), UTCBAR = "
           "tcgen05.commit -> mbarrier, SYNCS = mbarrier ops, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents "
-          "(programmatic dependent launch). No HMMA (mma.sync) anywhere: every contraction on the tensor path is tcgen05.\n")
+          "(programmatic dependent launch). HMMA (mma.sync; here HMMA.1688.F32.TF32) appears only in the fused attention kernels, whose 64 x 64 x 64 per-head products are too small for a 128-row tcgen05 tile; every other contraction on the tensor path is tcgen05.\n")
     print("| kernel | " + " | ".join(PATS) + " |")
     print("|---|" + "---|" * len(PATS))
     tot = collections.Counter()
