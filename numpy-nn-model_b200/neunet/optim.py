@@ -133,3 +133,18 @@ class SGD:
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+
+
+_OUT_OF_SCOPE = frozenset({"Momentum", "RMSprop", "Adagrad", "Adadelta", "Adamax", "NAdam"})
+
+
+class _OutOfScope(NotImplementedError, AttributeError):
+    """Also an AttributeError, so ``hasattr`` / ``getattr(..., default)`` keep working."""
+
+
+def __getattr__(name):
+    if name in _OUT_OF_SCOPE:
+        raise _OutOfScope(
+            f"neunet.optim.{name} exists in the reference (neunet/optim.py) but is outside the hot path this package implements "
+            "(SGD, Adam, AdamW; DESIGN.md section 8).")
+    raise AttributeError(f"module 'neunet.optim' has no attribute {name!r}")

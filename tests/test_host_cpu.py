@@ -269,3 +269,15 @@ def test_cuda_without_device_fails_loudly():
         pytest.skip("needs a machine without a GPU")
     with pytest.raises(RuntimeError):
         neunet.tensor([1.0], device="cuda")
+
+
+def test_reference_names_outside_the_scope_say_so():
+    import neunet.nn as nn
+    import neunet.optim as optim
+    with pytest.raises(NotImplementedError, match="outside the hot path"):
+        nn.LSTM
+    with pytest.raises(NotImplementedError, match="outside the hot path"):
+        optim.NAdam
+    with pytest.raises(AttributeError):
+        nn.NoSuchLayer
+    assert hasattr(nn, "Linear") and not hasattr(nn, "NoSuchLayer") and not hasattr(nn, "GRU")
