@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Launch every nn.Linear GEMM class of the GPT-small step (4 layer shapes x fwd/dgrad/wgrad, M = B*T)
+"""Launch every nn.Linear GEMM class of the GPT-small step (5 layer shapes x fwd/dgrad/wgrad, M = B*T; q/k/v as one GEMM)
 a few times through nnb_probe_linear_gemm, for an ncu pass that collects DRAM bytes per launch:
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
@@ -20,7 +20,8 @@ b200.set_precision("bf16")
 c = bench.GPT
 M = c["batch"] * c["seq"]
 d, ff, V, L = c["d_model"], c["d_ff"], c["vocab"], c["layers"]
-for K, N, n, name in [(d, d, 4 * L, "wq/wk/wv/fc"), (d, ff, L, "ffn.fc_1"), (ff, d, L, "ffn.fc_2"), (d, V, 1, "fc_out")]:
+for K, N, n, name in [(d, 3 * d, L, "wq|wk|wv (one GEMM)"), (d, d, L, "attn.fc"), (d, ff, L, "ffn.fc_1"), (ff, d, L, "ffn.fc_2"),
+                      (d, V, 1, "fc_out")]:  # = bench.GptWorkload.linear_shapes() with fusion on
     for form, fname in enumerate(("fwd", "dgrad", "wgrad")):
         us, nl = b200.probe_linear_gemm(M, K, N, form=form, with_bias=(form == 0), rounds=1, sets=1)
         print(f"class {name} {fname} M={M} K={K} N={N} per_step={n} kernels_per_gemm={nl} us={us:.2f}", flush=True)
