@@ -28,12 +28,15 @@ def _make(seed=0):
     return nn.Linear(12, 8), nn.Linear(8, 4)
 
 
-def _step(l1, l2, opt, x, y, bucket=None):
+def _step(l1, l2, opt, x, y, bucket=None, combined=False):
     import neunet
     import neunet.nn as nn
     opt.zero_grad()
     loss = nn.CrossEntropyLoss()(l2(nn.Swish()(l1(neunet.tensor(x)))), neunet.tensor(y, dtype=np.int32))
     loss.backward()
+    if bucket is not None and combined:
+        bucket.all_reduce_and_step(opt)  # on CPU: falls back to all_reduce() + step() (the chunk-wise optimizer is a device path)
+        return float(loss.data)
     if bucket is not None:
         bucket.all_reduce()
     opt.step()
@@ -56,7 +59,7 @@ def _worker(rank, world, port, xs, ys, out, overlap=False):
     opt = AdamW(params, lr=1e-2)
     opt.grad_scale = 1.0 / world
     for t in range(3):
-        _step(l1, l2, opt, xs[rank], ys[rank], bucket)
+        _step(l1, l2, opt, xs[rank], ys[rank], bucket, combined=(t == 2))
         if overlap and t == 0:
             bucket.overlap_backward()   # chunks reduced from Tensor.backward's ready-hooks from now on
             assert len(bucket._chunks) >= 2

@@ -192,3 +192,34 @@ def test_api_surface_and_ddpm_unet_on_the_mocked_device_match_the_reference_gold
         assert test_models._rel(pred.data, g["out"]) < 5e-5
         test_models._check_grads_and_params(du, g, 5e-4, after=False)
         assert "bn_forward_lrelu" in mock_b200.calls  # LeakyReLU was absorbed by the BatchNorm kernels
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_parked_dropout_gradient_with_a_second_consumer_of_the_linear_result(order):
+    """The backward of an nn.Dropout on an nn.Linear result is left to that Linear's dO staging (autograd._MaskedGrad). If the
+    Linear result has ANOTHER consumer, its contribution must be added to the MASKED gradient, whichever arrives first."""
+    with mock_b200.mocked():
+        import neunet
+        import neunet.nn as nn
+        from neunet import autograd, b200
+        np.random.seed(1)
+        lin, drop = nn.Linear(8, 16).to("cuda"), nn.Dropout(0.5)
+        xv = np.random.randn(6, 8).astype(np.float32)
+        res = {}
+        for fuse in (True, False):
+            prev = autograd.set_fusion(fuse)
+            try:
+                b200.manual_seed(3)
+                b200._mock_reset_rng()
+                mock_b200.calls.clear()
+                lin.weight.grad = lin.bias.grad = None
+                x = neunet.tensor(xv, device="cuda", requires_grad=True)
+                h = lin(x)
+                a, b = drop(h) * 3.0, h * h
+                loss = (a.sum() + b.sum()) if order == 0 else (b.sum() + a.sum())
+                loss.backward()
+                res[fuse] = [mock_b200.to_np(t).copy() for t in (x.grad, lin.weight.grad, lin.bias.grad, h.grad)]
+            finally:
+                autograd.set_fusion(prev)
+        for got, want in zip(res[True], res[False]):
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
